@@ -1,0 +1,170 @@
+/*
+ * sae_b200.h — C ABI of the B200-native Swapping-Autoencoder conv hot path.
+ *
+ * Every entry point takes raw DEVICE pointers to fp32 data, explicit sizes and a
+ * cudaStream_t (passed as void*); nothing is allocated inside, nothing depends on
+ * torch.  Return value: 0 on success, a negative SAE_E_* code otherwise;
+ * sae_last_error() returns a thread-local human-readable message for the last
+ * failure.  All entry points are re-entrant (no global mutable state apart from a
+ * per-device attribute cache guarded by std::call_once).
+ *
+ * Activation layout: NHWC ("[major, H, W, minor]" in the reference's own native
+ * signature, reference/models/networks/stylegan2_op/upfirdn2d.cpp:12-23, called
+ * here with major = batch, minor = channels instead of major = B*C, minor = 1).
+ * Weight layout for the conv entry points: [Cout, R, S, Cin] ("KRSC").
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to
+ * the reference checkout, taesungp/swapping-autoencoder-pytorch @ 6baa180).
+ */
+#ifndef SAE_B200_H_
+#define SAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAE_OK              0
+#define SAE_E_INVALID      -1   /* bad argument (shape / alignment / unsupported combination) */
+#define SAE_E_CUDA         -2   /* a CUDA runtime / driver call or the launch itself failed */
+#define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
+
+/* ABI version of this header; bumped on any signature change. */
+#define SAE_ABI_VERSION 3
+int         sae_abi_version(void);
+const char* sae_last_error(void);
+/* number of kernels launched by this library in the calling process since load
+ * (monotonic, relaxed atomic) — bench.py reports the delta as "gpu_launches". */
+int64_t     sae_launch_count(void);
+/* 1 when the tcgen05/TMA conv path is usable on the current device (sm_100 + driver entry points) */
+int         sae_tcgen05_available(void);
+
+/* ------------------------------------------------------------------------------------------
+ * upfirdn2d — zero-insert upsample, pad / crop, 2-D FIR (true convolution: taps read flipped),
+ * decimate.  Replaces  upfirdn2d_op.upfirdn2d(input[major,H,W,minor], kernel[kh,kw], up_x, up_y,
+ * down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+ *   (models/networks/stylegan2_op/upfirdn2d.cpp:12-23, upfirdn2d_kernel.cu:140-271).
+ * out is [major, out_h, out_w, minor] with out_h = (in_h*up_y + pad_y0 + pad_y1 - kh)/down_y + 1
+ * (upfirdn2d.py:108-109).  Unlike the reference there is no mode table: every
+ * (up, down, kh, kw <= 32) combination is handled by the same kernel.  Negative pads crop.
+ * 64-bit indexing throughout (the reference overflows int32 at >= 2^31 elements).
+ * ------------------------------------------------------------------------------------------ */
+int sae_upfirdn2d(const float* input, const float* kernel, float* out,
+                  int64_t major, int in_h, int in_w, int minor,
+                  int kernel_h, int kernel_w,
+                  int up_x, int up_y, int down_x, int down_y,
+                  int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * fused_bias_act — out = act(x + b[(i / step_b) % size_b]) * scale.
+ * Replaces  fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *   (models/networks/stylegan2_op/fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:19-99).
+ * act: 1 = linear, 3 = leaky-relu(alpha);  grad: 0 = forward, 1 = first-derivative form (masked
+ * by sign of ref = saved OUTPUT), 2 = second derivative (zero).  bias == NULL / ref == NULL mean
+ * "empty tensor" exactly as numel()==0 does in the reference.
+ * noise/noise_weight (extension, NULL to disable): adds noise_weight[0] * noise[i / noise_div]
+ * before the activation — NoiseInjection (stylegan2_layers.py:328-351) folded into the same pass.
+ * ------------------------------------------------------------------------------------------ */
+int sae_fused_bias_act(const float* x, const float* bias, const float* ref, float* out,
+                       int64_t size_x, int64_t step_b, int size_b,
+                       int act, int grad, float alpha, float scale,
+                       const float* noise, const float* noise_weight, int64_t noise_div,
+                       void* stream);
+
+/* Backward of the above in one pass: grad_in = grad_out * (out > 0 ? 1 : alpha) * scale and,
+ * fused, grad_bias[c] += sum over everything but the bias dim (the reference runs a separate
+ * .sum() kernel, fused_act.py:32-41).  grad_bias must be zero-initialised by the caller (or hold
+ * a value to accumulate into).  Optional: noise != NULL accumulates d/d(noise_weight) =
+ * sum(grad_in * noise) into grad_noise_weight[0].  Layout restriction: step_b == 1 (channels
+ * innermost, i.e. NHWC or [B, C]). */
+int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_in, float* grad_bias,
+                          int64_t size_x, int size_b, float alpha, float scale,
+                          const float* noise, int64_t noise_div, float* grad_noise_weight,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * modulate — x_s[n,h,w,c] = x[n,h,w,c] * s[n,c]: the "input * style" step of
+ * ModulatedConv2d.forward with new_demodulation (stylegan2_layers.py:278-284).
+ * backward: dx = dy * s;  ds[n,c] = sum_hw dy * x  (ds must be zero-initialised).
+ * round_tf32 != 0 rounds the result to TF32 (round-to-nearest) so the tensor-core conv that
+ * consumes it sees exactly-representable operands.
+ * ------------------------------------------------------------------------------------------ */
+int sae_modulate(const float* x, const float* s, float* out,
+                 int n, int64_t hw, int c, int round_tf32, void* stream);
+int sae_modulate_backward(const float* dy, const float* x, const float* s, float* dx, float* ds,
+                          int n, int64_t hw, int c, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * conv2d — dense implicit-GEMM convolution family on NHWC fp32 activations, TF32 tensor cores,
+ * fp32 accumulate.  Replaces the F.conv2d / F.conv_transpose2d call sites of
+ * EqualConv2d.forward (stylegan2_layers.py:136-142), EqualLinear.forward (:174-186, H=W=1) and
+ * ModulatedConv2d.forward (:299-323; the groups=batch grouped conv there uses identical weights
+ * for every sample — SURVEY.md §0.1 — so it is one dense conv on the style-scaled input).
+ *
+ * Geometry (one struct for the three directions of the same convolution):
+ *   y[n,p,q,o] = sum_{r,s,c} x[n, p*stride - pad_t + r, q*stride - pad_l + s, c] * w[o,r,s,c]
+ *   x: [N, H, W, C]   w: [K, R, S, C]   y: [N, P, Q, K]
+ * fprop computes y from (x, w); dgrad computes x-gradient from (dy, w) — and is also the forward
+ * of the stride-2 transposed convolution in the generator's upsampling path (:306);
+ * wgrad computes w-gradient from (dy, x).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sae_conv_geom {
+    int32_t N, H, W, C;      /* input  activation  [N,H,W,C]              */
+    int32_t K, R, S;         /* filter             [K,R,S,C]              */
+    int32_t P, Q;            /* output activation  [N,P,Q,K]              */
+    int32_t stride;          /* same in y and x                           */
+    int32_t pad_t, pad_l;    /* top / left zero padding (bottom/right implied by P,Q) */
+} sae_conv_geom;
+
+/* Optional fused epilogue for fprop / dgrad (all pointers may be NULL):
+ *   v = acc
+ *   v += bias[col]                                   (EqualConv2d bias, stylegan2_layers.py:139)
+ *   v += noise_weight[0] * noise[pixel]              (NoiseInjection, :351)
+ *   if act == 3: v = (v > 0 ? v : alpha * v) * gain  (FusedLeakyReLU, fused_act.py:89-96)
+ *   else       : v = v * gain
+ *   if residual: v = (v + residual[pixel, col]) * res_scale   (ResBlock (out+skip)/sqrt2, :691)
+ *   if round_tf32: v = rna_tf32(v)
+ */
+typedef struct sae_conv_epilogue {
+    const float* bias;
+    const float* noise;
+    const float* noise_weight;
+    const float* residual;
+    float   alpha;
+    float   gain;
+    float   res_scale;
+    int32_t act;           /* 1 = linear, 3 = leaky relu */
+    int32_t round_tf32;
+} sae_conv_epilogue;
+
+/* impl: 0 = auto (tcgen05/TMA kernel when the shape qualifies, otherwise the generic
+ * mma.sync kernel), 1 = force generic, 2 = force tcgen05 (SAE_E_UNSUPPORTED if not eligible). */
+int sae_conv2d_fprop(const float* x, const float* w, float* y, const sae_conv_geom* g,
+                     const sae_conv_epilogue* epi, int impl, void* stream);
+/* wt is the filter pre-transposed to [C, R, S, K] (host side does the tiny permute). */
+int sae_conv2d_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g,
+                     const sae_conv_epilogue* epi, int impl, void* stream);
+/* dw [K,R,S,C] is ACCUMULATED into (split-K reduction with fp32 atomics): zero it first. */
+int sae_conv2d_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
+                     int impl, void* stream);
+
+/* Which kernel `impl = 0` would pick for this geometry: 1 generic, 2 tcgen05. dir: 0 fprop, 1 dgrad, 2 wgrad */
+int sae_conv2d_query_impl(const sae_conv_geom* g, int dir);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange helpers: pack the active parameter group's
+ * gradients into one flat fp32 bucket for a single NCCL all-reduce, then unpack scaled by 1/world.
+ * Replaces nn.DataParallel's ReduceAddCoalesced onto GPU 0 (models/__init__.py:80).
+ * ptrs: device array of n pointers; sizes / offsets: device arrays of n int64 (elements).
+ * ------------------------------------------------------------------------------------------ */
+int sae_bucket_pack(const float* const* ptrs, const int64_t* offsets, const int64_t* sizes, int n,
+                    float* bucket, int64_t total, void* stream);
+int sae_bucket_unpack(float* const* ptrs, const int64_t* offsets, const int64_t* sizes, int n,
+                      const float* bucket, int64_t total, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SAE_B200_H_ */

@@ -1,0 +1,195 @@
+"""Tensor-level entry points of the hot path: thin wrappers that allocate outputs with torch and pass raw
+device pointers + the current CUDA stream to the C ABI (include/sae_b200.h).
+
+All activations here are *physical* NHWC: contiguous ``[N, H, W, C]`` (or ``[B, C]``) fp32 CUDA tensors.
+The autograd layer in ``stylegan2_op`` converts from / to the logical NCHW shapes the reference's modules
+expose.  ``set_kernels`` lets the CPU test-suite swap in an emulation built on the oracle so the host-side
+autograd logic can be grad-checked without a GPU; the product never does that — ``CudaKernels`` raises if
+the shared library is missing or a tensor lives on the CPU.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvEpilogue, ConvGeom, check
+
+
+def make_geom(N, H, W, C, K, R, S, stride, pad_t, pad_l, P=None, Q=None):
+    """Geometry of y[n,p,q,k] = sum x[n, p*stride - pad_t + r, q*stride - pad_l + s, c] w[k,r,s,c].
+    P/Q default to the F.conv2d rule with symmetric padding (pad_t on both sides)."""
+    if P is None:
+        P = (H + 2 * pad_t - R) // stride + 1
+    if Q is None:
+        Q = (W + 2 * pad_l - S) // stride + 1
+    return ConvGeom(N, H, W, C, K, R, S, P, Q, stride, pad_t, pad_l)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.SaeError("sae_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU fallback"
+                                % t.device.type)
+        if t.dtype != torch.float32:
+            raise _lib.SaeError("sae_b200 kernels are fp32-only (got %s)" % t.dtype)
+        if not t.is_contiguous():
+            raise _lib.SaeError("sae_b200 kernels need contiguous NHWC storage")
+
+
+class CudaKernels:
+    """The product path: every method is one (or two) launches of hand-written sm_100a kernels."""
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.conv_impl = 0       # 0 auto, 1 force generic (mma.sync), 2 force tcgen05
+        self.round_tf32 = True   # producers round to TF32 so the tensor-core truncation is exact
+
+    # ------------------------------------------------------------------ FIR
+    def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+        _need_cuda(x, kernel)
+        n, h, w, c = x.shape
+        kh, kw = kernel.shape
+        oh = (h * up_y + pad_y0 + pad_y1 - kh) // down_y + 1
+        ow = (w * up_x + pad_x0 + pad_x1 - kw) // down_x + 1
+        out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_upfirdn2d(_ptr(x), _ptr(kernel), _ptr(out), n, h, w, c, kh, kw, up_x, up_y,
+                                         down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, _stream()), "sae_upfirdn2d")
+        return out
+
+    # ------------------------------------------------------------- bias/act
+    def bias_act(self, x, bias, ref, act, grad, alpha, scale, noise=None, noise_weight=None):
+        """x: [..., C] channels innermost.  noise: one value per pixel (numel = x.numel() / C)."""
+        _need_cuda(x, bias, ref, noise, noise_weight)
+        out = torch.empty_like(x)
+        c = x.shape[-1]
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_fused_bias_act(_ptr(x), _ptr(bias), _ptr(ref), _ptr(out), x.numel(), 1,
+                                              bias.numel() if bias is not None else 1, act, grad, alpha, scale,
+                                              _ptr(noise), _ptr(noise_weight), c, _stream()), "sae_fused_bias_act")
+        return out
+
+    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None):
+        _need_cuda(grad_out, out, noise)
+        c = out.shape[-1]
+        gi = torch.empty_like(out)
+        gb = torch.zeros(c, device=out.device, dtype=out.dtype) if want_bias else None
+        gnw = torch.zeros(1, device=out.device, dtype=out.dtype) if noise is not None else None
+        with torch.cuda.device(out.device):
+            check(self.lib.sae_bias_act_backward(_ptr(grad_out), _ptr(out), _ptr(gi), _ptr(gb), out.numel(), c,
+                                                 alpha, scale, _ptr(noise), c, _ptr(gnw), _stream()),
+                  "sae_bias_act_backward")
+        return gi, gb, gnw
+
+    # ------------------------------------------------------------- modulate
+    def modulate(self, x, s):
+        _need_cuda(x, s)
+        n, h, w, c = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_modulate(_ptr(x), _ptr(s), _ptr(out), n, h * w, c, int(self.round_tf32), _stream()),
+                  "sae_modulate")
+        return out
+
+    def modulate_backward(self, dy, x, s):
+        _need_cuda(dy, x, s)
+        n, h, w, c = x.shape
+        dx = torch.empty_like(x)
+        ds = torch.zeros_like(s)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_modulate_backward(_ptr(dy), _ptr(x), _ptr(s), _ptr(dx), _ptr(ds), n, h * w, c,
+                                                 _stream()), "sae_modulate_backward")
+        return dx, ds
+
+    # ----------------------------------------------------------------- conv
+    def _epi(self, bias=None, act=1, alpha=0.2, gain=1.0, noise=None, noise_weight=None, residual=None,
+             res_scale=1.0, round_tf32=None):
+        _need_cuda(bias, noise, noise_weight, residual)
+        e = ConvEpilogue()
+        e.bias = bias.data_ptr() if bias is not None else None
+        e.noise = noise.data_ptr() if noise is not None else None
+        e.noise_weight = noise_weight.data_ptr() if noise_weight is not None else None
+        e.residual = residual.data_ptr() if residual is not None else None
+        e.alpha, e.gain, e.res_scale, e.act = alpha, gain, res_scale, act
+        e.round_tf32 = int(self.round_tf32 if round_tf32 is None else round_tf32)
+        return e
+
+    def conv_fprop(self, x, w_krsc, g, **epi):
+        """x [N,H,W,C], w [K,R,S,C] -> y [N,P,Q,K]"""
+        _need_cuda(x, w_krsc)
+        assert tuple(x.shape) == (g.N, g.H, g.W, g.C) and tuple(w_krsc.shape) == (g.K, g.R, g.S, g.C), \
+            (tuple(x.shape), tuple(w_krsc.shape), g.key())
+        y = torch.empty((g.N, g.P, g.Q, g.K), device=x.device, dtype=x.dtype)
+        e = self._epi(**epi)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_conv2d_fprop(_ptr(x), _ptr(w_krsc), _ptr(y), ctypes.byref(g), ctypes.byref(e),
+                                            self.conv_impl, _stream()), "sae_conv2d_fprop")
+        return y
+
+    def conv_dgrad(self, dy, w_krsc, g, **epi):
+        """dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C] (also the forward of the transposed convolution)."""
+        _need_cuda(dy, w_krsc)
+        assert tuple(dy.shape) == (g.N, g.P, g.Q, g.K) and tuple(w_krsc.shape) == (g.K, g.R, g.S, g.C), \
+            (tuple(dy.shape), tuple(w_krsc.shape), g.key())
+        wt = w_krsc.permute(3, 1, 2, 0).contiguous()      # [C,R,S,K]: tiny, stays in L2
+        dx = torch.empty((g.N, g.H, g.W, g.C), device=dy.device, dtype=dy.dtype)
+        e = self._epi(**epi)
+        with torch.cuda.device(dy.device):
+            check(self.lib.sae_conv2d_dgrad(_ptr(dy), _ptr(wt), _ptr(dx), ctypes.byref(g), ctypes.byref(e),
+                                            self.conv_impl, _stream()), "sae_conv2d_dgrad")
+        return dx
+
+    def conv_wgrad(self, dy, x, g):
+        """dy [N,P,Q,K], x [N,H,W,C] -> dw [K,R,S,C]"""
+        _need_cuda(dy, x)
+        assert tuple(dy.shape) == (g.N, g.P, g.Q, g.K) and tuple(x.shape) == (g.N, g.H, g.W, g.C), \
+            (tuple(dy.shape), tuple(x.shape), g.key())
+        dw = torch.zeros((g.K, g.R, g.S, g.C), device=dy.device, dtype=dy.dtype)
+        with torch.cuda.device(dy.device):
+            check(self.lib.sae_conv2d_wgrad(_ptr(dy), _ptr(x), _ptr(dw), ctypes.byref(g), self.conv_impl, _stream()),
+                  "sae_conv2d_wgrad")
+        return dw
+
+    def conv_impl_for(self, g, direction):
+        return int(self.lib.sae_conv2d_query_impl(ctypes.byref(g), direction))
+
+    # --------------------------------------------------------------- bucket
+    def bucket_pack(self, ptrs, offsets, sizes, n, bucket):
+        with torch.cuda.device(bucket.device):
+            check(self.lib.sae_bucket_pack(_ptr(ptrs), _ptr(offsets), _ptr(sizes), n, _ptr(bucket), bucket.numel(),
+                                           _stream()), "sae_bucket_pack")
+
+    def bucket_unpack(self, ptrs, offsets, sizes, n, bucket, scale):
+        with torch.cuda.device(bucket.device):
+            check(self.lib.sae_bucket_unpack(_ptr(ptrs), _ptr(offsets), _ptr(sizes), n, _ptr(bucket), bucket.numel(),
+                                             scale, _stream()), "sae_bucket_unpack")
+
+
+_kernels = None
+
+
+def kernels():
+    """The active kernel set; instantiates ``CudaKernels`` (loading the .so) on first use."""
+    global _kernels
+    if _kernels is None:
+        _kernels = CudaKernels()
+    return _kernels
+
+
+def set_kernels(k):
+    """Test hook (tests/ only): install an object with the ``CudaKernels`` interface."""
+    global _kernels
+    prev = _kernels
+    _kernels = k
+    return prev

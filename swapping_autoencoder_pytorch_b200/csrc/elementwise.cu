@@ -1,0 +1,355 @@
+// HBM-bound pointwise kernels: fused bias + (noise) + leaky-relu forward / backward (with the
+// bias-gradient reduction fused in), style modulation forward / backward, gradient bucket
+// pack / unpack.  Replaces models/networks/stylegan2_op/fused_bias_act_kernel.cu:19-99 and the
+// unfused ATen elementwise kernels listed in SURVEY.md §2.1.
+// All kernels: float4 accesses when the channel count allows, grid = multiple of the SM count,
+// 64-bit indexing.
+#include "common.cuh"
+
+namespace sae {
+
+static inline unsigned grid_for(int64_t work_items, int threads, int per_sm = 8) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+// ----------------------------------------------------------------------------- bias_act forward
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ ref,
+                float* __restrict__ out, int64_t size_v, int64_t step_b, int size_b,
+                int act, int grad, float alpha, float scale,
+                const float* __restrict__ noise, const float* __restrict__ noise_weight, int64_t noise_div) {
+    const float nw = noise ? __ldg(noise_weight) : 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < size_v;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float v[VEC], r[VEC];
+        const int64_t e0 = i * VEC;
+        if (VEC == 4) {
+            float4 t = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+            v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+            if (ref) {
+                float4 q = ldg_stream(reinterpret_cast<const float4*>(ref) + i);
+                r[0] = q.x; r[1 % VEC] = q.y; r[2 % VEC] = q.z; r[3 % VEC] = q.w;
+            }
+        } else {
+            v[0] = x[e0];
+            if (ref) r[0] = ref[e0];
+        }
+        float nz = 0.f;
+        if (noise) nz = nw * __ldg(noise + e0 / noise_div);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float t = v[j];
+            if (b) t += __ldg(b + (int)(((e0 + j) / step_b) % size_b));
+            t += nz;
+            float y;
+            if (act == 3) {
+                if (grad == 0)      y = (t > 0.f) ? t : t * alpha;
+                else if (grad == 1) y = ((ref ? r[j] : 0.f) > 0.f) ? t : t * alpha;
+                else                y = 0.f;
+            } else {
+                y = (grad == 2) ? 0.f : t;
+            }
+            v[j] = y * scale;
+        }
+        if (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+        else out[e0] = v[0];
+    }
+}
+
+// ---------------------------------------------------------------------------- bias_act backward
+// grad_in = grad_out * mask(out) * scale; grad_bias[c] += sum(grad_in); channels innermost.
+// Every thread keeps a fixed channel group across its grid-stride loop (stride is a multiple of
+// the number of channel groups), accumulates in registers, then one shared-memory reduction and
+// one global atomic per channel per CTA.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bias_act_bwd_kernel(const float* __restrict__ go, const float* __restrict__ outp, float* __restrict__ gi,
+                    float* __restrict__ gb, int64_t size_v, int cv, int64_t stride_v,
+                    float alpha, float scale,
+                    const float* __restrict__ noise, int64_t noise_div, float* __restrict__ gnw) {
+    extern __shared__ float sacc[];   // [cv * VEC] (+1 slot for the noise-weight grad)
+    const int C = cv * VEC;
+    for (int i = threadIdx.x; i <= C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    float bsum[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) bsum[j] = 0.f;
+    float nsum = 0.f;
+    if (tid < stride_v) {
+        for (int64_t i = tid; i < size_v; i += stride_v) {
+            float g[VEC], o[VEC];
+            if (VEC == 4) {
+                float4 t = ldg_stream(reinterpret_cast<const float4*>(go) + i);
+                float4 q = ldg_stream(reinterpret_cast<const float4*>(outp) + i);
+                g[0] = t.x; g[1 % VEC] = t.y; g[2 % VEC] = t.z; g[3 % VEC] = t.w;
+                o[0] = q.x; o[1 % VEC] = q.y; o[2 % VEC] = q.z; o[3 % VEC] = q.w;
+            } else {
+                g[0] = go[i]; o[0] = outp[i];
+            }
+            float lsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float y = ((o[j] > 0.f) ? g[j] : g[j] * alpha) * scale;
+                g[j] = y;
+                bsum[j] += y;
+                lsum += y;
+            }
+            if (noise) nsum = fmaf(lsum, __ldg(noise + (i * VEC) / noise_div), nsum);
+            if (VEC == 4) reinterpret_cast<float4*>(gi)[i] = make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]);
+            else gi[i] = g[0];
+        }
+        if (gb) {
+            const int c0 = (int)(tid % cv) * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) atomicAdd(&sacc[c0 + j], bsum[j]);
+        }
+    }
+    if (noise) {
+        nsum = warp_sum(nsum);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[C], nsum);
+    }
+    __syncthreads();
+    if (gb)
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            float v = sacc[i];
+            if (v != 0.f) atomicAdd(gb + i, v);
+        }
+    if (noise && threadIdx.x == 0) atomicAdd(gnw, sacc[C]);
+}
+
+// ------------------------------------------------------------------------------------ modulate
+__global__ void __launch_bounds__(256)
+modulate_kernel(const float4* __restrict__ x, const float4* __restrict__ s, float4* __restrict__ out,
+                int64_t total_v, int64_t hw, int cv, int round_tf32) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_v;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv);
+        int64_t n = (i / cv) / hw;
+        float4 v = ldg_stream(x + i);
+        float4 m = __ldg(s + n * cv + c);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+        if (round_tf32) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+modulate_scalar_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ out,
+                       int64_t total, int64_t hw, int c, int round_tf32) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int ch = (int)(i % c);
+        int64_t n = (i / c) / hw;
+        float v = x[i] * __ldg(s + n * c + ch);
+        out[i] = round_tf32 ? rna_tf32(v) : v;
+    }
+}
+
+// dx = dy * s;  ds[n, c] += sum_hw dy * x.   grid = (chunks, N); each CTA covers a pixel range of one
+// sample; thread keeps a fixed channel group; smem reduce then one atomic per channel per CTA.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+modulate_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ s,
+                    float* __restrict__ dx, float* __restrict__ ds, int64_t hw, int cv, int64_t pix_per_cta) {
+    extern __shared__ float sacc[];   // [cv*VEC]
+    const int C = cv * VEC;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int n = blockIdx.y;
+    const int64_t p0 = blockIdx.x * pix_per_cta;
+    int64_t p1 = p0 + pix_per_cta;
+    if (p1 > hw) p1 = hw;
+    const int64_t base_v = (int64_t)n * hw * cv;
+    const int64_t lo = p0 * cv, hi = p1 * cv;          // in VEC units inside this sample
+    const int64_t stride = (blockDim.x / cv > 0) ? (int64_t)(blockDim.x / cv) * cv : 0;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    if (stride > 0) {
+        if (threadIdx.x < stride) {
+            const int c = threadIdx.x % cv;
+            float m[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) m[j] = __ldg(s + (int64_t)n * C + c * VEC + j);
+            for (int64_t i = lo + threadIdx.x; i < hi; i += stride) {
+                float g[VEC], a[VEC];
+                if (VEC == 4) {
+                    float4 t = ldg_stream(reinterpret_cast<const float4*>(dy) + base_v + i);
+                    float4 q = ldg_stream(reinterpret_cast<const float4*>(x) + base_v + i);
+                    g[0] = t.x; g[1 % VEC] = t.y; g[2 % VEC] = t.z; g[3 % VEC] = t.w;
+                    a[0] = q.x; a[1 % VEC] = q.y; a[2 % VEC] = q.z; a[3 % VEC] = q.w;
+                } else {
+                    g[0] = dy[base_v + i]; a[0] = x[base_v + i];
+                }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { acc[j] = fmaf(g[j], a[j], acc[j]); g[j] *= m[j]; }
+                if (VEC == 4) reinterpret_cast<float4*>(dx)[base_v + i] = make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]);
+                else dx[base_v + i] = g[0];
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) atomicAdd(&sacc[c * VEC + j], acc[j]);
+        }
+    } else {
+        // more channel groups than threads: each thread walks several channel groups per pixel
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const int c = (int)(i % cv);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                int64_t e = (base_v + i) * VEC + j;
+                float g = dy[e], a = x[e];
+                atomicAdd(&sacc[c * VEC + j], g * a);
+                dx[e] = g * __ldg(s + (int64_t)n * C + c * VEC + j);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float v = sacc[i];
+        if (v != 0.f) atomicAdd(ds + (int64_t)n * C + i, v);
+    }
+}
+
+// --------------------------------------------------------------------------- bucket pack/unpack
+__global__ void __launch_bounds__(256)
+bucket_copy_kernel(float* const* __restrict__ ptrs, const int64_t* __restrict__ offsets,
+                   const int64_t* __restrict__ sizes, float* __restrict__ bucket, float scale, int to_bucket) {
+    const int t = blockIdx.y;
+    float* p = ptrs[t];
+    float* b = bucket + offsets[t];
+    const int64_t n = sizes[t];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (to_bucket) b[i] = p[i];
+        else p[i] = b[i] * scale;
+    }
+}
+
+}  // namespace sae
+
+using namespace sae;
+
+extern "C" int sae_fused_bias_act(const float* x, const float* bias, const float* ref, float* out,
+                                  int64_t size_x, int64_t step_b, int size_b,
+                                  int act, int grad, float alpha, float scale,
+                                  const float* noise, const float* noise_weight, int64_t noise_div,
+                                  void* stream) {
+    if (size_x == 0) return SAE_OK;
+    if (!x || !out || size_x < 0) return fail(SAE_E_INVALID, "fused_bias_act: bad input");
+    if (act != 1 && act != 3) return fail(SAE_E_INVALID, "fused_bias_act: act %d unsupported (1 linear, 3 lrelu)", act);
+    if (grad < 0 || grad > 2) return fail(SAE_E_INVALID, "fused_bias_act: grad must be 0..2");
+    if (bias && (size_b <= 0 || step_b <= 0)) return fail(SAE_E_INVALID, "fused_bias_act: bad bias geometry");
+    if (noise && (!noise_weight || noise_div <= 0)) return fail(SAE_E_INVALID, "fused_bias_act: noise needs weight and divisor");
+    if (!bias) { size_b = 1; step_b = 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ref);
+    bool vec = (size_x % 4 == 0) && (al % 16 == 0) && (!noise || noise_div % 4 == 0);
+    if (vec) {
+        int64_t nv = size_x / 4;
+        bias_act_kernel<4><<<grid_for(nv, 256), 256, 0, st>>>(x, bias, ref, out, nv, step_b, size_b, act, grad, alpha,
+                                                             scale, noise, noise_weight, noise_div);
+    } else {
+        bias_act_kernel<1><<<grid_for(size_x, 256), 256, 0, st>>>(x, bias, ref, out, size_x, step_b, size_b, act, grad,
+                                                                 alpha, scale, noise, noise_weight, noise_div);
+    }
+    return check_launch("fused_bias_act");
+}
+
+extern "C" int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_in, float* grad_bias,
+                                     int64_t size_x, int size_b, float alpha, float scale,
+                                     const float* noise, int64_t noise_div, float* grad_noise_weight,
+                                     void* stream) {
+    if (size_x == 0) return SAE_OK;
+    if (!grad_out || !out || !grad_in || size_b <= 0 || size_x % size_b != 0)
+        return fail(SAE_E_INVALID, "bias_act_backward: bad arguments (size_x %% size_b must be 0)");
+    if (noise && (!grad_noise_weight || noise_div <= 0)) return fail(SAE_E_INVALID, "bias_act_backward: noise needs grad slot");
+    if (size_b > 12000) return fail(SAE_E_UNSUPPORTED, "bias_act_backward: more than 12000 channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    uintptr_t al = reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(grad_in);
+    bool vec = (size_b % 4 == 0) && (al % 16 == 0) && (!noise || noise_div % 4 == 0);
+    const int V = vec ? 4 : 1;
+    const int cv = size_b / V;
+    const int64_t size_v = size_x / V;
+    unsigned blocks = grid_for(size_v, 256, 4);
+    int64_t threads = (int64_t)blocks * 256;
+    // stride must be a multiple of cv so each thread's channel group is loop-invariant
+    int64_t stride = (threads / cv) * cv;
+    if (stride == 0) {  // fewer threads than channel groups: grow the grid
+        blocks = (unsigned)((cv + 255) / 256);
+        threads = (int64_t)blocks * 256;
+        stride = (threads / cv) * cv;
+    }
+    size_t smem = (size_t)(size_b + 1) * sizeof(float);
+    if (vec) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(bias_act_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        bias_act_bwd_kernel<4><<<blocks, 256, smem, st>>>(grad_out, out, grad_in, grad_bias, size_v, cv, stride, alpha, scale,
+                                                         noise, noise_div, grad_noise_weight);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(bias_act_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        bias_act_bwd_kernel<1><<<blocks, 256, smem, st>>>(grad_out, out, grad_in, grad_bias, size_v, cv, stride, alpha, scale,
+                                                         noise, noise_div, grad_noise_weight);
+    }
+    return check_launch("bias_act_backward");
+}
+
+extern "C" int sae_modulate(const float* x, const float* s, float* out, int n, int64_t hw, int c, int round_tf32,
+                            void* stream) {
+    if (n == 0 || hw == 0) return SAE_OK;
+    if (!x || !s || !out || n < 0 || hw < 0 || c <= 0) return fail(SAE_E_INVALID, "modulate: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(s);
+    if (c % 4 == 0 && al % 16 == 0) {
+        int64_t tv = (int64_t)n * hw * (c / 4);
+        modulate_kernel<<<grid_for(tv, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s),
+                                                          reinterpret_cast<float4*>(out), tv, hw, c / 4, round_tf32);
+    } else {
+        int64_t t = (int64_t)n * hw * c;
+        modulate_scalar_kernel<<<grid_for(t, 256), 256, 0, st>>>(x, s, out, t, hw, c, round_tf32);
+    }
+    return check_launch("modulate");
+}
+
+extern "C" int sae_modulate_backward(const float* dy, const float* x, const float* s, float* dx, float* ds,
+                                     int n, int64_t hw, int c, void* stream) {
+    if (n == 0 || hw == 0) return SAE_OK;
+    if (!dy || !x || !s || !dx || !ds || n < 0 || c <= 0) return fail(SAE_E_INVALID, "modulate_backward: bad arguments");
+    if (c > 12000) return fail(SAE_E_UNSUPPORTED, "modulate_backward: more than 12000 channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    uintptr_t al = reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx);
+    const bool vec = (c % 4 == 0) && (al % 16 == 0);
+    const int V = vec ? 4 : 1;
+    // aim for ~4 CTAs per SM over the whole batch
+    int64_t want = ((int64_t)sm_count() * 4 + n - 1) / n;
+    if (want < 1) want = 1;
+    int64_t pix_per_cta = (hw + want - 1) / want;
+    if (pix_per_cta < 8) pix_per_cta = 8;
+    unsigned chunks = (unsigned)((hw + pix_per_cta - 1) / pix_per_cta);
+    dim3 grid(chunks, (unsigned)n);
+    size_t smem = (size_t)c * sizeof(float);
+    if (vec) modulate_bwd_kernel<4><<<grid, 256, smem, st>>>(dy, x, s, dx, ds, hw, c / V, pix_per_cta);
+    else     modulate_bwd_kernel<1><<<grid, 256, smem, st>>>(dy, x, s, dx, ds, hw, c / V, pix_per_cta);
+    return check_launch("modulate_backward");
+}
+
+extern "C" int sae_bucket_pack(const float* const* ptrs, const int64_t* offsets, const int64_t* sizes, int n,
+                               float* bucket, int64_t total, void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!ptrs || !offsets || !sizes || !bucket || n < 0 || total < 0) return fail(SAE_E_INVALID, "bucket_pack: bad arguments");
+    dim3 grid(64, (unsigned)n);
+    bucket_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(const_cast<float* const*>(ptrs), offsets, sizes, bucket, 1.f, 1);
+    return check_launch("bucket_pack");
+}
+
+extern "C" int sae_bucket_unpack(float* const* ptrs, const int64_t* offsets, const int64_t* sizes, int n,
+                                 const float* bucket, int64_t total, float scale, void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!ptrs || !offsets || !sizes || !bucket || n < 0 || total < 0) return fail(SAE_E_INVALID, "bucket_unpack: bad arguments");
+    dim3 grid(64, (unsigned)n);
+    bucket_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ptrs, offsets, sizes, const_cast<float*>(bucket), scale, 0);
+    return check_launch("bucket_unpack");
+}

@@ -1,0 +1,224 @@
+// upfirdn2d on NHWC fp32 — replaces models/networks/stylegan2_op/upfirdn2d_kernel.cu:52-137 of the
+// reference.  HBM-bound: algorithmic traffic 4*(N_in + N_out) bytes.
+//
+// Design (B200): channels are the innermost (minor) dimension, so one warp reads 32 consecutive
+// float4 = 512 contiguous bytes per tap and writes 512 contiguous bytes per output pixel; the
+// (up to kh*kw) tap re-reads of a neighbourhood are served by L1/L2 (a 4x4 FIR touches each input
+// line 16 times within a few hundred cycles from neighbouring warps of the same CTA).  Taps live in
+// shared memory, already flipped, so the inner loop is a plain correlation.  A column-strip variant
+// keeps a rolling kh x kw register window so each input element is loaded kw (not kh*kw) times.
+#include "common.cuh"
+
+namespace sae {
+
+struct FirParams {
+    int64_t major;
+    int in_h, in_w, minor;
+    int kh, kw;
+    int up_x, up_y, down_x, down_y;
+    int pad_x0, pad_y0;
+    int out_h, out_w;
+};
+
+constexpr int kMaxTaps = 32 * 32;
+
+__device__ __forceinline__ int floordiv(int a, int b) {
+    int q = a / b;
+    return (q * b > a) ? q - 1 : q;
+}
+
+// Generic kernel: one thread per VEC output channels of one output pixel.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+fir_generic_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ out, FirParams p) {
+    __shared__ float sk[kMaxTaps];
+    const int ntaps = p.kh * p.kw;
+    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) {
+        int ky = i / p.kw, kx = i - ky * p.kw;
+        sk[i] = k[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];   // flipped: true convolution
+    }
+    __syncthreads();
+
+    const int cv = p.minor / VEC;
+    const int64_t total = p.major * (int64_t)p.out_h * p.out_w * cv;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(idx % cv);
+        int64_t pix = idx / cv;
+        int ox = (int)(pix % p.out_w);
+        int64_t t = pix / p.out_w;
+        int oy = (int)(t % p.out_h);
+        int64_t n = t / p.out_h;
+
+        // position of tap (0,0) in zero-upsampled, unpadded coordinates
+        const int uy0 = oy * p.down_y - p.pad_y0;
+        const int ux0 = ox * p.down_x - p.pad_x0;
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+
+        const float* xn = x + n * (int64_t)p.in_h * p.in_w * p.minor + (int64_t)c * VEC;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            int uy = uy0 + ky;
+            if (uy < 0) continue;
+            int iy = uy / p.up_y;
+            if (iy * p.up_y != uy || iy >= p.in_h) continue;
+            for (int kx = 0; kx < p.kw; ++kx) {
+                int ux = ux0 + kx;
+                if (ux < 0) continue;
+                int ix = ux / p.up_x;
+                if (ix * p.up_x != ux || ix >= p.in_w) continue;
+                float w = sk[ky * p.kw + kx];
+                const float* src = xn + ((int64_t)iy * p.in_w + ix) * p.minor;
+                if (VEC == 4) {
+                    float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                    acc[0] = fmaf(v.x, w, acc[0]);
+                    acc[1 % VEC] = fmaf(v.y, w, acc[1 % VEC]);
+                    acc[2 % VEC] = fmaf(v.z, w, acc[2 % VEC]);
+                    acc[3 % VEC] = fmaf(v.w, w, acc[3 % VEC]);
+                } else {
+                    acc[0] = fmaf(__ldg(src), w, acc[0]);
+                }
+            }
+        }
+        float* dst = out + pix * p.minor + (int64_t)c * VEC;
+        if (VEC == 4) {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+        } else {
+            dst[0] = acc[0];
+        }
+    }
+}
+
+// Column-strip kernel for the training hot path (up = down = 1, kh,kw <= 4, minor % 4 == 0):
+// a thread owns (n, ox, c4) and walks ROWS output rows downwards keeping the last KH input rows x KW
+// columns in registers, so every input float4 is loaded KW times instead of KH*KW times.
+template <int KH, int KW, int ROWS>
+__global__ void __launch_bounds__(256)
+fir_strip_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ out, FirParams p) {
+    __shared__ float sk[KH * KW];
+    if (threadIdx.x < KH * KW) {
+        int ky = threadIdx.x / KW, kx = threadIdx.x - ky * KW;
+        sk[threadIdx.x] = k[(KH - 1 - ky) * KW + (KW - 1 - kx)];
+    }
+    __syncthreads();
+    float w[KH][KW];
+#pragma unroll
+    for (int a = 0; a < KH; ++a)
+#pragma unroll
+        for (int b = 0; b < KW; ++b) w[a][b] = sk[a * KW + b];
+
+    const int cv = p.minor >> 2;
+    const int strips = (p.out_h + ROWS - 1) / ROWS;
+    const int64_t total = p.major * (int64_t)strips * p.out_w * cv;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(idx % cv);
+        int64_t t = idx / cv;
+        int ox = (int)(t % p.out_w);
+        t /= p.out_w;
+        int strip = (int)(t % strips);
+        int64_t n = t / strips;
+
+        const int oy0 = strip * ROWS;
+        const int ix0 = ox - p.pad_x0;
+        const float* xn = x + n * (int64_t)p.in_h * p.in_w * p.minor + (int64_t)c * 4;
+        float4 win[KH][KW];
+
+        auto load_row = [&](int iy, float4 (&row)[KW]) {
+            const bool yok = (iy >= 0) && (iy < p.in_h);
+#pragma unroll
+            for (int b = 0; b < KW; ++b) {
+                int ix = ix0 + b;
+                if (yok && ix >= 0 && ix < p.in_w)
+                    row[b] = __ldg(reinterpret_cast<const float4*>(xn + ((int64_t)iy * p.in_w + ix) * p.minor));
+                else
+                    row[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // prime the window with the first KH-1 rows
+#pragma unroll
+        for (int a = 0; a < KH - 1; ++a) load_row(oy0 - p.pad_y0 + a, win[a]);
+
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int oy = oy0 + r;
+            if (oy >= p.out_h) break;
+            load_row(oy - p.pad_y0 + KH - 1, win[KH - 1]);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < KH; ++a)
+#pragma unroll
+                for (int b = 0; b < KW; ++b) {
+                    acc.x = fmaf(win[a][b].x, w[a][b], acc.x);
+                    acc.y = fmaf(win[a][b].y, w[a][b], acc.y);
+                    acc.z = fmaf(win[a][b].z, w[a][b], acc.z);
+                    acc.w = fmaf(win[a][b].w, w[a][b], acc.w);
+                }
+            float* dst = out + ((n * p.out_h + oy) * (int64_t)p.out_w + ox) * p.minor + (int64_t)c * 4;
+            *reinterpret_cast<float4*>(dst) = acc;
+            // slide the window up by one row
+#pragma unroll
+            for (int a = 0; a < KH - 1; ++a)
+#pragma unroll
+                for (int b = 0; b < KW; ++b) win[a][b] = win[a + 1][b];
+        }
+    }
+}
+
+template <int KH, int KW>
+static void launch_strip(const float* x, const float* k, float* out, const FirParams& p, cudaStream_t st) {
+    constexpr int ROWS = 8;
+    const int strips = (p.out_h + ROWS - 1) / ROWS;
+    int64_t total = p.major * (int64_t)strips * p.out_w * (p.minor / 4);
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    fir_strip_kernel<KH, KW, ROWS><<<(unsigned)blocks, 256, 0, st>>>(x, k, out, p);
+}
+
+}  // namespace sae
+
+extern "C" int sae_upfirdn2d(const float* input, const float* kernel, float* out,
+                             int64_t major, int in_h, int in_w, int minor,
+                             int kernel_h, int kernel_w,
+                             int up_x, int up_y, int down_x, int down_y,
+                             int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                             void* stream) {
+    using namespace sae;
+    if (!input || !kernel || !out) return fail(SAE_E_INVALID, "upfirdn2d: null pointer");
+    if (major < 0 || in_h <= 0 || in_w <= 0 || minor <= 0) return fail(SAE_E_INVALID, "upfirdn2d: bad input shape");
+    if (kernel_h <= 0 || kernel_w <= 0 || kernel_h * kernel_w > kMaxTaps)
+        return fail(SAE_E_INVALID, "upfirdn2d: kernel %dx%d unsupported (max 32x32)", kernel_h, kernel_w);
+    if (up_x <= 0 || up_y <= 0 || down_x <= 0 || down_y <= 0) return fail(SAE_E_INVALID, "upfirdn2d: up/down must be >= 1");
+    FirParams p;
+    p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor;
+    p.kh = kernel_h; p.kw = kernel_w;
+    p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
+    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+    int full_h = in_h * up_y + pad_y0 + pad_y1 - kernel_h;
+    int full_w = in_w * up_x + pad_x0 + pad_x1 - kernel_w;
+    if (full_h < 0 || full_w < 0) return fail(SAE_E_INVALID, "upfirdn2d: kernel larger than padded input");
+    p.out_h = full_h / down_y + 1;
+    p.out_w = full_w / down_x + 1;
+    if (major == 0) return SAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(input) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const bool vec = (minor % 4 == 0) && aligned;
+    const bool unit = (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1);
+    if (vec && unit && kernel_h == 4 && kernel_w == 4) {
+        launch_strip<4, 4>(input, kernel, out, p, st);
+    } else if (vec && unit && kernel_h == 3 && kernel_w == 3) {
+        launch_strip<3, 3>(input, kernel, out, p, st);
+    } else {
+        int64_t total = major * (int64_t)p.out_h * p.out_w * (vec ? minor / 4 : minor);
+        int64_t blocks = (total + 255) / 256;
+        int64_t cap = (int64_t)sm_count() * 32;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        if (vec) fir_generic_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(input, kernel, out, p);
+        else     fir_generic_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(input, kernel, out, p);
+    }
+    return check_launch("upfirdn2d");
+}

@@ -1,0 +1,137 @@
+"""Dense convolution family with closed first- and second-order autograd on the sm_100a implicit-GEMM kernels.
+
+Replaces the ``F.conv2d`` / ``F.conv_transpose2d`` / ``F.linear`` call sites of the reference operator surface
+(models/networks/stylegan2_layers.py:136-142, :174-186, :299-323).  A convolution is bilinear in (input, weight),
+so three primitives — fprop(x, w), dgrad(dy, w), wgrad(dy, x) — are closed under differentiation; each is an
+``autograd.Function`` whose backward is written with the other two.  That is what lets
+``SwappingAutoencoderModel.compute_R1_loss`` (reference swapping_autoencoder_model.py:138-185) take
+``autograd.grad(..., create_graph=True)`` through D / Dpatch and back-propagate the penalty.
+
+Weights enter in the reference's parameter layout ``[Cout, Cin, R, S]`` and are permuted to the kernels'
+``[K, R, S, C]`` by a (differentiable) torch permute of the small filter tensor.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import backend
+from ..backend import make_geom
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+class _ConvFprop(Function):
+    """y = conv(x, w)   x: logical NCHW, w: [K,R,S,C]"""
+
+    @staticmethod
+    def forward(ctx, x, w, g):
+        ctx.g = g
+        ctx.save_for_backward(x, w)
+        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = _ConvDgrad.apply(dy, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dw = _ConvWgrad.apply(dy, x, ctx.g) if ctx.needs_input_grad[1] else None
+        return dx, dw, None
+
+
+class _ConvDgrad(Function):
+    """dx = conv^T(dy, w)   (also the forward of a transposed convolution)"""
+
+    @staticmethod
+    def forward(ctx, dy, w, g):
+        ctx.g = g
+        ctx.save_for_backward(dy, w)
+        return _nchw(backend.kernels().conv_dgrad(_nhwc(dy), w.contiguous(), g))
+
+    @staticmethod
+    def backward(ctx, ddx):
+        dy, w = ctx.saved_tensors
+        d_dy = _ConvFprop.apply(ddx, w, ctx.g) if ctx.needs_input_grad[0] else None
+        d_w = _ConvWgrad.apply(dy, ddx, ctx.g) if ctx.needs_input_grad[1] else None
+        return d_dy, d_w, None
+
+
+class _ConvWgrad(Function):
+    """dw[K,R,S,C] = sum_pixels dy (x) x_gathered"""
+
+    @staticmethod
+    def forward(ctx, dy, x, g):
+        ctx.g = g
+        ctx.save_for_backward(dy, x)
+        return backend.kernels().conv_wgrad(_nhwc(dy), _nhwc(x), g)
+
+    @staticmethod
+    def backward(ctx, ddw):
+        dy, x = ctx.saved_tensors
+        d_dy = _ConvFprop.apply(x, ddw, ctx.g) if ctx.needs_input_grad[0] else None
+        d_x = _ConvDgrad.apply(dy, ddw, ctx.g) if ctx.needs_input_grad[1] else None
+        return d_dy, d_x, None
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0):
+    """``F.conv2d(input, weight, bias, stride, padding)`` for NCHW-shaped input, [Cout,Cin,R,S] weight."""
+    n, c, h, w_ = input.shape
+    k, c2, r, s = weight.shape
+    assert c == c2, "channel mismatch: input %d vs weight %d" % (c, c2)
+    if (h + 2 * padding - r) < 0 or (w_ + 2 * padding - s) < 0:
+        # same failure the reference hits at 64x64 with default options
+        raise RuntimeError("Kernel size can't be greater than actual input size")
+    g = make_geom(n, h, w_, c, k, r, s, stride, padding, padding)
+    out = _ConvFprop.apply(input, weight.permute(0, 2, 3, 1), g)
+    if bias is not None:
+        out = out + bias.view(1, -1, 1, 1)
+    return out
+
+
+def conv_transpose2d(input, weight, stride=2, padding=0):
+    """``F.conv_transpose2d(input, weight[Cin,Cout,R,S], stride, padding)`` — computed as the data-gradient of
+    the strided convolution whose filter is ``weight`` read as [K=Cin, C=Cout, R, S]."""
+    n, cin, h, w_ = input.shape
+    cin2, cout, r, s = weight.shape
+    assert cin == cin2
+    oh = (h - 1) * stride - 2 * padding + r
+    ow = (w_ - 1) * stride - 2 * padding + s
+    g = make_geom(n, oh, ow, cout, cin, r, s, stride, padding, padding, P=h, Q=w_)
+    return _ConvDgrad.apply(input, weight.permute(0, 2, 3, 1), g)
+
+
+def linear(input, weight, bias=None):
+    """``F.linear`` for [B, in] x [out, in]: a 1x1 convolution on a 1x1 map."""
+    b, cin = input.shape
+    cout = weight.shape[0]
+    g = make_geom(b, 1, 1, cin, cout, 1, 1, 1, 0, 0)
+    out = _ConvFprop.apply(input.view(b, cin, 1, 1), weight.view(cout, 1, 1, cin), g).reshape(b, cout)
+    if bias is not None:
+        out = out + bias
+    return out
+
+
+class _Modulate(Function):
+    """x * s[:, :, None, None] (stylegan2_layers.py:284) with the style gradient reduced in the same pass.
+    Only the generator modulates, and the generator is never differentiated twice, so the
+    backward is once-differentiable: a second-order request raises instead of silently detaching."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.save_for_backward(x, s)
+        return _nchw(backend.kernels().modulate(_nhwc(x), s.contiguous()))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, s = ctx.saved_tensors
+        dx, ds = backend.kernels().modulate_backward(_nhwc(dy), _nhwc(x), s.contiguous())
+        return _nchw(dx), ds
+
+
+def modulate(x, s):
+    return _Modulate.apply(x, s)
