@@ -313,19 +313,25 @@ def swap(x):
     return x.reshape(x.shape[0] // 2, 2, *x.shape[1:]).flip(1).reshape(x.shape)
 
 
+def draw_crop_parameters(B, opt):
+    """flip, scale, offset in the reference's draw order (util/util.py:326-336)"""
+    flip = torch.round(torch.rand(B, 1, 1, 1)) * 2 - 1.0
+    scale = torch.rand(B, 1, 1, 2) * (opt.patch_max_scale - opt.patch_min_scale) + opt.patch_min_scale
+    offset = (torch.rand(B, 1, 1, 2) * 2 - 1) * (1 - scale)
+    return flip, scale, offset
+
+
 def random_crops(x, opt):
-    """reference util/util.py:323-343 (same order of random draws)"""
+    """reference util/util.py:323-343"""
     n = opt.patch_num_crops
     size = opt.patch_size
     B = x.size(0) * n
-    flip = torch.round(torch.rand(B, 1, 1, 1)) * 2 - 1.0
+    flip, scale, offset = (t.to(x.dtype) for t in draw_crop_parameters(B, opt))
     lin = torch.linspace(-1.0, 1.0, size, dtype=x.dtype)
     gx = lin.view(1, 1, size, 1).expand(B, size, size, 1)
     gy = lin.view(1, size, 1, 1).expand(B, size, size, 1)
-    unit = torch.cat([gx * flip.to(x.dtype), gy], dim=3)
+    unit = torch.cat([gx * flip, gy], dim=3)
     xx = x.unsqueeze(1).expand(-1, n, -1, -1, -1).flatten(0, 1)
-    scale = (torch.rand(B, 1, 1, 2) * (opt.patch_max_scale - opt.patch_min_scale) + opt.patch_min_scale).to(x.dtype)
-    offset = ((torch.rand(B, 1, 1, 2) * 2 - 1).to(x.dtype)) * (1 - scale)
     crop = F.grid_sample(xx, unit * scale + offset, align_corners=False)
     return crop.view(B // n, n, crop.size(1), crop.size(2), crop.size(3))
 

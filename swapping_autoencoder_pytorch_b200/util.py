@@ -10,22 +10,27 @@ def normalize(v):
     return v * torch.rsqrt(v.square().sum(dim=1, keepdim=True) + 1e-8)
 
 
+def draw_crop_parameters(b, scale_range, device):
+    """The three random tensors of a crop batch, drawn in the reference's order (flip, scale, offset)."""
+    lo, hi = scale_range
+    flip = torch.round(torch.rand(b, 1, 1, 1, device=device)) * 2 - 1.0
+    scale = torch.rand(b, 1, 1, 2, device=device) * (hi - lo) + lo
+    offset = (torch.rand(b, 1, 1, 2, device=device) * 2 - 1) * (1 - scale)
+    return flip, scale, offset
+
+
 def apply_random_crop(x, target_size, scale_range, num_crops=1, return_rect=False):
     """Random square crops, random horizontal flip, bilinear resample to ``target_size``
     (reference util/util.py:323-343).  Draw order of the three random tensors (flip, scale, offset) matches the
     reference so a shared RNG seed reproduces the same crops.  Returns [B, num_crops, C, S, S]."""
     b = x.size(0) * num_crops
-    dev = x.device
-    flip = torch.round(torch.rand(b, 1, 1, 1, device=dev)) * 2 - 1.0
-    lin = torch.linspace(-1.0, 1.0, target_size, device=dev)
+    flip, scale, offset = draw_crop_parameters(b, scale_range, x.device)
+    lin = torch.linspace(-1.0, 1.0, target_size, device=x.device)
     gx = lin.view(1, 1, target_size, 1).expand(b, target_size, target_size, 1)
     gy = lin.view(1, target_size, 1, 1).expand(b, target_size, target_size, 1)
     unit = torch.cat([gx * flip, gy], dim=3)
     x = x.unsqueeze(1).expand(-1, num_crops, -1, -1, -1).flatten(0, 1)
-    lo, hi = scale_range
-    scale = torch.rand(b, 1, 1, 2, device=dev) * (hi - lo) + lo
-    offset = (torch.rand(b, 1, 1, 2, device=dev) * 2 - 1) * (1 - scale)
-    crop = F.grid_sample(x, unit * scale + offset, align_corners=False)
+    crop = F.grid_sample(x, (unit * scale + offset).to(x.dtype), align_corners=False)
     return crop.view(b // num_crops, num_crops, crop.size(1), crop.size(2), crop.size(3))
 
 

@@ -1,0 +1,401 @@
+"""GPU (B200): the CUDA path — called through the C ABI — against the oracle and the reference's golden fixtures.
+
+Tolerances (BASELINE.json: "within a stated fp32 tolerance (1e-3 rel)"; metric rel = max|a-b| / max|b|,
+SURVEY.md §9.5):
+  * FIR, bias-act, modulate (plain fp32 arithmetic): 2e-6
+  * anything containing a convolution (TF32 tensor-core operands, fp32 accumulate): 1e-3 per op against a strict
+    fp64 oracle; network-level outputs accumulate ~25 TF32 convs and get 3e-3 (the reference's own GPU path runs
+    cuDNN with TF32 enabled, so it has the same spread against a strict-fp32 computation).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sae_oracle as O
+from oracle.fixtures import TINY, load_golden, perturbed_state_dict, rel_err, rel_l2, rnd
+from swapping_autoencoder_pytorch_b200 import backend, default_options
+from swapping_autoencoder_pytorch_b200.backend import make_geom
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_FP32 = 2e-6
+TOL_TF32 = 1e-3
+TOL_NET = 3e-3
+
+
+def cuda(t):
+    return t.float().to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ FIR
+def test_fir_golden_cases_and_second_order():
+    from swapping_autoencoder_pytorch_b200.stylegan2_layers import make_kernel
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
+    meta, G = load_golden("ops_upfirdn2d")
+    for i, c in enumerate(meta["cases"]):
+        k = (make_kernel(c["taps"]) * c["gain"]).to(DEV)
+        x = cuda(rnd(meta["x_seed0"] + i, *meta["shape"])).requires_grad_()
+        y = upfirdn2d(x, k, up=c["up"], down=c["down"], pad=tuple(c["pad"]))
+        assert rel_err(y, G["y%d" % i]) < TOL_FP32, c
+        w = cuda(rnd(meta["w_seed0"] + i, *y.shape)).requires_grad_()
+        gx, = torch.autograd.grad((y * w).sum(), x, create_graph=True)
+        assert rel_err(gx, G["gx%d" % i]) < TOL_FP32, c
+        v = cuda(rnd(77 + i, *x.shape))
+        gw, = torch.autograd.grad((gx * v).sum(), w)
+        assert rel_err(gw, upfirdn2d(v, k, up=c["up"], down=c["down"], pad=tuple(c["pad"]))) < TOL_FP32, c
+
+
+@pytest.mark.parametrize("taps,pad,c,h", [([1, 3, 3, 1], (2, 2), 128, 64), ([1, 3, 3, 1], (1, 1), 64, 65),
+                                          ([1, 2, 1], (0, 0), 32, 67), ([1, 2, 1], (1, 0), 256, 16),
+                                          ([1], (0, 0), 512, 7), ([1, 3, 3, 1], (1, 1), 3, 33),
+                                          ([1, 3, 3, 1], (2, 2), 384, 4)])
+def test_fir_hot_path_shapes(taps, pad, c, h):
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
+    k = O.make_kernel(taps, torch.float64)
+    x = rnd(5, 3, c, h, h + 1)
+    y_ref = O.upfirdn2d(x, k, pad=pad)
+    y = upfirdn2d(cuda(x), cuda(k), pad=pad)
+    assert y.shape == y_ref.shape
+    assert rel_err(y, y_ref) < TOL_FP32
+
+
+def test_fir_edge_cases():
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
+    k = cuda(O.make_kernel([1, 3, 3, 1], torch.float64))
+    # empty batch, and a 5x5 generic kernel with up=2/down=3
+    y = upfirdn2d(torch.zeros(0, 8, 6, 6, device=DEV), k, pad=(1, 1))
+    assert y.shape == (0, 8, 5, 5)
+    k5 = rnd(9, 5, 5)
+    x = rnd(10, 2, 6, 11, 9)
+    ref = O.fir_numpy(x.numpy(), k5.numpy(), (2, 2), (3, 3), (3, 1, 3, 1))
+    got = upfirdn2d(cuda(x), cuda(k5), up=2, down=3, pad=(3, 1))
+    assert rel_err(got, torch.from_numpy(ref.copy())) < TOL_FP32
+
+
+# -------------------------------------------------------------------------------------------- bias/act
+@pytest.mark.parametrize("shape", [(2, 4, 5, 6), (3, 8), (4, 128, 32, 32), (16, 2048), (2, 3, 7, 5), (8, 384, 2, 2)])
+def test_fused_leaky_relu_fwd_bwd_double_bwd(shape):
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import fused_leaky_relu
+    x = rnd(1, *shape)
+    b = rnd(2, shape[1])
+    w = rnd(3, *shape)
+    xr, br, wr = (t.clone().requires_grad_() for t in (x, b, w))
+    gx_r, gb_r = torch.autograd.grad((O.fused_leaky_relu(xr, br) * wr).sum(), [xr, br], create_graph=True)
+    xg, bg, wg = (cuda(t).requires_grad_() for t in (x, b, w))
+    y = fused_leaky_relu(xg, bg)
+    assert rel_err(y, O.fused_leaky_relu(x, b)) < TOL_FP32
+    gx, gb = torch.autograd.grad((y * wg).sum(), [xg, bg], create_graph=True)
+    assert rel_err(gx, gx_r) < TOL_FP32
+    assert rel_err(gb, gb_r) < 2e-5          # fp32 atomics over up to 4k elements per channel
+    u, ub = rnd(4, *shape), rnd(5, shape[1])
+    gw_r, = torch.autograd.grad((gx_r * u).sum() + (gb_r * ub).sum(), wr)
+    gw, = torch.autograd.grad((gx * cuda(u)).sum() + (gb * cuda(ub)).sum(), wg)
+    assert rel_err(gw, gw_r) < TOL_FP32
+
+
+def test_noise_bias_act_fused():
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import fused_noise_bias_leaky_relu
+    x, nz, b = rnd(1, 2, 64, 16, 16), rnd(2, 2, 1, 16, 16), rnd(3, 64)
+    nw = torch.tensor([0.37], dtype=torch.float64)
+    xr, nwr, br = (t.clone().requires_grad_() for t in (x, nw, b))
+    yr = O.fused_leaky_relu(xr + nwr * nz, br)
+    w = rnd(4, *yr.shape)
+    gr = torch.autograd.grad((yr * w).sum(), [xr, nwr, br])
+    xg, nwg, bg = (cuda(t).requires_grad_() for t in (x, nw, b))
+    y = fused_noise_bias_leaky_relu(xg, cuda(nz), nwg, bg)
+    assert rel_err(y, yr) < TOL_FP32
+    g = torch.autograd.grad((y * cuda(w)).sum(), [xg, nwg, bg])
+    for a, r in zip(g, gr):
+        assert rel_err(a, r) < 2e-5
+
+
+def test_modulate():
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import modulate
+    kern = backend.kernels()
+    prev, kern.round_tf32 = kern.round_tf32, False
+    try:
+        for c in (8, 512, 3, 2048):
+            x, s, w = rnd(1, 3, c, 9, 7), rnd(2, 3, c), rnd(3, 3, c, 9, 7)
+            xg, sg = cuda(x).requires_grad_(), cuda(s).requires_grad_()
+            y = modulate(xg, sg)
+            assert rel_err(y, x * s[:, :, None, None]) < TOL_FP32
+            gx, gs = torch.autograd.grad((y * cuda(w)).sum(), [xg, sg])
+            assert rel_err(gx, w * s[:, :, None, None]) < TOL_FP32
+            assert rel_err(gs, (w * x).sum(dim=(2, 3))) < 2e-5
+    finally:
+        kern.round_tf32 = prev
+
+
+# ------------------------------------------------------------------------------------------------ conv
+CONV_CASES = [
+    # N, H, W, C, K, R, stride, pad          (covers every conv flavour of SURVEY.md Appendix A, scaled down)
+    (2, 16, 16, 32, 64, 3, 1, 1),            # plain 3x3
+    (2, 17, 17, 32, 64, 3, 2, 0),            # blurred (H+1) -> stride-2 3x3
+    (2, 15, 15, 32, 64, 1, 2, 0),            # skip: 1x1 stride 2
+    (3, 16, 16, 3, 32, 1, 1, 0),             # FromRGB (Cin = 3)
+    (3, 16, 16, 3, 32, 3, 1, 1),             # Dpatch first conv (K = 27)
+    (2, 16, 16, 128, 3, 1, 1, 0),            # ToRGB (Cout = 3)
+    (2, 16, 16, 8, 256, 3, 1, 1),            # HeadResnetBlock0.conv1 (K = 72)
+    (4, 7, 7, 64, 128, 3, 2, 0),             # encoder tail 7x7 -> 3x3
+    (5, 4, 4, 96, 96, 3, 1, 1),              # 4x4 maps, channel count not a multiple of 32
+    (2, 4, 4, 64, 32, 3, 1, 0),              # Dpatch convs.6: 4x4 -> 2x2, pad 0
+    (2, 32, 32, 128, 128, 3, 1, 1),          # tensor-core tile shape
+    (1, 64, 64, 256, 256, 3, 1, 1),
+    (2, 32, 32, 512, 256, 1, 1, 0),          # generator skip 1x1
+    (2, 33, 33, 128, 256, 3, 2, 0),
+]
+
+
+def _conv_ref(x, w, stride, pad):
+    return F.conv2d(x, w, stride=stride, padding=pad)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad(case, impl):
+    n, h, w_, c, k, r, stride, pad = case
+    kern = backend.kernels()
+    x = rnd(11, n, c, h, w_)
+    wt = rnd(12, k, c, r, r) / math.sqrt(c * r * r)
+    xr, wr = x.clone().requires_grad_(), wt.clone().requires_grad_()
+    yr = _conv_ref(xr, wr, stride, pad)
+    dy = rnd(13, *yr.shape)
+    gxr, gwr = torch.autograd.grad((yr * dy).sum(), [xr, wr])
+    g = make_geom(n, h, w_, c, k, r, r, stride, pad, pad)
+    prev, kern.conv_impl = kern.conv_impl, impl
+    try:
+        xg = cuda(x).permute(0, 2, 3, 1).contiguous()
+        wg = cuda(wt).permute(0, 2, 3, 1).contiguous()
+        dyg = cuda(dy).permute(0, 2, 3, 1).contiguous()
+        y = kern.conv_fprop(xg, wg, g, round_tf32=False).permute(0, 3, 1, 2)
+        gx = kern.conv_dgrad(dyg, wg, g, round_tf32=False).permute(0, 3, 1, 2)
+        gw = kern.conv_wgrad(dyg, xg, g).permute(0, 3, 1, 2)
+    finally:
+        kern.conv_impl = prev
+    assert rel_err(y, yr) < TOL_TF32, ("fprop", rel_err(y, yr))
+    assert rel_err(gx, gxr) < TOL_TF32, ("dgrad", rel_err(gx, gxr))
+    assert rel_err(gw, gwr) < TOL_TF32, ("wgrad", rel_err(gw, gwr))
+
+
+def test_conv_transpose_and_linear():
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import conv_transpose2d, linear
+    x, w = rnd(1, 2, 64, 9, 9), rnd(2, 64, 32, 3, 3) / 24
+    ref = F.conv_transpose2d(x, w, stride=2)
+    assert rel_err(conv_transpose2d(cuda(x), cuda(w)), ref) < TOL_TF32
+    xl, wl = rnd(3, 16, 2048), rnd(4, 512, 2048) / 45
+    assert rel_err(linear(cuda(xl), cuda(wl)), F.linear(xl, wl)) < TOL_TF32
+    xl, wl = rnd(5, 6, 512), rnd(6, 1, 512) / 22
+    assert rel_err(linear(cuda(xl), cuda(wl)), F.linear(xl, wl)) < TOL_TF32
+
+
+def test_conv_epilogue_fusion():
+    kern = backend.kernels()
+    n, h, c, k = 2, 16, 64, 128
+    x, w, b = rnd(1, n, c, h, h), rnd(2, k, c, 3, 3) / 24, rnd(3, k)
+    res, nz = rnd(4, n, k, h, h), rnd(5, n, 1, h, h)
+    nw = torch.tensor([0.25], dtype=torch.float64)
+    ref = (O.fused_leaky_relu(F.conv2d(x, w, padding=1) + nw * nz, b) + res) / math.sqrt(2)
+    g = make_geom(n, h, h, c, k, 3, 3, 1, 1, 1)
+    for impl in (1, 0):
+        prev, kern.conv_impl = kern.conv_impl, impl
+        try:
+            y = kern.conv_fprop(cuda(x).permute(0, 2, 3, 1).contiguous(), cuda(w).permute(0, 2, 3, 1).contiguous(), g,
+                                bias=cuda(b), act=3, alpha=0.2, gain=math.sqrt(2), noise=cuda(nz).reshape(-1).contiguous(),
+                                noise_weight=cuda(nw), residual=cuda(res).permute(0, 2, 3, 1).contiguous(),
+                                res_scale=1 / math.sqrt(2), round_tf32=False)
+        finally:
+            kern.conv_impl = prev
+        assert rel_err(y.permute(0, 3, 1, 2), ref) < TOL_TF32
+
+
+@pytest.mark.parametrize("shape", [(4, 256, 256, 128, 128), (4, 64, 64, 512, 512), (2, 128, 128, 256, 256)])
+def test_conv_full_size_adjointness(shape):
+    """Size-independent property at BASELINE layer sizes: <fprop(x,w), dy> = <x, dgrad(dy,w)> = <w, wgrad(dy,x)>."""
+    n, h, w_, c, k = shape
+    kern = backend.kernels()
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(n, h, w_, c, device=DEV, generator=gen)
+    w = torch.randn(k, 3, 3, c, device=DEV, generator=gen) / math.sqrt(9 * c)
+    g = make_geom(n, h, w_, c, k, 3, 3, 1, 1, 1)
+    dy = torch.randn(n, h, w_, k, device=DEV, generator=gen)
+    y = kern.conv_fprop(x, w, g, round_tf32=False)
+    a = (y.double() * dy.double()).sum()
+    b = (x.double() * kern.conv_dgrad(dy, w, g, round_tf32=False).double()).sum()
+    c_ = (w.double() * kern.conv_wgrad(dy, x, g).double()).sum()
+    scale = y.double().norm() * dy.double().norm()
+    assert abs(a - b) / scale < 1e-4 and abs(a - c_) / scale < 1e-4
+    # linearity in x
+    y2 = kern.conv_fprop(2.5 * x, w, g, round_tf32=False)
+    assert rel_err(y2, 2.5 * y) < TOL_TF32
+
+
+# ---------------------------------------------------------------------------------- layers and networks
+def _load(mod, params):
+    sd = mod.state_dict()
+    for k in sd:
+        if k in params:
+            sd[k] = params[k].float()
+    mod.load_state_dict(sd)
+    return mod.to(DEV)
+
+
+def test_layers_against_reference_golden():
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    meta, G = load_golden("layers")
+    for i, (cin, cout, k, demod, up) in enumerate(meta["modconv"]):
+        m = _load(L.ModulatedConv2d(cin, cout, k, 16, demodulate=demod, upsample=up),
+                  {"weight": rnd(400 + i, 1, cout, cin, k, k), "modulation.weight": rnd(410 + i, cin, 16),
+                   "modulation.bias": rnd(420 + i, cin) * 0.1 + 1})
+        x = cuda(rnd(430 + i, 2, cin, 6, 7)).requires_grad_()
+        s = cuda(rnd(440 + i, 2, 16)).requires_grad_()
+        y = m(x, s)
+        w = cuda(rnd(450 + i, *y.shape))
+        gx, gs, gw = torch.autograd.grad((y * w).sum(), [x, s, m.weight])
+        for got, key in ((y, "y"), (gx, "gx"), (gs, "gs"), (gw, "gw")):
+            assert rel_err(got, G["modconv%d_%s" % (i, key)]) < TOL_TF32, (i, key)
+    for i, (cin, cout, blur, refl, down) in enumerate(meta["resblock"]):
+        m = _load(L.ResBlock(cin, cout, blur, reflection_pad=refl, downsample=down),
+                  {"conv1.Conv.weight": rnd(500 + i, cin, cin, 3, 3), "conv1.Act.bias": rnd(510 + i, cin) * 0.1,
+                   "conv2.Conv.weight": rnd(520 + i, cout, cin, 3, 3), "conv2.Act.bias": rnd(530 + i, cout) * 0.1,
+                   "skip.Conv.weight": rnd(540 + i, cout, cin, 1, 1)})
+        x = cuda(rnd(550 + i, 2, cin, 10, 10)).requires_grad_()
+        y = m(x)
+        w = cuda(rnd(560 + i, *y.shape))
+        gx, = torch.autograd.grad((y * w).sum(), x, create_graph=True)
+        gg, = torch.autograd.grad(gx.pow(2).sum(), m.conv1.Conv.weight)
+        assert rel_err(y, G["resblock%d_y" % i]) < TOL_TF32
+        assert rel_err(gx, G["resblock%d_gx" % i]) < TOL_TF32
+        assert rel_err(gg, G["resblock%d_gg" % i]) < 2 * TOL_TF32      # three chained TF32 convs
+    for i, up in enumerate([False, True]):
+        m = _load(L.StyledConv(8, 8, 3, 16, upsample=up),
+                  {"conv.weight": rnd(600 + i, 1, 8, 8, 3, 3), "conv.modulation.weight": rnd(610 + i, 8, 16),
+                   "conv.modulation.bias": torch.ones(8), "noise.weight": torch.tensor([0.3]),
+                   "activate.bias": rnd(620 + i, 8) * 0.1})
+        hw = 10 if up else 5
+        y = m(cuda(rnd(630 + i, 2, 8, 5, 5)), cuda(rnd(640 + i, 2, 16)), noise=cuda(rnd(650 + i, 2, 1, hw, hw)))
+        assert rel_err(y, G["styled%d_y" % i]) < TOL_TF32
+    m = _load(L.EqualLinear(16, 8, activation='fused_lrelu'), {"weight": rnd(700, 8, 16), "bias": rnd(701, 8) * 0.1})
+    assert rel_err(m(cuda(rnd(702, 3, 16))), G["linear_act_y"]) < TOL_TF32
+    m = _load(L.EqualLinear(16, 8, bias_init=1), {"weight": rnd(703, 8, 16), "bias": rnd(704, 8)})
+    assert rel_err(m(cuda(rnd(705, 3, 16))), G["linear_y"]) < TOL_TF32
+
+
+def _tiny_product_model(dtype_sd=torch.float32):
+    from swapping_autoencoder_pytorch_b200.model import SwappingAutoencoderModel
+    opt = default_options(**dict(TINY, num_gpus=1))
+    model = SwappingAutoencoderModel(opt)
+    model.initialize()
+    sd = {k: v.float() for k, v in perturbed_state_dict(opt).items()}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected
+    return opt, model
+
+
+def test_networks_against_reference_golden():
+    meta, G = load_golden("networks_tiny")
+    opt, model = _tiny_product_model()
+    real = cuda(rnd(meta["real_seed"], 2, 3, 64, 64).clamp(-1, 1))
+    sp, gl = model.E(real)
+    assert rel_err(sp, G["sp"]) < TOL_NET and rel_err(gl, G["gl"]) < TOL_NET
+    # feed the golden codes so G's error is measured on its own
+    sp_ref, gl_ref = cuda(G["sp"]), cuda(G["gl"])
+    model.G(sp_ref, gl_ref)
+    model.G.fix_and_gather_noise_parameters()
+    mods = dict(model.G.named_modules())
+    for idx, name in enumerate(meta["noise_names"]):
+        mods[name].fixed_noise = torch.nn.Parameter(cuda(rnd(meta["noise_seed0"] + idx, *meta["noise_shapes"][idx])))
+    rec = model.G(sp_ref, gl_ref)
+    assert rel_err(rec, G["rec"]) < TOL_NET, (rel_err(rec, G["rec"]), rel_l2(rec, G["rec"]))
+    assert rel_err(model.D(real), G["d_real"]) < TOL_NET
+    f1 = model.Dpatch.extract_features(cuda(rnd(meta["crop_seeds"][0], 2, 2, 3, 32, 32)), aggregate=True)
+    f2 = model.Dpatch.extract_features(cuda(rnd(meta["crop_seeds"][1], 2, 2, 3, 32, 32)))
+    assert rel_err(f1, G["patch_feat_agg"]) < TOL_NET and rel_err(f2, G["patch_feat"]) < TOL_NET
+    assert rel_err(model.Dpatch.discriminate_features(f1, f2), G["patch_pred"]) < TOL_NET
+
+
+class _CropDraws:
+    """Crop randoms from a private CPU generator, so the oracle (CPU) and the product (GPU) see identical crops no
+    matter what else consumes the global RNG streams."""
+
+    def __init__(self):
+        self.gen = torch.Generator()
+
+    def reseed(self, seed):
+        self.gen.manual_seed(seed)
+
+    def draw(self, b, lo, hi):
+        r = lambda *shape: torch.rand(*shape, generator=self.gen, dtype=torch.float64)
+        flip = torch.round(r(b, 1, 1, 1)) * 2 - 1.0
+        scale = r(b, 1, 1, 2) * (hi - lo) + lo
+        offset = (r(b, 1, 1, 2) * 2 - 1) * (1 - scale)
+        return flip, scale, offset
+
+
+def test_loss_graph_against_oracle(monkeypatch):
+    """D / G / R1 losses and an R1 gradient (double backward through conv / FIR / bias-act / linear kernels)."""
+    from swapping_autoencoder_pytorch_b200 import util
+    opt, model = _tiny_product_model()
+    copt = default_options(**TINY)
+    oracle = O.OracleModel(copt, perturbed_state_dict(copt))
+    real = rnd(900, 2, 3, 64, 64).clamp(-1, 1)
+    draws = _CropDraws()
+    monkeypatch.setattr(O, "draw_crop_parameters", lambda b, o: draws.draw(b, o.patch_min_scale, o.patch_max_scale))
+    monkeypatch.setattr(util, "draw_crop_parameters",
+                        lambda b, sr, device: tuple(t.float().to(device) for t in draws.draw(b, sr[0], sr[1])))
+    # generator noise cannot be reproduced across CPU / CUDA generators: silence it on both sides
+    for k in list(oracle.G):
+        if k.endswith("noise.weight"):
+            oracle.G[k] = torch.zeros_like(oracle.G[k])
+    for n, p in model.G.named_parameters():
+        if n.endswith("noise.weight"):
+            p.data.zero_()
+
+    realg = cuda(real)
+    draws.reseed(1)
+    ref_d = oracle.discriminator_losses(real)
+    draws.reseed(1)
+    got_d, _, _, _ = model(realg, command="compute_discriminator_losses")
+    for k, v in got_d.items():
+        assert rel_err(v, ref_d[k]) < TOL_NET, (k, v, ref_d[k])
+
+    draws.reseed(2)
+    ref_g = oracle.generator_losses(real)
+    draws.reseed(2)
+    got_g, _ = model(realg, None, None, command="compute_generator_losses")
+    for k, v in got_g.items():
+        assert rel_err(v, ref_g[k]) < TOL_NET, (k, v, ref_g[k])
+
+    wD = oracle.D["stylegan2_D.convs.3.conv1.Conv.weight"].requires_grad_()
+    wP = oracle.Dp["convs.2.conv2.Conv.weight"].requires_grad_()
+    draws.reseed(3)
+    ref_r1 = oracle.r1_loss(real)["D_R1"]
+    ref_gD, ref_gP = torch.autograd.grad(ref_r1.mean(), [wD, wP])
+    draws.reseed(3)
+    r1 = model(realg.clone(), command="compute_R1_loss")["D_R1"]
+    assert rel_err(r1, ref_r1) < 2 * TOL_NET, (r1, ref_r1)
+    gD, gP = torch.autograd.grad(r1.mean(), [model.D.stylegan2_D.convs[1].conv1.Conv.weight,
+                                             model.Dpatch.convs[1].conv2.Conv.weight])
+    assert rel_l2(gD, ref_gD) < 5e-3, rel_l2(gD, ref_gD)
+    assert rel_l2(gP, ref_gP) < 5e-3, rel_l2(gP, ref_gP)
+
+
+def test_train_steps_default_nets_256():
+    """BASELINE config 2 shape (256x256, default nets) at a small batch: D step with R1, then G step."""
+    import swapping_autoencoder_pytorch_b200 as S
+    opt = default_options(num_gpus=1, batch_size=2, R1_once_every=1)
+    torch.manual_seed(0)
+    model = S.create_model(opt)
+    trainer = S.create_optimizer(opt, model)
+    real = torch.randn(2, 3, 256, 256, device=DEV).clamp(-1, 1)
+    n0 = backend._lib.launch_count()
+    d = trainer.train_one_step({"real_A": real}, 0)
+    g = trainer.train_one_step({"real_A": real}, 0)
+    assert backend._lib.launch_count() - n0 > 500
+    for k in ("D_real", "D_rec", "D_mix", "PatchD_real", "PatchD_mix", "D_R1", "D_total"):
+        assert k in d and math.isfinite(float(d[k])), (k, d)
+    for k in ("G_L1", "G_GAN_rec", "G_GAN_mix", "G_mix", "L1_dist"):
+        assert k in g and math.isfinite(float(g[k])), (k, g)
+    # first-iteration losses at init are ~softplus(0)=0.69-ish; guard against blow-ups
+    assert 0.05 < float(d["D_real"]) < 5 and 0.05 < float(g["G_GAN_mix"]) < 5

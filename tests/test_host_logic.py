@@ -1,0 +1,192 @@
+"""CPU: the product's host-side logic (autograd Functions incl. double backward, layer wiring, state_dict contract,
+loss graph) on an oracle-backed emulation of the kernel interface, against the reference's golden numbers (fp64)."""
+import pytest
+import torch
+
+from oracle.fixtures import TINY, load_golden, perturbed_state_dict, rel_err, rnd
+from swapping_autoencoder_pytorch_b200 import default_options
+
+TOL = 1e-9
+pytestmark = pytest.mark.usefixtures("emulated_kernels")
+
+
+def _load(mod, params):
+    mod.double()
+    sd = mod.state_dict()
+    for k in sd:
+        if k in params:
+            sd[k] = params[k].double()
+    mod.load_state_dict(sd)
+    return mod
+
+
+def test_upfirdn2d_first_and_second_order():
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
+    from swapping_autoencoder_pytorch_b200.stylegan2_layers import make_kernel
+    meta, G = load_golden("ops_upfirdn2d")
+    for i, c in enumerate(meta["cases"]):
+        k = make_kernel(c["taps"]).double() * c["gain"]
+        x = rnd(meta["x_seed0"] + i, *meta["shape"]).requires_grad_()
+        y = upfirdn2d(x, k, up=c["up"], down=c["down"], pad=tuple(c["pad"]))
+        assert rel_err(y, G["y%d" % i]) < TOL, c
+        w = rnd(meta["w_seed0"] + i, *y.shape).requires_grad_()
+        gx, = torch.autograd.grad((y * w).sum(), x, create_graph=True)
+        assert rel_err(gx, G["gx%d" % i]) < TOL, c
+        # backward-of-backward: d/dw sum(gx * v) must equal upfirdn2d(v)
+        v = rnd(77 + i, *x.shape)
+        gw, = torch.autograd.grad((gx * v).sum(), w)
+        assert rel_err(gw, upfirdn2d(v, k, up=c["up"], down=c["down"], pad=tuple(c["pad"]))) < TOL, c
+
+
+def test_fused_leaky_relu_first_and_second_order():
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import fused_leaky_relu
+    from oracle import sae_oracle as O
+    meta, G = load_golden("ops_fused_leaky_relu")
+    for i, shape in enumerate(meta["shapes"]):
+        x = rnd(meta["x_seed0"] + i, *shape).requires_grad_()
+        b = rnd(meta["b_seed0"] + i, shape[1]).requires_grad_()
+        y = fused_leaky_relu(x, b)
+        w = rnd(meta["w_seed0"] + i, *shape).requires_grad_()
+        gx, gb = torch.autograd.grad((y * w).sum(), [x, b], create_graph=True)
+        assert rel_err(y, G["y%d" % i]) < TOL and rel_err(gx, G["gx%d" % i]) < TOL and rel_err(gb, G["gb%d" % i]) < TOL
+        # second order against plain autograd through the oracle formulation
+        x2 = x.detach().clone().requires_grad_()
+        b2 = b.detach().clone().requires_grad_()
+        w2 = w.detach().clone().requires_grad_()
+        gx2, gb2 = torch.autograd.grad((O.fused_leaky_relu(x2, b2) * w2).sum(), [x2, b2], create_graph=True)
+        u, ub = rnd(55 + i, *shape), rnd(56 + i, shape[1])
+        gw, = torch.autograd.grad((gx * u).sum() + (gb * ub).sum(), w)
+        gw2, = torch.autograd.grad((gx2 * u).sum() + (gb2 * ub).sum(), w2)
+        assert rel_err(gw, gw2) < TOL
+
+
+def test_conv_family_gradcheck():
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import conv2d, conv_transpose2d, linear
+    x = rnd(1, 2, 3, 6, 5).requires_grad_()
+    w = rnd(2, 4, 3, 3, 3).requires_grad_()
+    for stride, pad in ((1, 1), (2, 0), (1, 0), (2, 1)):
+        assert torch.autograd.gradcheck(lambda a, b: conv2d(a, b, stride=stride, padding=pad), (x, w), atol=1e-7)
+        assert torch.autograd.gradgradcheck(lambda a, b: conv2d(a, b, stride=stride, padding=pad), (x, w), atol=1e-7)
+        ref = torch.nn.functional.conv2d(x, w, stride=stride, padding=pad)
+        assert rel_err(conv2d(x, w, stride=stride, padding=pad), ref) < TOL
+    wt = rnd(3, 3, 4, 3, 3).requires_grad_()
+    assert rel_err(conv_transpose2d(x, wt, stride=2, padding=0),
+                   torch.nn.functional.conv_transpose2d(x, wt, stride=2, padding=0)) < TOL
+    assert torch.autograd.gradcheck(lambda a, b: conv_transpose2d(a, b), (x, wt), atol=1e-7)
+    assert torch.autograd.gradgradcheck(lambda a, b: conv_transpose2d(a, b), (x, wt), atol=1e-7)
+    xl, wl = rnd(4, 3, 7).requires_grad_(), rnd(5, 5, 7).requires_grad_()
+    assert rel_err(linear(xl, wl), torch.nn.functional.linear(xl, wl)) < TOL
+    assert torch.autograd.gradcheck(linear, (xl, wl), atol=1e-7)
+
+
+def test_layers_against_reference():
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    meta, G = load_golden("layers")
+    for i, (cin, cout, k, demod, up) in enumerate(meta["modconv"]):
+        m = _load(L.ModulatedConv2d(cin, cout, k, 16, demodulate=demod, upsample=up),
+                  {"weight": rnd(400 + i, 1, cout, cin, k, k), "modulation.weight": rnd(410 + i, cin, 16),
+                   "modulation.bias": rnd(420 + i, cin) * 0.1 + 1})
+        x = rnd(430 + i, 2, cin, 6, 7).requires_grad_()
+        s = rnd(440 + i, 2, 16).requires_grad_()
+        y = m(x, s)
+        w = rnd(450 + i, *y.shape)
+        gx, gs, gw = torch.autograd.grad((y * w).sum(), [x, s, m.weight])
+        for got, key in ((y, "y"), (gx, "gx"), (gs, "gs"), (gw, "gw")):
+            assert rel_err(got, G["modconv%d_%s" % (i, key)]) < TOL, (i, key)
+    for i, (cin, cout, blur, refl, down) in enumerate(meta["resblock"]):
+        m = _load(L.ResBlock(cin, cout, blur, reflection_pad=refl, downsample=down),
+                  {"conv1.Conv.weight": rnd(500 + i, cin, cin, 3, 3), "conv1.Act.bias": rnd(510 + i, cin) * 0.1,
+                   "conv2.Conv.weight": rnd(520 + i, cout, cin, 3, 3), "conv2.Act.bias": rnd(530 + i, cout) * 0.1,
+                   "skip.Conv.weight": rnd(540 + i, cout, cin, 1, 1)})
+        x = rnd(550 + i, 2, cin, 10, 10).requires_grad_()
+        y = m(x)
+        w = rnd(560 + i, *y.shape)
+        gx, = torch.autograd.grad((y * w).sum(), x, create_graph=True)
+        gg, = torch.autograd.grad(gx.pow(2).sum(), m.conv1.Conv.weight)
+        assert rel_err(y, G["resblock%d_y" % i]) < TOL
+        assert rel_err(gx, G["resblock%d_gx" % i]) < TOL
+        assert rel_err(gg, G["resblock%d_gg" % i]) < TOL
+    for i, up in enumerate([False, True]):
+        m = _load(L.StyledConv(8, 8, 3, 16, upsample=up),
+                  {"conv.weight": rnd(600 + i, 1, 8, 8, 3, 3), "conv.modulation.weight": rnd(610 + i, 8, 16),
+                   "conv.modulation.bias": torch.ones(8), "noise.weight": torch.tensor([0.3], dtype=torch.float64),
+                   "activate.bias": rnd(620 + i, 8) * 0.1})
+        hw = 10 if up else 5
+        y = m(rnd(630 + i, 2, 8, 5, 5), rnd(640 + i, 2, 16), noise=rnd(650 + i, 2, 1, hw, hw))
+        assert rel_err(y, G["styled%d_y" % i]) < TOL
+    m = _load(L.EqualLinear(16, 8, activation='fused_lrelu'), {"weight": rnd(700, 8, 16), "bias": rnd(701, 8) * 0.1})
+    assert rel_err(m(rnd(702, 3, 16)), G["linear_act_y"]) < TOL
+    m = _load(L.EqualLinear(16, 8, bias_init=1), {"weight": rnd(703, 8, 16), "bias": rnd(704, 8)})
+    assert rel_err(m(rnd(705, 3, 16)), G["linear_y"]) < TOL
+
+
+def _tiny_product_model():
+    from swapping_autoencoder_pytorch_b200.model import SwappingAutoencoderModel
+    opt = default_options(**TINY)
+    model = SwappingAutoencoderModel(opt)
+    model.initialize()
+    model.double()
+    missing, unexpected = model.load_state_dict(perturbed_state_dict(opt), strict=False)
+    assert not unexpected
+    assert all(k.endswith(".kernel") or k == "num_discriminator_iters" for k in missing), missing
+    return opt, model
+
+
+def test_networks_against_reference():
+    meta, G = load_golden("networks_tiny")
+    opt, model = _tiny_product_model()
+    real = rnd(meta["real_seed"], 2, 3, 64, 64).clamp(-1, 1)
+    sp, gl = model.E(real)
+    assert rel_err(sp, G["sp"]) < TOL and rel_err(gl, G["gl"]) < TOL
+    model.G(sp, gl)
+    model.G.fix_and_gather_noise_parameters()
+    mods = dict(model.G.named_modules())
+    for idx, name in enumerate(meta["noise_names"]):
+        mods[name].fixed_noise = torch.nn.Parameter(rnd(meta["noise_seed0"] + idx, *meta["noise_shapes"][idx]))
+    assert rel_err(model.G(sp, gl), G["rec"]) < TOL
+    assert rel_err(model.D(real), G["d_real"]) < TOL
+    f1 = model.Dpatch.extract_features(rnd(meta["crop_seeds"][0], 2, 2, 3, 32, 32), aggregate=True)
+    f2 = model.Dpatch.extract_features(rnd(meta["crop_seeds"][1], 2, 2, 3, 32, 32))
+    assert rel_err(f1, G["patch_feat_agg"]) < TOL and rel_err(f2, G["patch_feat"]) < TOL
+    assert rel_err(model.Dpatch.discriminate_features(f1, f2), G["patch_pred"]) < TOL
+
+
+def test_loss_graph_against_reference(fp64_default):
+    meta, G = load_golden("losses_tiny")
+    opt, model = _tiny_product_model()
+    real = rnd(meta["real_seed"], 2, 3, 64, 64).clamp(-1, 1)
+    torch.manual_seed(meta["seeds"]["D"])
+    dl, _, sp, gl = model(real, command="compute_discriminator_losses")
+    for k, v in dl.items():
+        assert rel_err(v, G["D/" + k]) < 1e-8, k
+    torch.manual_seed(meta["seeds"]["G"])
+    gl_, gm = model(real, None, None, command="compute_generator_losses")
+    for k, v in gl_.items():
+        assert rel_err(v, G["G/" + k]) < 1e-8, k
+    torch.manual_seed(meta["seeds"]["R1"])
+    r1 = model(real.clone(), command="compute_R1_loss")["D_R1"]
+    assert rel_err(r1, G["R1/D_R1"]) < 1e-8
+    g, gp = torch.autograd.grad(r1.mean(), [model.D.stylegan2_D.convs[1].conv1.Conv.weight,
+                                            model.Dpatch.convs[1].conv2.Conv.weight])
+    assert rel_err(g, G["R1/grad_D_convs1_conv1"]) < 1e-7
+    assert rel_err(gp, G["R1/grad_Dpatch_convs1_conv2"]) < 1e-7
+
+
+def test_train_steps_run_and_alternate(fp64_default):
+    from swapping_autoencoder_pytorch_b200.optimizer import SwappingAutoencoderOptimizer
+    from swapping_autoencoder_pytorch_b200.parallel import MultiGPUModelWrapper
+    opt, model = _tiny_product_model()
+    opt.R1_once_every = 1
+    wrapped = MultiGPUModelWrapper(opt, model)
+    trainer = SwappingAutoencoderOptimizer(wrapped)
+    real = rnd(3, 2, 3, 64, 64).clamp(-1, 1)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    d = trainer.train_one_step({"real_A": real}, 0)
+    assert "D_total" in d and "D_R1" in d and "PatchD_real" in d
+    changed = {k for k, v in model.state_dict().items() if not torch.equal(v, before[k])}
+    assert any(k.startswith("D.") for k in changed) and any(k.startswith("Dpatch.") for k in changed)
+    assert not any(k.startswith("G.") or k.startswith("E.") for k in changed)
+    g = trainer.train_one_step({"real_A": real}, 0)
+    assert "G_L1" in g and "G_GAN_mix" in g and "L1_dist" in g
+    changed2 = {k for k, v in model.state_dict().items() if not torch.equal(v, before[k])}
+    assert any(k.startswith("G.") for k in changed2) and any(k.startswith("E.") for k in changed2)
