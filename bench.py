@@ -86,7 +86,8 @@ def cpu_step_rate(steps, warmup, batch=CPU_SAMPLE_BATCH, threads=None):
     """Reference CPU path (oracle port of the native-PyTorch fallback): D/G half-steps at 256x256, default nets."""
     from oracle import sae_oracle as O
     from swapping_autoencoder_pytorch_b200 import default_options
-    threads = threads or os.cpu_count() or 1
+    # all host cores up to 32: beyond that the reference's many small ATen ops only lose time to oversubscription
+    threads = threads or min(os.cpu_count() or 1, 32)
     torch.set_num_threads(threads)
     opt = default_options(num_gpus=0, batch_size=batch, crop_size=RES)
     model = O.OracleModel(opt, O.init_state_dict(opt, seed=0))

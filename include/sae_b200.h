@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 3
+#define SAE_ABI_VERSION 4
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -49,13 +49,16 @@ int         sae_tcgen05_available(void);
  * (upfirdn2d.py:108-109).  Unlike the reference there is no mode table: every
  * (up, down, kh, kw <= 32) combination is handled by the same kernel.  Negative pads crop.
  * 64-bit indexing throughout (the reference overflows int32 at >= 2^31 elements).
+ * round_tf32 (here and below): when non-zero the result is rounded to the nearest TF32 value before it is stored
+ * (still an fp32 array).  The tensor-core convolutions read operands at TF32 precision by IGNORING the low 13
+ * mantissa bits; rounding-to-nearest in the producer makes that truncation exact and unbiased.
  * ------------------------------------------------------------------------------------------ */
 int sae_upfirdn2d(const float* input, const float* kernel, float* out,
                   int64_t major, int in_h, int in_w, int minor,
                   int kernel_h, int kernel_w,
                   int up_x, int up_y, int down_x, int down_y,
                   int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                  void* stream);
+                  int round_tf32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * fused_bias_act — out = act(x + b[(i / step_b) % size_b]) * scale.
@@ -71,7 +74,7 @@ int sae_fused_bias_act(const float* x, const float* bias, const float* ref, floa
                        int64_t size_x, int64_t step_b, int size_b,
                        int act, int grad, float alpha, float scale,
                        const float* noise, const float* noise_weight, int64_t noise_div,
-                       void* stream);
+                       int round_tf32, void* stream);
 
 /* Backward of the above in one pass: grad_in = grad_out * (out > 0 ? 1 : alpha) * scale and,
  * fused, grad_bias[c] += sum over everything but the bias dim (the reference runs a separate
@@ -82,7 +85,7 @@ int sae_fused_bias_act(const float* x, const float* bias, const float* ref, floa
 int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_in, float* grad_bias,
                           int64_t size_x, int size_b, float alpha, float scale,
                           const float* noise, int64_t noise_div, float* grad_noise_weight,
-                          void* stream);
+                          int round_tf32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * modulate — x_s[n,h,w,c] = x[n,h,w,c] * s[n,c]: the "input * style" step of
@@ -94,7 +97,13 @@ int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_i
 int sae_modulate(const float* x, const float* s, float* out,
                  int n, int64_t hw, int c, int round_tf32, void* stream);
 int sae_modulate_backward(const float* dy, const float* x, const float* s, float* dx, float* ds,
-                          int n, int64_t hw, int c, void* stream);
+                          int n, int64_t hw, int c, int round_tf32, void* stream);
+
+/* out = (a + b) * scale — the residual merge "(out + skip) / sqrt(2)" of ResBlock (stylegan2_layers.py:691) and of the
+ * generator blocks (generator.py:36,53) in one pass; b == NULL gives out = a * scale (its backward).
+ * sae_round_tf32: out = rna_tf32(x) (used on the small filter tensors before a tensor-core conv). */
+int sae_add_scale(const float* a, const float* b, float* out, int64_t n, float scale, int round_tf32, void* stream);
+int sae_round_tf32(const float* x, float* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * conv2d — dense implicit-GEMM convolution family on NHWC fp32 activations, TF32 tensor cores,

@@ -53,7 +53,10 @@ class CudaKernels:
     def __init__(self):
         self.lib = _lib.load()
         self.conv_impl = 0       # 0 auto, 1 force generic (mma.sync), 2 force tcgen05
-        self.round_tf32 = True   # producers round to TF32 so the tensor-core truncation is exact
+        # Every activation / gradient / filter this library writes is rounded to the nearest TF32 value (still stored
+        # as fp32): the tensor cores ignore the low 13 mantissa bits of their operands, so rounding in the producer
+        # makes that truncation exact and unbiased.  Set False for bit-exact fp32 results from the pointwise kernels.
+        self.round_tf32 = True
 
     # ------------------------------------------------------------------ FIR
     def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
@@ -65,7 +68,8 @@ class CudaKernels:
         out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
         with torch.cuda.device(x.device):
             check(self.lib.sae_upfirdn2d(_ptr(x), _ptr(kernel), _ptr(out), n, h, w, c, kh, kw, up_x, up_y,
-                                         down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, _stream()), "sae_upfirdn2d")
+                                         down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, int(self.round_tf32), _stream()),
+                  "sae_upfirdn2d")
         return out
 
     # ------------------------------------------------------------- bias/act
@@ -77,7 +81,8 @@ class CudaKernels:
         with torch.cuda.device(x.device):
             check(self.lib.sae_fused_bias_act(_ptr(x), _ptr(bias), _ptr(ref), _ptr(out), x.numel(), 1,
                                               bias.numel() if bias is not None else 1, act, grad, alpha, scale,
-                                              _ptr(noise), _ptr(noise_weight), c, _stream()), "sae_fused_bias_act")
+                                              _ptr(noise), _ptr(noise_weight), c, int(self.round_tf32), _stream()),
+                  "sae_fused_bias_act")
         return out
 
     def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None):
@@ -88,7 +93,7 @@ class CudaKernels:
         gnw = torch.zeros(1, device=out.device, dtype=out.dtype) if noise is not None else None
         with torch.cuda.device(out.device):
             check(self.lib.sae_bias_act_backward(_ptr(grad_out), _ptr(out), _ptr(gi), _ptr(gb), out.numel(), c,
-                                                 alpha, scale, _ptr(noise), c, _ptr(gnw), _stream()),
+                                                 alpha, scale, _ptr(noise), c, _ptr(gnw), int(self.round_tf32), _stream()),
                   "sae_bias_act_backward")
         return gi, gb, gnw
 
@@ -109,8 +114,28 @@ class CudaKernels:
         ds = torch.zeros_like(s)
         with torch.cuda.device(x.device):
             check(self.lib.sae_modulate_backward(_ptr(dy), _ptr(x), _ptr(s), _ptr(dx), _ptr(ds), n, h * w, c,
-                                                 _stream()), "sae_modulate_backward")
+                                                 int(self.round_tf32), _stream()), "sae_modulate_backward")
         return dx, ds
+
+    # ------------------------------------------------------- residual merge
+    def add_scale(self, a, b, scale):
+        """(a + b) * scale, or a * scale when b is None; any shape, a and b contiguous with identical layout"""
+        _need_cuda(a, b)
+        out = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            check(self.lib.sae_add_scale(_ptr(a), _ptr(b), _ptr(out), a.numel(), scale, int(self.round_tf32), _stream()),
+                  "sae_add_scale")
+        return out
+
+    def _filter(self, w):
+        """contiguous copy of a (small) filter tensor, rounded to TF32 when the policy says so"""
+        w = w.contiguous()
+        if not self.round_tf32:
+            return w
+        out = torch.empty_like(w)
+        with torch.cuda.device(w.device):
+            check(self.lib.sae_round_tf32(_ptr(w), _ptr(out), w.numel(), _stream()), "sae_round_tf32")
+        return out
 
     # ----------------------------------------------------------------- conv
     def _epi(self, bias=None, act=1, alpha=0.2, gain=1.0, noise=None, noise_weight=None, residual=None,
@@ -125,40 +150,41 @@ class CudaKernels:
         e.round_tf32 = int(self.round_tf32 if round_tf32 is None else round_tf32)
         return e
 
-    def conv_fprop(self, x, w_krsc, g, **epi):
+    def conv_fprop(self, x, w_krsc, g, impl=None, **epi):
         """x [N,H,W,C], w [K,R,S,C] -> y [N,P,Q,K]"""
         _need_cuda(x, w_krsc)
+        w_krsc = self._filter(w_krsc)
         assert tuple(x.shape) == (g.N, g.H, g.W, g.C) and tuple(w_krsc.shape) == (g.K, g.R, g.S, g.C), \
             (tuple(x.shape), tuple(w_krsc.shape), g.key())
         y = torch.empty((g.N, g.P, g.Q, g.K), device=x.device, dtype=x.dtype)
         e = self._epi(**epi)
         with torch.cuda.device(x.device):
             check(self.lib.sae_conv2d_fprop(_ptr(x), _ptr(w_krsc), _ptr(y), ctypes.byref(g), ctypes.byref(e),
-                                            self.conv_impl, _stream()), "sae_conv2d_fprop")
+                                            self.conv_impl if impl is None else impl, _stream()), "sae_conv2d_fprop")
         return y
 
-    def conv_dgrad(self, dy, w_krsc, g, **epi):
+    def conv_dgrad(self, dy, w_krsc, g, impl=None, **epi):
         """dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C] (also the forward of the transposed convolution)."""
         _need_cuda(dy, w_krsc)
         assert tuple(dy.shape) == (g.N, g.P, g.Q, g.K) and tuple(w_krsc.shape) == (g.K, g.R, g.S, g.C), \
             (tuple(dy.shape), tuple(w_krsc.shape), g.key())
-        wt = w_krsc.permute(3, 1, 2, 0).contiguous()      # [C,R,S,K]: tiny, stays in L2
+        wt = self._filter(w_krsc.permute(3, 1, 2, 0))     # [C,R,S,K]: tiny, stays in L2
         dx = torch.empty((g.N, g.H, g.W, g.C), device=dy.device, dtype=dy.dtype)
         e = self._epi(**epi)
         with torch.cuda.device(dy.device):
             check(self.lib.sae_conv2d_dgrad(_ptr(dy), _ptr(wt), _ptr(dx), ctypes.byref(g), ctypes.byref(e),
-                                            self.conv_impl, _stream()), "sae_conv2d_dgrad")
+                                            self.conv_impl if impl is None else impl, _stream()), "sae_conv2d_dgrad")
         return dx
 
-    def conv_wgrad(self, dy, x, g):
+    def conv_wgrad(self, dy, x, g, impl=None):
         """dy [N,P,Q,K], x [N,H,W,C] -> dw [K,R,S,C]"""
         _need_cuda(dy, x)
         assert tuple(dy.shape) == (g.N, g.P, g.Q, g.K) and tuple(x.shape) == (g.N, g.H, g.W, g.C), \
             (tuple(dy.shape), tuple(x.shape), g.key())
         dw = torch.zeros((g.K, g.R, g.S, g.C), device=dy.device, dtype=dy.dtype)
         with torch.cuda.device(dy.device):
-            check(self.lib.sae_conv2d_wgrad(_ptr(dy), _ptr(x), _ptr(dw), ctypes.byref(g), self.conv_impl, _stream()),
-                  "sae_conv2d_wgrad")
+            check(self.lib.sae_conv2d_wgrad(_ptr(dy), _ptr(x), _ptr(dw), ctypes.byref(g),
+                                            self.conv_impl if impl is None else impl, _stream()), "sae_conv2d_wgrad")
         return dw
 
     def conv_impl_for(self, g, direction):

@@ -1,11 +1,411 @@
-// placeholder until the tcgen05 kernel lands
-#include "conv_internal.cuh"
+// Implicit-GEMM convolution on the 5th-generation tensor cores: TMA-fed tcgen05.mma (kind::tf32), fp32
+// accumulators in TMEM, fused epilogue, TMA store.  sm_100a only.
+//
+//   y[n,p,q,k] = sum_{tap t} sum_c  src[n, p*st + oy_t, q*st + ox_t, c] * wmat[k, t*C + c]
+//
+// GEMM view: M = output pixels, N = output channels, K = taps x channels.  One CTA computes a
+// 128 (pixels) x BLOCK_N (channels) tile:
+//   * the 128 pixels are a (tn x th x tw) box of the NHWC output; for tap t the matching A tile is the SAME box of
+//     the input shifted by (oy_t, ox_t) — fetched with ONE 4-D TMA (box 32ch x tw x th x tn, element stride = conv
+//     stride), out-of-bounds rows/columns zero-filled by the TMA unit (that is the conv's zero padding), landing in
+//     shared memory directly in the K-major 128-byte-swizzled layout tcgen05 consumes: no im2col buffer, no
+//     register staging;
+//   * B tile = 32 (k) x BLOCK_N rows of the [Cout, taps*C] filter matrix, 2-D TMA, same swizzle;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2..5 = epilogue
+//     (tcgen05.ld 32 lanes x 32 columns per warp -> bias / noise / leaky-ReLU / residual / TF32 rounding -> swizzled
+//     staging -> TMA store, which also clips ragged tile edges);
+//   * STAGES-deep mbarrier ring (full/empty), tcgen05.commit releases a stage as soon as its MMAs retire.
+// fprop uses it with taps (r - pad_t, s - pad_l); stride-1 dgrad with taps (pad_t - r, pad_l - s) over dy and the
+// [C, R*S*K] transposed filter.  Operands are consumed at TF32 precision (low 13 mantissa bits ignored by the tensor
+// core); producers in this library round-to-nearest to TF32 so that this truncation is exact.
+#include "tc_common.cuh"
+#include <mutex>
+
 namespace sae {
-bool tc_available() { return false; }
-bool tc_fprop_eligible(const sae_conv_geom*) { return false; }
-bool tc_dgrad_eligible(const sae_conv_geom*) { return false; }
-bool tc_wgrad_eligible(const sae_conv_geom*) { return false; }
-int tc_fprop(const float*, const float*, float*, const sae_conv_geom*, const EpiParams&, cudaStream_t) { return fail(SAE_E_UNSUPPORTED, "tcgen05 path not built"); }
-int tc_dgrad(const float*, const float*, float*, const sae_conv_geom*, const EpiParams&, cudaStream_t) { return fail(SAE_E_UNSUPPORTED, "tcgen05 path not built"); }
-int tc_wgrad(const float*, const float*, float*, const sae_conv_geom*, cudaStream_t) { return fail(SAE_E_UNSUPPORTED, "tcgen05 path not built"); }
+
+// ------------------------------------------------------------------------------------------------ host: driver API
+EncodeTiledFn g_encode = nullptr;
+static bool g_tc_ok = false;
+
+static void tc_init_once() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
+        if (prop.major != 10) return;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess) return;
+        if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return;
+        g_encode = (EncodeTiledFn)fn;
+        const char* off = getenv("SAE_DISABLE_TCGEN05");
+        g_tc_ok = !(off && off[0] == '1');
+    });
 }
+
+bool tc_available() {
+    tc_init_once();
+    return g_tc_ok;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+constexpr int TC_MAX_TAPS = 16;
+constexpr int TC_THREADS = 192;
+constexpr int TC_BK = 32;                      // fp32 elements per K block = one 128-byte swizzle row
+constexpr int TC_A_BYTES = 128 * TC_BK * 4;    // 16 KB
+
+struct TcParams {
+    int num_cblk;                 // source channels / 32
+    int ntaps;
+    int stride;
+    int tw, th, tn;               // output tile box (tw*th*tn == 128)
+    int tiles_w, tiles_h, tiles_n;
+    int ON, OH, OW, Ncol;         // output [ON, OH, OW, Ncol]
+    int src_c;                    // source channels
+    int o_mul, o_offy, o_offx;    // output sub-grid -> full-resolution pixel (strided outputs of transposed conv)
+    int FH, FW;                   // full-resolution output extent (for noise / residual addressing)
+    signed char oy[TC_MAX_TAPS], ox[TC_MAX_TAPS];
+    int wk[TC_MAX_TAPS];          // K offset of the tap's filter slice inside a wmat row
+    EpiParams epi;
+};
+
+template <int BLOCK_N>
+constexpr int tc_stages() { return BLOCK_N >= 256 ? 4 : (BLOCK_N == 128 ? 4 : 6); }
+
+template <int BLOCK_N>
+constexpr size_t tc_smem_bytes() {
+    // stage ring (A + B per stage); the epilogue staging (BLOCK_N/32 chunks of 16 KB) reuses it after the main loop.
+    size_t ring = (size_t)tc_stages<BLOCK_N>() * (TC_A_BYTES + BLOCK_N * 128);
+    size_t epi = (size_t)(BLOCK_N / 32) * TC_A_BYTES;
+    return (ring > epi ? ring : epi) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+    constexpr int STAGES = tc_stages<BLOCK_N>();
+    constexpr int B_BYTES = BLOCK_N * 128;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    // instruction descriptor: D fp32, A/B tf32, both K-major, N = BLOCK_N, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-byte alignment
+    constexpr uint32_t RING = (uint32_t)STAGES * STAGE_BYTES;
+    constexpr uint32_t EPI = (uint32_t)(BLOCK_N / 32) * TC_A_BYTES;
+    constexpr uint32_t BAR_OFF = RING > EPI ? RING : EPI;
+    const uint32_t bar_full = base + BAR_OFF;                          // STAGES x 8 bytes
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_acc = bar_empty + 8 * STAGES;
+    const uint32_t tmem_slot = bar_acc + 8;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));       // generic pointer to the aligned base
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int tile = blockIdx.x;
+    const int tq = tile % p.tiles_w; tile /= p.tiles_w;
+    const int tp = tile % p.tiles_h; tile /= p.tiles_h;
+    const int tnb = tile;
+    const int q0 = tq * p.tw, p0 = tp * p.th, n0 = tnb * p.tn;
+    const int col0 = blockIdx.y * BLOCK_N;
+    const int KB = p.ntaps * p.num_cblk;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (elect_one()) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                const int t = kb / p.num_cblk, cb = kb - t * p.num_cblk;
+                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+                mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                tma_load_4d(sa, &map_src, bar_full + 8 * s, cb * TC_BK, q0 * p.stride + p.ox[t], p0 * p.stride + p.oy[t], n0);
+                tma_load_2d(sb, &map_w, bar_full + 8 * s, p.wk[t] + cb * TC_BK, col0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (elect_one()) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(bar_full + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+            umma_commit(bar_acc);
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;                 // tile row == TMEM lane
+        const int iw = row % p.tw, ih = (row / p.tw) % p.th, in_ = row / (p.tw * p.th);
+        const int n = n0 + in_, pp = p0 + ih, qq = q0 + iw;
+        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
+        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float nz = 0.f;
+        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+            const int colb = col0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float t = v[j];
+                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
+                t += nz;
+                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
+                t *= p.epi.gain;
+                v[j] = t;
+            }
+            if (p.epi.residual && valid) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 r = __ldg(r4 + j);
+                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
+                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
+                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
+                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
+                }
+            }
+            if (p.epi.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+            }
+            // staging tile for this 32-column chunk: [128 rows][128 bytes], 16-byte chunks XOR-swizzled by (row & 7)
+            uint8_t* stg = smem_gen + (size_t)ch * TC_A_BYTES + (size_t)row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                tma_store_4d(&map_out, base + (uint32_t)ch * TC_A_BYTES, colb, q0, p0, n0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle) {
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SAE_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SAE_OK;
+}
+
+struct TcProblem {
+    const float* src; int SN, SH, SW, SC;      // source activation [SN,SH,SW,SC]
+    const float* wmat; int Ncol, Ktot;          // filter matrix [Ncol, Ktot = ntaps*SC]
+    float* out; int OH, OW;                     // output sub-grid [SN, OH, OW, Ncol] ...
+    int o_mul, o_offy, o_offx, FH, FW;          // ... placed at (o_mul*p + o_offy, o_mul*q + o_offx) of the full [SN,FH,FW,Ncol]
+    int stride, ntaps;
+    int oy[TC_MAX_TAPS], ox[TC_MAX_TAPS], wk[TC_MAX_TAPS];
+};
+
+static bool tc_shape_ok(int src_c, int ncol, int ntaps, int stride, int ow) {
+    if (src_c % 32 != 0 || ncol % 32 != 0) return false;
+    if (ntaps < 1 || ntaps > TC_MAX_TAPS) return false;
+    if (stride != 1 && stride != 2) return false;
+    int tw = pow2_ceil(ow) < 16 ? pow2_ceil(ow) : 16;
+    if (tw * stride > 256) return false;
+    return true;
+}
+
+template <int BLOCK_N>
+static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    TcParams p;
+    p.num_cblk = pr.SC / 32;
+    p.ntaps = pr.ntaps;
+    p.stride = pr.stride;
+    p.tw = pow2_ceil(pr.OW) < 16 ? pow2_ceil(pr.OW) : 16;
+    int th = 128 / p.tw;
+    if (pow2_ceil(pr.OH) < th) th = pow2_ceil(pr.OH);
+    p.th = th;
+    p.tn = 128 / (p.tw * p.th);
+    p.tiles_w = (pr.OW + p.tw - 1) / p.tw;
+    p.tiles_h = (pr.OH + p.th - 1) / p.th;
+    p.tiles_n = (pr.SN + p.tn - 1) / p.tn;
+    p.ON = pr.SN; p.OH = pr.OH; p.OW = pr.OW; p.Ncol = pr.Ncol; p.src_c = pr.SC;
+    for (int t = 0; t < pr.ntaps; ++t) { p.oy[t] = (signed char)pr.oy[t]; p.ox[t] = (signed char)pr.ox[t]; p.wk[t] = pr.wk[t]; }
+    p.o_mul = pr.o_mul; p.o_offy = pr.o_offy; p.o_offx = pr.o_offx; p.FH = pr.FH; p.FW = pr.FW;
+    p.epi = e;
+
+    CUtensorMap msrc, mw, mout;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)pr.SC, (cuuint64_t)pr.SW, (cuuint64_t)pr.SH, (cuuint64_t)pr.SN};
+        cuuint64_t strides[3] = {(cuuint64_t)pr.SC * 4, (cuuint64_t)pr.SW * pr.SC * 4, (cuuint64_t)pr.SH * pr.SW * pr.SC * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)(p.tw * pr.stride), (cuuint32_t)(p.th * pr.stride), (cuuint32_t)p.tn};
+        cuuint32_t es[4] = {1, (cuuint32_t)pr.stride, (cuuint32_t)pr.stride, 1};
+        int rc = encode_map(&msrc, pr.src, 4, dims, strides, box, es);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)pr.Ktot, (cuuint64_t)pr.Ncol};
+        cuuint64_t strides[1] = {(cuuint64_t)pr.Ktot * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)BLOCK_N};
+        cuuint32_t es[2] = {1, 1};
+        int rc = encode_map(&mw, pr.wmat, 2, dims, strides, box, es);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)pr.Ncol, (cuuint64_t)pr.OW, (cuuint64_t)pr.OH, (cuuint64_t)pr.SN};
+        cuuint64_t strides[3] = {(cuuint64_t)pr.o_mul * pr.Ncol * 4, (cuuint64_t)pr.o_mul * pr.FW * pr.Ncol * 4,
+                                 (cuuint64_t)pr.FH * pr.FW * pr.Ncol * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        int rc = encode_map(&mout, pr.out + ((int64_t)pr.o_offy * pr.FW + pr.o_offx) * pr.Ncol, 4, dims, strides, box, es);
+        if (rc) return rc;
+    }
+    constexpr size_t smem = tc_smem_bytes<BLOCK_N>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(pr.Ncol / BLOCK_N));
+    conv_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(msrc, mw, mout, p);
+    return check_launch("conv_tc");
+}
+
+static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    if (pr.Ncol % 128 == 0) return tc_launch<128>(pr, e, st);
+    if (pr.Ncol % 64 == 0) return tc_launch<64>(pr, e, st);
+    return tc_launch<32>(pr, e, st);
+}
+
+static bool ptr_ok(const void* a, const void* b, const void* c) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
+bool tc_fprop_eligible(const sae_conv_geom* g) {
+    if (g->R * g->S > TC_MAX_TAPS) return false;
+    if (g->pad_t > 100 || g->pad_l > 100) return false;
+    return tc_shape_ok(g->C, g->K, g->R * g->S, g->stride, g->Q);
+}
+
+bool tc_dgrad_eligible(const sae_conv_geom* g) {
+    if (g->stride != 1 && g->stride != 2) return false;
+    if (g->R * g->S > TC_MAX_TAPS) return false;
+    if (g->pad_t > 100 || g->pad_l > 100) return false;
+    return tc_shape_ok(g->K, g->C, g->R * g->S, 1, (g->W + g->stride - 1) / g->stride);
+}
+
+int tc_fprop(const float* x, const float* w, float* y, const sae_conv_geom* g, const EpiParams& e, cudaStream_t st) {
+    if (!ptr_ok(x, w, y)) return fail(SAE_E_INVALID, "conv2d_fprop(tcgen05): pointers must be 16-byte aligned");
+    TcProblem pr;
+    pr.src = x; pr.SN = g->N; pr.SH = g->H; pr.SW = g->W; pr.SC = g->C;
+    pr.wmat = w; pr.Ncol = g->K; pr.Ktot = g->R * g->S * g->C;
+    pr.out = y; pr.OH = g->P; pr.OW = g->Q;
+    pr.o_mul = 1; pr.o_offy = 0; pr.o_offx = 0; pr.FH = g->P; pr.FW = g->Q;
+    pr.stride = g->stride; pr.ntaps = g->R * g->S;
+    for (int r = 0; r < g->R; ++r)
+        for (int s = 0; s < g->S; ++s) {
+            const int t = r * g->S + s;
+            pr.oy[t] = r - g->pad_t; pr.ox[t] = s - g->pad_l; pr.wk[t] = t * g->C;
+        }
+    return tc_dispatch(pr, e, st);
+}
+
+int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g, const EpiParams& e, cudaStream_t st) {
+    if (!ptr_ok(dy, wt, dx)) return fail(SAE_E_INVALID, "conv2d_dgrad(tcgen05): pointers must be 16-byte aligned");
+    TcProblem pr;
+    pr.src = dy; pr.SN = g->N; pr.SH = g->P; pr.SW = g->Q; pr.SC = g->K;
+    pr.wmat = wt; pr.Ncol = g->C; pr.Ktot = g->R * g->S * g->K;
+    pr.stride = 1; pr.FH = g->H; pr.FW = g->W;
+    const int st_ = g->stride;
+    if (st_ == 1) {
+        pr.out = dx; pr.OH = g->H; pr.OW = g->W; pr.o_mul = 1; pr.o_offy = 0; pr.o_offx = 0;
+        pr.ntaps = g->R * g->S;
+        for (int r = 0; r < g->R; ++r)
+            for (int s = 0; s < g->S; ++s) {
+                const int t = r * g->S + s;
+                pr.oy[t] = g->pad_t - r; pr.ox[t] = g->pad_l - s; pr.wk[t] = t * g->K;
+            }
+        return tc_dispatch(pr, e, st);
+    }
+    // stride 2 (the generator's transposed convolution and the data-gradient of the strided convs): the output
+    // splits into 4 parity classes (ho, wo); class outputs x[2i+ho, 2j+wo] only see taps with r = (ho + pad_t) mod 2,
+    // s = (wo + pad_l) mod 2, read at source offset (ho + pad_t - r) / 2 — four dense stride-1 problems writing
+    // interleaved sub-grids (the output tensor map carries the doubled strides).
+    bool need_zero = false;
+    for (int ho = 0; ho < 2; ++ho)
+        for (int wo = 0; wo < 2; ++wo) {
+            const int rp = (ho + g->pad_t) & 1, sp = (wo + g->pad_l) & 1;
+            if (rp >= g->R || sp >= g->S) need_zero = true;
+        }
+    if (need_zero) SAE_CUDA_TRY(cudaMemsetAsync(dx, 0, (size_t)g->N * g->H * g->W * g->C * sizeof(float), st));
+    for (int ho = 0; ho < 2; ++ho)
+        for (int wo = 0; wo < 2; ++wo) {
+            const int rp = (ho + g->pad_t) & 1, sp = (wo + g->pad_l) & 1;
+            if (rp >= g->R || sp >= g->S) continue;
+            if (ho >= g->H || wo >= g->W) continue;
+            pr.out = dx; pr.o_mul = 2; pr.o_offy = ho; pr.o_offx = wo;
+            pr.OH = (g->H - ho + 1) / 2; pr.OW = (g->W - wo + 1) / 2;
+            int nt = 0;
+            for (int r = rp; r < g->R; r += 2)
+                for (int s = sp; s < g->S; s += 2) {
+                    // exact division: (ho + pad_t - r) is even; C++ division truncates toward zero, so floor by hand
+                    const int ny = ho + g->pad_t - r, nx = wo + g->pad_l - s;
+                    pr.oy[nt] = ny >= 0 ? ny / 2 : -((-ny) / 2);
+                    pr.ox[nt] = nx >= 0 ? nx / 2 : -((-nx) / 2);
+                    pr.wk[nt] = (r * g->S + s) * g->K;
+                    ++nt;
+                }
+            pr.ntaps = nt;
+            int rc = tc_dispatch(pr, e, st);
+            if (rc) return rc;
+        }
+    return SAE_OK;
+}
+
+}  // namespace sae

@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256)
 bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ ref,
                 float* __restrict__ out, int64_t size_v, int64_t step_b, int size_b,
                 int act, int grad, float alpha, float scale,
-                const float* __restrict__ noise, const float* __restrict__ noise_weight, int64_t noise_div) {
+                const float* __restrict__ noise, const float* __restrict__ noise_weight, int64_t noise_div,
+                int round_tf32) {
     const float nw = noise ? __ldg(noise_weight) : 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < size_v;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -54,7 +55,7 @@ bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, const 
             } else {
                 y = (grad == 2) ? 0.f : t;
             }
-            v[j] = y * scale;
+            v[j] = round_tf32 ? rna_tf32(y * scale) : y * scale;
         }
         if (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
         else out[e0] = v[0];
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256)
 bias_act_bwd_kernel(const float* __restrict__ go, const float* __restrict__ outp, float* __restrict__ gi,
                     float* __restrict__ gb, int64_t size_v, int cv, int64_t stride_v,
                     float alpha, float scale,
-                    const float* __restrict__ noise, int64_t noise_div, float* __restrict__ gnw) {
+                    const float* __restrict__ noise, int64_t noise_div, float* __restrict__ gnw, int round_tf32) {
     extern __shared__ float sacc[];   // [cv * VEC] (+1 slot for the noise-weight grad)
     const int C = cv * VEC;
     for (int i = threadIdx.x; i <= C; i += blockDim.x) sacc[i] = 0.f;
@@ -97,7 +98,7 @@ bias_act_bwd_kernel(const float* __restrict__ go, const float* __restrict__ outp
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 float y = ((o[j] > 0.f) ? g[j] : g[j] * alpha) * scale;
-                g[j] = y;
+                g[j] = round_tf32 ? rna_tf32(y) : y;
                 bsum[j] += y;
                 lsum += y;
             }
@@ -157,7 +158,7 @@ modulate_scalar_kernel(const float* __restrict__ x, const float* __restrict__ s,
 template <int VEC>
 __global__ void __launch_bounds__(256)
 modulate_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ s,
-                    float* __restrict__ dx, float* __restrict__ ds, int64_t hw, int cv, int64_t pix_per_cta) {
+                    float* __restrict__ dx, float* __restrict__ ds, int64_t hw, int cv, int64_t pix_per_cta, int round_tf32) {
     extern __shared__ float sacc[];   // [cv*VEC]
     const int C = cv * VEC;
     for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
@@ -189,7 +190,10 @@ modulate_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
                     g[0] = dy[base_v + i]; a[0] = x[base_v + i];
                 }
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) { acc[j] = fmaf(g[j], a[j], acc[j]); g[j] *= m[j]; }
+                for (int j = 0; j < VEC; ++j) {
+                    acc[j] = fmaf(g[j], a[j], acc[j]);
+                    g[j] = round_tf32 ? rna_tf32(g[j] * m[j]) : g[j] * m[j];
+                }
                 if (VEC == 4) reinterpret_cast<float4*>(dx)[base_v + i] = make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]);
                 else dx[base_v + i] = g[0];
             }
@@ -205,7 +209,8 @@ modulate_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
                 int64_t e = (base_v + i) * VEC + j;
                 float g = dy[e], a = x[e];
                 atomicAdd(&sacc[c * VEC + j], g * a);
-                dx[e] = g * __ldg(s + (int64_t)n * C + c * VEC + j);
+                float d = g * __ldg(s + (int64_t)n * C + c * VEC + j);
+                dx[e] = round_tf32 ? rna_tf32(d) : d;
             }
         }
     }
@@ -213,6 +218,30 @@ modulate_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         float v = sacc[i];
         if (v != 0.f) atomicAdd(ds + (int64_t)n * C + i, v);
+    }
+}
+
+// ------------------------------------------------------------------------- residual merge / rounding
+template <int VEC>
+__global__ void __launch_bounds__(256)
+add_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t nv, float scale,
+                 int round_tf32) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        if (VEC == 4) {
+            float4 u = ldg_stream(reinterpret_cast<const float4*>(a) + i);
+            if (b) {
+                float4 w = ldg_stream(reinterpret_cast<const float4*>(b) + i);
+                u.x += w.x; u.y += w.y; u.z += w.z; u.w += w.w;
+            }
+            u.x *= scale; u.y *= scale; u.z *= scale; u.w *= scale;
+            if (round_tf32) { u.x = rna_tf32(u.x); u.y = rna_tf32(u.y); u.z = rna_tf32(u.z); u.w = rna_tf32(u.w); }
+            reinterpret_cast<float4*>(out)[i] = u;
+        } else {
+            float u = a[i];
+            if (b) u += b[i];
+            u *= scale;
+            out[i] = round_tf32 ? rna_tf32(u) : u;
+        }
     }
 }
 
@@ -238,7 +267,7 @@ extern "C" int sae_fused_bias_act(const float* x, const float* bias, const float
                                   int64_t size_x, int64_t step_b, int size_b,
                                   int act, int grad, float alpha, float scale,
                                   const float* noise, const float* noise_weight, int64_t noise_div,
-                                  void* stream) {
+                                  int round_tf32, void* stream) {
     if (size_x == 0) return SAE_OK;
     if (!x || !out || size_x < 0) return fail(SAE_E_INVALID, "fused_bias_act: bad input");
     if (act != 1 && act != 3) return fail(SAE_E_INVALID, "fused_bias_act: act %d unsupported (1 linear, 3 lrelu)", act);
@@ -252,10 +281,10 @@ extern "C" int sae_fused_bias_act(const float* x, const float* bias, const float
     if (vec) {
         int64_t nv = size_x / 4;
         bias_act_kernel<4><<<grid_for(nv, 256), 256, 0, st>>>(x, bias, ref, out, nv, step_b, size_b, act, grad, alpha,
-                                                             scale, noise, noise_weight, noise_div);
+                                                             scale, noise, noise_weight, noise_div, round_tf32);
     } else {
         bias_act_kernel<1><<<grid_for(size_x, 256), 256, 0, st>>>(x, bias, ref, out, size_x, step_b, size_b, act, grad,
-                                                                 alpha, scale, noise, noise_weight, noise_div);
+                                                                 alpha, scale, noise, noise_weight, noise_div, round_tf32);
     }
     return check_launch("fused_bias_act");
 }
@@ -263,7 +292,7 @@ extern "C" int sae_fused_bias_act(const float* x, const float* bias, const float
 extern "C" int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_in, float* grad_bias,
                                      int64_t size_x, int size_b, float alpha, float scale,
                                      const float* noise, int64_t noise_div, float* grad_noise_weight,
-                                     void* stream) {
+                                     int round_tf32, void* stream) {
     if (size_x == 0) return SAE_OK;
     if (!grad_out || !out || !grad_in || size_b <= 0 || size_x % size_b != 0)
         return fail(SAE_E_INVALID, "bias_act_backward: bad arguments (size_x %% size_b must be 0)");
@@ -288,11 +317,11 @@ extern "C" int sae_bias_act_backward(const float* grad_out, const float* out, fl
     if (vec) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(bias_act_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         bias_act_bwd_kernel<4><<<blocks, 256, smem, st>>>(grad_out, out, grad_in, grad_bias, size_v, cv, stride, alpha, scale,
-                                                         noise, noise_div, grad_noise_weight);
+                                                         noise, noise_div, grad_noise_weight, round_tf32);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(bias_act_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         bias_act_bwd_kernel<1><<<blocks, 256, smem, st>>>(grad_out, out, grad_in, grad_bias, size_v, cv, stride, alpha, scale,
-                                                         noise, noise_div, grad_noise_weight);
+                                                         noise, noise_div, grad_noise_weight, round_tf32);
     }
     return check_launch("bias_act_backward");
 }
@@ -315,7 +344,7 @@ extern "C" int sae_modulate(const float* x, const float* s, float* out, int n, i
 }
 
 extern "C" int sae_modulate_backward(const float* dy, const float* x, const float* s, float* dx, float* ds,
-                                     int n, int64_t hw, int c, void* stream) {
+                                     int n, int64_t hw, int c, int round_tf32, void* stream) {
     if (n == 0 || hw == 0) return SAE_OK;
     if (!dy || !x || !s || !dx || !ds || n < 0 || c <= 0) return fail(SAE_E_INVALID, "modulate_backward: bad arguments");
     if (c > 12000) return fail(SAE_E_UNSUPPORTED, "modulate_backward: more than 12000 channels");
@@ -331,9 +360,23 @@ extern "C" int sae_modulate_backward(const float* dy, const float* x, const floa
     unsigned chunks = (unsigned)((hw + pix_per_cta - 1) / pix_per_cta);
     dim3 grid(chunks, (unsigned)n);
     size_t smem = (size_t)c * sizeof(float);
-    if (vec) modulate_bwd_kernel<4><<<grid, 256, smem, st>>>(dy, x, s, dx, ds, hw, c / V, pix_per_cta);
-    else     modulate_bwd_kernel<1><<<grid, 256, smem, st>>>(dy, x, s, dx, ds, hw, c / V, pix_per_cta);
+    if (vec) modulate_bwd_kernel<4><<<grid, 256, smem, st>>>(dy, x, s, dx, ds, hw, c / V, pix_per_cta, round_tf32);
+    else     modulate_bwd_kernel<1><<<grid, 256, smem, st>>>(dy, x, s, dx, ds, hw, c / V, pix_per_cta, round_tf32);
     return check_launch("modulate_backward");
+}
+
+extern "C" int sae_add_scale(const float* a, const float* b, float* out, int64_t n, float scale, int round_tf32, void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!a || !out || n < 0) return fail(SAE_E_INVALID, "add_scale: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out);
+    if (n % 4 == 0 && al % 16 == 0) add_scale_kernel<4><<<grid_for(n / 4, 256), 256, 0, st>>>(a, b, out, n / 4, scale, round_tf32);
+    else add_scale_kernel<1><<<grid_for(n, 256), 256, 0, st>>>(a, b, out, n, scale, round_tf32);
+    return check_launch("add_scale");
+}
+
+extern "C" int sae_round_tf32(const float* x, float* out, int64_t n, void* stream) {
+    return sae_add_scale(x, nullptr, out, n, 1.0f, 1, stream);
 }
 
 extern "C" int sae_bucket_pack(const float* const* ptrs, const int64_t* offsets, const int64_t* sizes, int n,

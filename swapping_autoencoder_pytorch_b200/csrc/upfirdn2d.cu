@@ -18,6 +18,7 @@ struct FirParams {
     int up_x, up_y, down_x, down_y;
     int pad_x0, pad_y0;
     int out_h, out_w;
+    int round_tf32;
 };
 
 constexpr int kMaxTaps = 32 * 32;
@@ -82,6 +83,10 @@ fir_generic_kernel(const float* __restrict__ x, const float* __restrict__ k, flo
             }
         }
         float* dst = out + pix * p.minor + (int64_t)c * VEC;
+        if (p.round_tf32) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = rna_tf32(acc[v]);
+        }
         if (VEC == 4) {
             *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
         } else {
@@ -156,6 +161,7 @@ fir_strip_kernel(const float* __restrict__ x, const float* __restrict__ k, float
                     acc.w = fmaf(win[a][b].w, w[a][b], acc.w);
                 }
             float* dst = out + ((n * p.out_h + oy) * (int64_t)p.out_w + ox) * p.minor + (int64_t)c * 4;
+            if (p.round_tf32) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
             *reinterpret_cast<float4*>(dst) = acc;
             // slide the window up by one row
 #pragma unroll
@@ -185,8 +191,9 @@ extern "C" int sae_upfirdn2d(const float* input, const float* kernel, float* out
                              int kernel_h, int kernel_w,
                              int up_x, int up_y, int down_x, int down_y,
                              int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                             void* stream) {
+                             int round_tf32, void* stream) {
     using namespace sae;
+    if (major == 0) return SAE_OK;                                     // empty batch: nothing to do
     if (!input || !kernel || !out) return fail(SAE_E_INVALID, "upfirdn2d: null pointer");
     if (major < 0 || in_h <= 0 || in_w <= 0 || minor <= 0) return fail(SAE_E_INVALID, "upfirdn2d: bad input shape");
     if (kernel_h <= 0 || kernel_w <= 0 || kernel_h * kernel_w > kMaxTaps)
@@ -196,13 +203,12 @@ extern "C" int sae_upfirdn2d(const float* input, const float* kernel, float* out
     p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor;
     p.kh = kernel_h; p.kw = kernel_w;
     p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
-    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.round_tf32 = round_tf32;
     int full_h = in_h * up_y + pad_y0 + pad_y1 - kernel_h;
     int full_w = in_w * up_x + pad_x0 + pad_x1 - kernel_w;
     if (full_h < 0 || full_w < 0) return fail(SAE_E_INVALID, "upfirdn2d: kernel larger than padded input");
     p.out_h = full_h / down_y + 1;
     p.out_w = full_w / down_x + 1;
-    if (major == 0) return SAE_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool aligned = ((reinterpret_cast<uintptr_t>(input) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     const bool vec = (minor % 4 == 0) && aligned;

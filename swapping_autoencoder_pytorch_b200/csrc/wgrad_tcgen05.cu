@@ -1,0 +1,245 @@
+// Weight-gradient of the convolution on tcgen05 tensor cores (kind::tf32), TMA-fed, split over pixels.
+//
+//   dW[o, (r,s), c] += sum_{pixels (n,p,q)}  dy[n,p,q,o] * x[n, p*st - pad_t + r, q*st - pad_l + s, c]
+//
+// GEMM view per filter tap: M = out channels (128 per CTA), N = in channels (128 per CTA), K = pixels.
+// Both operands are "MN-major" for the tensor core (the contiguous NHWC dimension is the channel = M resp. N
+// dimension, the reduction runs over pixels), which tcgen05 supports for tf32 through the transposed
+// (a_major = b_major = MN) shared-memory descriptors — so the NHWC activations are consumed as they are, no
+// transposes materialised:
+//   * A stage  = dy box of 32 pixels x 128 channels  = 4 TMA boxes (32 ch x 32 px, SWIZZLE_128B_ATOM_32B — the only
+//     layout tcgen05 accepts for MN-major 32-bit operands)
+//   * B stages = for each of the (up to 3) taps of this CTA's tap group, the x box shifted by the tap, 4 TMA boxes;
+//     out-of-bounds pixels are zero-filled by TMA (= the conv padding), element stride = conv stride
+//   * one TMEM accumulator (128 x 128 fp32 = 128 columns) per tap; the dy tile is reused by all taps of the group
+//   * grid = (M tiles x N tiles, tap groups, pixel splits); partial sums are reduced with vectorised fp32 atomics
+//     (red.global.add.v4.f32) straight from the TMEM read — dW must be zero-initialised by the caller.
+#include "tc_common.cuh"
+
+namespace sae {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_KPIX = 32;                        // pixels per pipeline stage
+constexpr int WG_SUB = WG_KPIX * 128;              // one 32-channel sub-tile: 32 rows x 128 B = 4 KB
+constexpr int WG_OPER = 4 * WG_SUB;                // 128 channels: 16 KB
+constexpr int WG_MAX_GROUP = 3;
+constexpr int WG_STAGES = 3;
+
+struct WgParams {
+    int tw, th, tn;                  // pixel box of a K chunk (tw*th*tn == 32)
+    int tiles_w, tiles_h, tiles_n;   // over the OUTPUT (dy) pixel space
+    int chunks_total, chunks_per_split;
+    int stride, pad_t, pad_l;
+    int R, S;
+    int Ko, C;                       // channels of dy / x
+    int group_taps;                  // taps per tap group (<= 3); group g covers taps [g*group_taps, ...)
+    int ntaps;
+    int n_tiles_c;                   // number of 128-wide tiles along C
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+    // MN-major 32-bit operands have exactly one legal shared-memory layout on tcgen05: the 128-byte swizzle with
+    // 32-byte atoms (descriptor layout type 1, TMA mode SWIZZLE_128B_ATOM_32B).  Atom = 32 fp32 along M/N (128 B) x 4
+    // along K; next atom along M/N: LBO = 4096 B (the next 32-channel sub-tile); next 4 pixels along K: SBO = 512 B.
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(WG_SUB >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                float* __restrict__ dw, const WgParams p) {
+    constexpr int STAGE_BYTES = WG_OPER * (1 + WG_MAX_GROUP);       // 64 KB
+    // D fp32, A/B tf32, A and B MN-major (bits 15, 16), N = 128, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t TMEM_COLS = 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + WG_STAGES * STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + 8 * WG_STAGES;
+    const uint32_t bar_acc = bar_empty + 8 * WG_STAGES;
+    const uint32_t tmem_slot = bar_acc + 8;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_o = blockIdx.x / p.n_tiles_c, tile_c = blockIdx.x % p.n_tiles_c;
+    const int o0 = tile_o * 128, c0 = tile_c * 128;
+    const int tap0 = blockIdx.y * p.group_taps;
+    const int ntap = min(p.group_taps, p.ntaps - tap0);
+    const int chunk_begin = blockIdx.z * p.chunks_per_split;
+    const int chunk_end = min(chunk_begin + p.chunks_per_split, p.chunks_total);
+    const int KB = chunk_end - chunk_begin;
+    const uint32_t stage_tx = (uint32_t)WG_OPER * (1 + ntap);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (KB > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int s = kb % WG_STAGES;
+                    const uint32_t ph = (uint32_t)(kb / WG_STAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    int ch = chunk_begin + kb;
+                    const int tq = ch % p.tiles_w; ch /= p.tiles_w;
+                    const int tp = ch % p.tiles_h; ch /= p.tiles_h;
+                    const int q0 = tq * p.tw, p0 = tp * p.th, n0 = ch * p.tn;
+                    const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * s, stage_tx);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        tma_load_4d(sa + i * WG_SUB, &map_dy, bar_full + 8 * s, o0 + 32 * i, q0, p0, n0);
+                    for (int g = 0; g < ntap; ++g) {
+                        const int tap = tap0 + g;
+                        const int r = tap / p.S, sx = tap - r * p.S;
+                        const uint32_t sb = sa + (uint32_t)(1 + g) * WG_OPER;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_4d(sb + i * WG_SUB, &map_x, bar_full + 8 * s, c0 + 32 * i,
+                                        q0 * p.stride - p.pad_l + sx, p0 * p.stride - p.pad_t + r, n0);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int s = kb % WG_STAGES;
+                    const uint32_t ph = (uint32_t)(kb / WG_STAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
+                    const uint64_t da = make_desc_mn_sw128(sa);
+                    for (int g = 0; g < ntap; ++g) {
+                        const uint64_t db = make_desc_mn_sw128(sa + (uint32_t)(1 + g) * WG_OPER);
+#pragma unroll
+                        for (int k = 0; k < WG_KPIX / 8; ++k) {
+                            // next 8 pixels along K: +1024 B = +64 in the (addr >> 4) field
+                            umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), IDESC,
+                                      (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_acc);
+            }
+        } else {
+            const int lg = warp & 3;
+            const int row = lg * 32 + lane;
+            const int o = o0 + row;
+            mbar_wait(bar_acc, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t ld = (int64_t)p.ntaps * p.C;
+            for (int g = 0; g < ntap; ++g) {
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * 128 + ch * 32), v);
+                    const int c = c0 + ch * 32;
+                    if (o < p.Ko && c < p.C) {
+                        float* dst = dw + (int64_t)o * ld + (int64_t)(tap0 + g) * p.C + c;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j]),
+                                         "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+bool tc_wgrad_eligible(const sae_conv_geom* g) {
+    if (g->K % 32 != 0 || g->C % 32 != 0) return false;
+    if (g->stride != 1 && g->stride != 2) return false;
+    if (g->R * g->S > 49) return false;
+    int tw = pow2_ceil(g->Q) < 32 ? pow2_ceil(g->Q) : 32;
+    if (tw * g->stride > 256) return false;
+    if ((int64_t)g->N * g->P * g->Q < 256) return false;      // too few pixels to be worth a tensor-core launch
+    return true;
+}
+
+int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g, cudaStream_t st) {
+    if (((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) != 0)
+        return fail(SAE_E_INVALID, "conv2d_wgrad(tcgen05): pointers must be 16-byte aligned");
+    WgParams p;
+    p.tw = pow2_ceil(g->Q) < 32 ? pow2_ceil(g->Q) : 32;
+    int th = 32 / p.tw;
+    if (pow2_ceil(g->P) < th) th = pow2_ceil(g->P);
+    p.th = th;
+    p.tn = 32 / (p.tw * p.th);
+    p.tiles_w = (g->Q + p.tw - 1) / p.tw;
+    p.tiles_h = (g->P + p.th - 1) / p.th;
+    p.tiles_n = (g->N + p.tn - 1) / p.tn;
+    p.chunks_total = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l; p.R = g->R; p.S = g->S;
+    p.Ko = g->K; p.C = g->C;
+    p.ntaps = g->R * g->S;
+    p.group_taps = p.ntaps < WG_MAX_GROUP ? p.ntaps : WG_MAX_GROUP;
+    const int groups = (p.ntaps + p.group_taps - 1) / p.group_taps;
+    const int tiles_o = (g->K + 127) / 128;
+    p.n_tiles_c = (g->C + 127) / 128;
+    const int tiles = tiles_o * p.n_tiles_c * groups;
+    int splits = (sm_count() + tiles - 1) / tiles;                  // one CTA per SM (192 KB of shared memory each)
+    if (splits > p.chunks_total) splits = p.chunks_total;
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
+    splits = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
+
+    CUtensorMap mdy, mx;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g->K, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g->K * 4, (cuuint64_t)g->Q * g->K * 4, (cuuint64_t)g->P * g->Q * g->K * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        int rc = encode_map(&mdy, dy, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g->C, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)(p.tw * g->stride), (cuuint32_t)(p.th * g->stride), (cuuint32_t)p.tn};
+        cuuint32_t es[4] = {1, (cuuint32_t)g->stride, (cuuint32_t)g->stride, 1};
+        int rc = encode_map(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    }
+    constexpr size_t smem = (size_t)WG_STAGES * WG_OPER * (1 + WG_MAX_GROUP) + 1024 + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)(tiles_o * p.n_tiles_c), (unsigned)groups, (unsigned)splits);
+    wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(mdy, mx, dw, p);
+    return check_launch("wgrad_tc");
+}
+
+}  // namespace sae

@@ -7,6 +7,7 @@ import torch.nn.functional as F
 
 from .. import util
 from ..stylegan2_layers import ConvLayer, EqualLinear, StyledConv, ToRGB
+from ..stylegan2_op import add_scale
 from .base_network import BaseNetwork
 
 _INV_SQRT2 = 1.0 / math.sqrt(2.0)
@@ -36,7 +37,7 @@ class ResolutionPreservingResnetBlock(torch.nn.Module):
 
     def forward(self, x, style):
         res = self.conv2(self.conv1(x, style), style)
-        return (self.skip(x) + res) * _INV_SQRT2
+        return add_scale(self.skip(x), res, _INV_SQRT2)
 
 
 class UpsamplingResnetBlock(torch.nn.Module):
@@ -53,7 +54,7 @@ class UpsamplingResnetBlock(torch.nn.Module):
     def forward(self, x, style):
         skip = F.interpolate(self.skip(x), scale_factor=2, mode='bilinear', align_corners=False)
         res = self.conv2(self.conv1(x, style), style)
-        return (skip + res) * _INV_SQRT2
+        return add_scale(skip, res, _INV_SQRT2)
 
 
 class GeneratorModulation(torch.nn.Module):

@@ -19,7 +19,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from .stylegan2_op import (FusedLeakyReLU, conv2d, conv_transpose2d, fused_leaky_relu,
+from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv_transpose2d, fused_leaky_relu,
                            fused_noise_bias_leaky_relu, linear, modulate, upfirdn2d)
 
 _SQRT2 = math.sqrt(2.0)
@@ -409,7 +409,7 @@ class ResBlock(nn.Module):
 
     def forward(self, input):
         out = self.conv2(self.conv1(input))
-        return (out + self.skip(input)) / _SQRT2
+        return add_scale(out, self.skip(input), 1.0 / _SQRT2)
 
 
 class Discriminator(nn.Module):

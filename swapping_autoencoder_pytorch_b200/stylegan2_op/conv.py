@@ -26,6 +26,13 @@ def _nchw(t):
     return t.permute(0, 3, 1, 2)
 
 
+def _impl(g):
+    """Kernel choice hint: linears (1x1 maps) have M = batch rows only — far below a 128-row tensor-core tile — and
+    take unrounded inputs (style codes, pooled features), so they always use the generic kernel, which rounds its
+    operands itself; everything else lets the library pick (None)."""
+    return 1 if (g.H == 1 and g.W == 1 and g.P == 1 and g.Q == 1) else None
+
+
 class _ConvFprop(Function):
     """y = conv(x, w)   x: logical NCHW, w: [K,R,S,C]"""
 
@@ -33,7 +40,7 @@ class _ConvFprop(Function):
     def forward(ctx, x, w, g):
         ctx.g = g
         ctx.save_for_backward(x, w)
-        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g))
+        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g)))
 
     @staticmethod
     def backward(ctx, dy):
@@ -50,7 +57,7 @@ class _ConvDgrad(Function):
     def forward(ctx, dy, w, g):
         ctx.g = g
         ctx.save_for_backward(dy, w)
-        return _nchw(backend.kernels().conv_dgrad(_nhwc(dy), w.contiguous(), g))
+        return _nchw(backend.kernels().conv_dgrad(_nhwc(dy), w.contiguous(), g, impl=_impl(g)))
 
     @staticmethod
     def backward(ctx, ddx):
@@ -67,7 +74,7 @@ class _ConvWgrad(Function):
     def forward(ctx, dy, x, g):
         ctx.g = g
         ctx.save_for_backward(dy, x)
-        return backend.kernels().conv_wgrad(_nhwc(dy), _nhwc(x), g)
+        return backend.kernels().conv_wgrad(_nhwc(dy), _nhwc(x), g, impl=_impl(g))
 
     @staticmethod
     def backward(ctx, ddw):
@@ -135,3 +142,25 @@ class _Modulate(Function):
 
 def modulate(x, s):
     return _Modulate.apply(x, s)
+
+
+class _AddScale(Function):
+    """(a + b) * scale in one pass — the residual merges "(out + skip) / sqrt(2)" (stylegan2_layers.py:691,
+    generator.py:36,53).  Linear, so its backward is the same kernel with b = None and stays differentiable."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        ctx.scale = scale
+        k = backend.kernels()
+        if a.dim() == 4:
+            return _nchw(k.add_scale(_nhwc(a), _nhwc(b) if b is not None else None, scale))
+        return k.add_scale(a.contiguous(), b.contiguous() if b is not None else None, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = _AddScale.apply(dy, None, ctx.scale)
+        return g, (g if ctx.needs_input_grad[1] else None), None
+
+
+def add_scale(a, b, scale):
+    return _AddScale.apply(a, b, scale)

@@ -73,6 +73,9 @@ class EmulatedKernels:
     def modulate_backward(self, dy, x, s):
         return dy * s[:, None, None, :], (dy * x).sum(dim=(1, 2))
 
+    def add_scale(self, a, b, scale):
+        return (a + b) * scale if b is not None else a * scale
+
     def _epilogue(self, y, bias=None, act=1, alpha=0.2, gain=1.0, noise=None, noise_weight=None, residual=None,
                   res_scale=1.0, round_tf32=None):
         if bias is not None:
@@ -86,18 +89,18 @@ class EmulatedKernels:
             y = (y + residual) * res_scale
         return y
 
-    def conv_fprop(self, x, w_krsc, g, **epi):
+    def conv_fprop(self, x, w_krsc, g, impl=None, **epi):
         y = _nhwc(_conv(g, _nchw(x), w_krsc))
         return self._epilogue(y, **epi)
 
-    def conv_dgrad(self, dy, w_krsc, g, **epi):
+    def conv_dgrad(self, dy, w_krsc, g, impl=None, **epi):
         x0 = torch.zeros(g.N, g.C, g.H, g.W, dtype=dy.dtype, requires_grad=True)
         with torch.enable_grad():
             y = _conv(g, x0, w_krsc.detach())
         dx, = torch.autograd.grad(y, x0, _nchw(dy).detach())
         return self._epilogue(_nhwc(dx), **epi)
 
-    def conv_wgrad(self, dy, x, g):
+    def conv_wgrad(self, dy, x, g, impl=None):
         w0 = torch.zeros(g.K, g.R, g.S, g.C, dtype=dy.dtype, requires_grad=True)
         with torch.enable_grad():
             y = _conv(g, _nchw(x).detach(), w0)

@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE — "shadow" kernel set: every call goes to the CUDA kernels AND, on CPU copies of the same
+inputs in fp64, to the oracle-backed emulation; the per-call error is recorded.  Running a real network step under
+it checks every kernel configuration the networks actually produce (shapes, pads, strides, epilogues) and points
+at the exact call that deviates."""
+import torch
+
+from swapping_autoencoder_pytorch_b200 import backend
+from tests.cpu_emulation import EmulatedKernels
+
+
+def _cpu(v):
+    if torch.is_tensor(v):
+        return v.detach().double().cpu()
+    return v
+
+
+def _err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if b.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+class ShadowKernels:
+    name = "shadow"
+
+    def __init__(self):
+        self.real = backend.CudaKernels()
+        self.emu = EmulatedKernels()
+        self.log = []          # (method, description, error)
+
+    @property
+    def conv_impl(self):
+        return self.real.conv_impl
+
+    @conv_impl.setter
+    def conv_impl(self, v):
+        self.real.conv_impl = v
+
+    @property
+    def round_tf32(self):
+        return self.real.round_tf32
+
+    def _both(self, name, desc, args, kwargs):
+        out = getattr(self.real, name)(*args, **kwargs)
+        kw = {k: _cpu(v) for k, v in kwargs.items() if k != "round_tf32"}
+        ref = getattr(self.emu, name)(*[_cpu(a) for a in args], **kw)
+        outs = out if isinstance(out, tuple) else (out,)
+        refs = ref if isinstance(ref, tuple) else (ref,)
+        for i, (o, r) in enumerate(zip(outs, refs)):
+            if o is None:
+                continue
+            self.log.append((name, "%s out%d" % (desc, i), _err(o, r)))
+        return out
+
+    def upfirdn2d(self, x, kernel, *cfg):
+        return self._both("upfirdn2d", "x%s k%s cfg%s" % (tuple(x.shape), tuple(kernel.shape), cfg), (x, kernel) + cfg, {})
+
+    def bias_act(self, x, bias, ref, act, grad, alpha, scale, noise=None, noise_weight=None):
+        return self._both("bias_act", "x%s act%d grad%d noise%s" % (tuple(x.shape), act, grad, noise is not None),
+                          (x, bias, ref, act, grad, alpha, scale), dict(noise=noise, noise_weight=noise_weight))
+
+    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None):
+        return self._both("bias_act_backward", "x%s noise%s" % (tuple(out.shape), noise is not None),
+                          (grad_out, out, alpha, scale), dict(want_bias=want_bias, noise=noise))
+
+    def modulate(self, x, s):
+        return self._both("modulate", "x%s" % (tuple(x.shape),), (x, s), {})
+
+    def modulate_backward(self, dy, x, s):
+        return self._both("modulate_backward", "x%s" % (tuple(x.shape),), (dy, x, s), {})
+
+    def add_scale(self, a, b, scale):
+        return self._both("add_scale", "x%s" % (tuple(a.shape),), (a, b, scale), {})
+
+    def _impl_name(self, g, d, impl):
+        return impl if impl is not None else self.real.conv_impl_for(g, d)
+
+    def conv_fprop(self, x, w, g, impl=None, **epi):
+        return self._both("conv_fprop", "g%s impl%s epi%s" % (g.key(), self._impl_name(g, 0, impl), sorted(epi)), (x, w, g),
+                          dict(epi, impl=impl))
+
+    def conv_dgrad(self, dy, w, g, impl=None, **epi):
+        return self._both("conv_dgrad", "g%s impl%s" % (g.key(), self._impl_name(g, 1, impl)), (dy, w, g), dict(epi, impl=impl))
+
+    def conv_wgrad(self, dy, x, g, impl=None):
+        return self._both("conv_wgrad", "g%s impl%s" % (g.key(), self._impl_name(g, 2, impl)), (dy, x, g), dict(impl=impl))
+
+    def conv_impl_for(self, g, d):
+        return self.real.conv_impl_for(g, d)
+
+    def bucket_pack(self, *a):
+        return self.real.bucket_pack(*a)
+
+    def bucket_unpack(self, *a):
+        return self.real.bucket_unpack(*a)
+
+    def worst(self, n=12):
+        return sorted(self.log, key=lambda t: -t[2])[:n]
+
+    def failures(self, tol_conv=1.5e-3, tol_other=5e-4):
+        bad = []
+        for name, desc, e in self.log:
+            tol = tol_conv if name.startswith("conv") else tol_other
+            if not (e < tol):
+                bad.append((name, desc, e))
+        return bad

@@ -31,7 +31,7 @@ def test_abi_version_and_error_reporting():
     lib = _lib.load()
     assert lib.sae_abi_version() == _lib.SAE_ABI_VERSION
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
-    rc = lib.sae_upfirdn2d(None, None, None, 1, 4, 4, 4, 3, 3, 1, 1, 1, 1, 0, 0, 0, 0, None)
+    rc = lib.sae_upfirdn2d(None, None, None, 1, 4, 4, 4, 3, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0, None)   # major=1, null data
     assert rc == -1 and b"null" in lib.sae_last_error()
     g = _lib.ConvGeom(1, 4, 4, 8, 8, 3, 3, 0, 4, 1, 1, 1)      # P = 0 is invalid
     rc = lib.sae_conv2d_fprop(None, None, None, ctypes.byref(g), None, 0, None)

@@ -29,8 +29,23 @@ def cuda(t):
     return t.float().to(DEV)
 
 
+def tf32(t):
+    """round-to-nearest (ties away) to TF32, as a float64 tensor — what cvt.rna.tf32.f32 does to an fp32 value"""
+    bits = t.float().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32).double()
+
+
+@pytest.fixture
+def exact_fp32():
+    """pointwise kernels without the TF32 output rounding policy: results must match fp32 arithmetic"""
+    kern = backend.kernels()
+    prev, kern.round_tf32 = kern.round_tf32, False
+    yield
+    kern.round_tf32 = prev
+
+
 # ------------------------------------------------------------------------------------------------ FIR
-def test_fir_golden_cases_and_second_order():
+def test_fir_golden_cases_and_second_order(exact_fp32):
     from swapping_autoencoder_pytorch_b200.stylegan2_layers import make_kernel
     from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
     meta, G = load_golden("ops_upfirdn2d")
@@ -51,7 +66,7 @@ def test_fir_golden_cases_and_second_order():
                                           ([1, 2, 1], (0, 0), 32, 67), ([1, 2, 1], (1, 0), 256, 16),
                                           ([1], (0, 0), 512, 7), ([1, 3, 3, 1], (1, 1), 3, 33),
                                           ([1, 3, 3, 1], (2, 2), 384, 4)])
-def test_fir_hot_path_shapes(taps, pad, c, h):
+def test_fir_hot_path_shapes(taps, pad, c, h, exact_fp32):
     from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
     k = O.make_kernel(taps, torch.float64)
     x = rnd(5, 3, c, h, h + 1)
@@ -61,7 +76,7 @@ def test_fir_hot_path_shapes(taps, pad, c, h):
     assert rel_err(y, y_ref) < TOL_FP32
 
 
-def test_fir_edge_cases():
+def test_fir_edge_cases(exact_fp32):
     from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
     k = cuda(O.make_kernel([1, 3, 3, 1], torch.float64))
     # empty batch, and a 5x5 generic kernel with up=2/down=3
@@ -76,7 +91,7 @@ def test_fir_edge_cases():
 
 # -------------------------------------------------------------------------------------------- bias/act
 @pytest.mark.parametrize("shape", [(2, 4, 5, 6), (3, 8), (4, 128, 32, 32), (16, 2048), (2, 3, 7, 5), (8, 384, 2, 2)])
-def test_fused_leaky_relu_fwd_bwd_double_bwd(shape):
+def test_fused_leaky_relu_fwd_bwd_double_bwd(shape, exact_fp32):
     from swapping_autoencoder_pytorch_b200.stylegan2_op import fused_leaky_relu
     x = rnd(1, *shape)
     b = rnd(2, shape[1])
@@ -95,7 +110,7 @@ def test_fused_leaky_relu_fwd_bwd_double_bwd(shape):
     assert rel_err(gw, gw_r) < TOL_FP32
 
 
-def test_noise_bias_act_fused():
+def test_noise_bias_act_fused(exact_fp32):
     from swapping_autoencoder_pytorch_b200.stylegan2_op import fused_noise_bias_leaky_relu
     x, nz, b = rnd(1, 2, 64, 16, 16), rnd(2, 2, 1, 16, 16), rnd(3, 64)
     nw = torch.tensor([0.37], dtype=torch.float64)
@@ -111,21 +126,32 @@ def test_noise_bias_act_fused():
         assert rel_err(a, r) < 2e-5
 
 
-def test_modulate():
-    from swapping_autoencoder_pytorch_b200.stylegan2_op import modulate
-    kern = backend.kernels()
-    prev, kern.round_tf32 = kern.round_tf32, False
-    try:
-        for c in (8, 512, 3, 2048):
-            x, s, w = rnd(1, 3, c, 9, 7), rnd(2, 3, c), rnd(3, 3, c, 9, 7)
-            xg, sg = cuda(x).requires_grad_(), cuda(s).requires_grad_()
-            y = modulate(xg, sg)
-            assert rel_err(y, x * s[:, :, None, None]) < TOL_FP32
-            gx, gs = torch.autograd.grad((y * cuda(w)).sum(), [xg, sg])
-            assert rel_err(gx, w * s[:, :, None, None]) < TOL_FP32
-            assert rel_err(gs, (w * x).sum(dim=(2, 3))) < 2e-5
-    finally:
-        kern.round_tf32 = prev
+def test_modulate_and_add_scale(exact_fp32):
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import add_scale, modulate
+    for c in (8, 512, 3, 2048):
+        x, s, w = rnd(1, 3, c, 9, 7), rnd(2, 3, c), rnd(3, 3, c, 9, 7)
+        xg, sg = cuda(x).requires_grad_(), cuda(s).requires_grad_()
+        y = modulate(xg, sg)
+        assert rel_err(y, x * s[:, :, None, None]) < TOL_FP32
+        gx, gs = torch.autograd.grad((y * cuda(w)).sum(), [xg, sg])
+        assert rel_err(gx, w * s[:, :, None, None]) < TOL_FP32
+        assert rel_err(gs, (w * x).sum(dim=(2, 3))) < 2e-5
+        a, b = cuda(x).requires_grad_(), cuda(w).requires_grad_()
+        z = add_scale(a, b, 0.7071)
+        assert rel_err(z, (x + w) * 0.7071) < TOL_FP32
+        ga, gb = torch.autograd.grad((z * cuda(x)).sum(), [a, b])
+        assert rel_err(ga, x * 0.7071) < TOL_FP32 and rel_err(gb, x * 0.7071) < TOL_FP32
+
+
+def test_tf32_rounding_policy():
+    """with the policy on, every stored value is the nearest TF32 number of the exact fp32 result"""
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import add_scale, fused_leaky_relu
+    x, b = rnd(1, 2, 64, 8, 8), rnd(2, 64)
+    y = fused_leaky_relu(cuda(x), cuda(b))
+    exact = O.fused_leaky_relu(x.float(), b.float())
+    assert torch.equal(y.cpu().double(), tf32(exact))
+    z = add_scale(cuda(x), cuda(x), 0.5)
+    assert torch.equal(z.cpu().double(), tf32(x.float()))
 
 
 # ------------------------------------------------------------------------------------------------ conv
@@ -157,11 +183,12 @@ def _conv_ref(x, w, stride, pad):
 def test_conv_fprop_dgrad_wgrad(case, impl):
     n, h, w_, c, k, r, stride, pad = case
     kern = backend.kernels()
-    x = rnd(11, n, c, h, w_)
-    wt = rnd(12, k, c, r, r) / math.sqrt(c * r * r)
+    # operands pre-rounded to TF32: products are then exact in fp32, so the kernels must agree with fp64 to ~1e-6
+    x = tf32(rnd(11, n, c, h, w_))
+    wt = tf32(rnd(12, k, c, r, r) / math.sqrt(c * r * r))
     xr, wr = x.clone().requires_grad_(), wt.clone().requires_grad_()
     yr = _conv_ref(xr, wr, stride, pad)
-    dy = rnd(13, *yr.shape)
+    dy = tf32(rnd(13, *yr.shape))
     gxr, gwr = torch.autograd.grad((yr * dy).sum(), [xr, wr])
     g = make_geom(n, h, w_, c, k, r, r, stride, pad, pad)
     prev, kern.conv_impl = kern.conv_impl, impl
@@ -174,16 +201,18 @@ def test_conv_fprop_dgrad_wgrad(case, impl):
         gw = kern.conv_wgrad(dyg, xg, g).permute(0, 3, 1, 2)
     finally:
         kern.conv_impl = prev
-    assert rel_err(y, yr) < TOL_TF32, ("fprop", rel_err(y, yr))
-    assert rel_err(gx, gxr) < TOL_TF32, ("dgrad", rel_err(gx, gxr))
-    assert rel_err(gw, gwr) < TOL_TF32, ("wgrad", rel_err(gw, gwr))
+    assert rel_err(y, yr) < 2e-5, ("fprop", rel_err(y, yr))
+    assert rel_err(gx, gxr) < 2e-5, ("dgrad", rel_err(gx, gxr))
+    assert rel_err(gw, gwr) < 2e-5, ("wgrad", rel_err(gw, gwr))
 
 
 def test_conv_transpose_and_linear():
     from swapping_autoencoder_pytorch_b200.stylegan2_op import conv_transpose2d, linear
-    x, w = rnd(1, 2, 64, 9, 9), rnd(2, 64, 32, 3, 3) / 24
+    x, w = tf32(rnd(1, 2, 64, 9, 9)), tf32(rnd(2, 64, 32, 3, 3) / 24)
     ref = F.conv_transpose2d(x, w, stride=2)
     assert rel_err(conv_transpose2d(cuda(x), cuda(w)), ref) < TOL_TF32
+    x, w = tf32(rnd(1, 2, 128, 17, 15)), tf32(rnd(2, 128, 96, 3, 3) / 24)      # ragged tiles, Cout not a multiple of 64
+    assert rel_err(conv_transpose2d(cuda(x), cuda(w)), F.conv_transpose2d(x, w, stride=2)) < TOL_TF32
     xl, wl = rnd(3, 16, 2048), rnd(4, 512, 2048) / 45
     assert rel_err(linear(cuda(xl), cuda(wl)), F.linear(xl, wl)) < TOL_TF32
     xl, wl = rnd(5, 6, 512), rnd(6, 1, 512) / 22
@@ -399,3 +428,48 @@ def test_train_steps_default_nets_256():
         assert k in g and math.isfinite(float(g[k])), (k, g)
     # first-iteration losses at init are ~softplus(0)=0.69-ish; guard against blow-ups
     assert 0.05 < float(d["D_real"]) < 5 and 0.05 < float(g["G_GAN_mix"]) < 5
+
+
+# ------------------------------------------------------------------------- every kernel call of a real step
+def _run_shadow(fn):
+    from tests.shadow_check import ShadowKernels
+    sh = ShadowKernels()
+    prev = backend.set_kernels(sh)
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        backend.set_kernels(prev)
+    bad = sh.failures()
+    assert len(sh.log) > 0
+    assert not bad, "kernel calls deviating from the oracle emulation (of %d):\n%s" % (
+        len(sh.log), "\n".join("%-18s %-90s %.3e" % b for b in bad[:25]))
+    return sh
+
+
+def test_shadow_resblock_forward_backward():
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    blk = L.ResBlock(32, 64).to(DEV)
+
+    def go():
+        x = torch.randn(2, 32, 32, 32, device=DEV, requires_grad=True)
+        y = blk(x)
+        gx, = torch.autograd.grad((y * torch.randn_like(y)).sum(), x, create_graph=True)
+        gx.pow(2).sum().backward()
+    _run_shadow(go)
+
+
+def test_shadow_tiny_model_training_steps():
+    """Every kernel call of a D step (+R1 double backward) and a G step of the reduced-capacity model."""
+    import swapping_autoencoder_pytorch_b200 as S
+    opt = default_options(**dict(TINY, num_gpus=1, R1_once_every=1))
+    torch.manual_seed(0)
+    model = S.create_model(opt)
+    trainer = S.create_optimizer(opt, model)
+    real = torch.randn(2, 3, 64, 64, device=DEV).clamp(-1, 1)
+
+    def go():
+        trainer.train_one_step({"real_A": real}, 0)
+        trainer.train_one_step({"real_A": real}, 0)
+    sh = _run_shadow(go)
+    assert len(sh.log) > 300
