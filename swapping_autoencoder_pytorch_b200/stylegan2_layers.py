@@ -19,8 +19,8 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv_transpose2d, fused_leaky_relu,
-                           fused_noise_bias_leaky_relu, linear, modulate, upfirdn2d)
+from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv2d_bias_act, conv2d_noise_bias_act, conv2d_residual,
+                           conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, modulate, upfirdn2d)
 
 _SQRT2 = math.sqrt(2.0)
 
@@ -195,7 +195,8 @@ class ModulatedConv2d(nn.Module):
             w = w * torch.rsqrt(w.square().sum(dim=(1, 2, 3), keepdim=True) + 1e-8)
         return w
 
-    def forward(self, input, style):
+    def modulated_input(self, input, style):
+        """input * (RMS-normalised) style — reference :269-284"""
         batch = input.shape[0]
         if style.dim() > 2:
             # spatially varying style (reference :269-276; evaluation-time only)
@@ -203,12 +204,14 @@ class ModulatedConv2d(nn.Module):
             style = self.modulation(style)
             if self.demodulate:
                 style = style * torch.rsqrt(style.square().mean(dim=1, keepdim=True) + 1e-8)
-            input = input * style
-        else:
-            s = self.modulation(style.reshape(batch, -1))
-            if self.demodulate:
-                s = s * torch.rsqrt(s.square().mean(dim=1, keepdim=True) + 1e-8)
-            input = modulate(input, s)
+            return input * style
+        s = self.modulation(style.reshape(batch, -1))
+        if self.demodulate:
+            s = s * torch.rsqrt(s.square().mean(dim=1, keepdim=True) + 1e-8)
+        return modulate(input, s)
+
+    def forward(self, input, style):
+        input = self.modulated_input(input, style)
         w = self.filter()
         if self.upsample:
             out = conv_transpose2d(input, w.transpose(0, 1), stride=2, padding=0)
@@ -216,6 +219,16 @@ class ModulatedConv2d(nn.Module):
         if self.downsample:
             return conv2d(self.blur(input), w, stride=2, padding=0)
         return conv2d(input, w, padding=self.padding)
+
+
+class _ShapeOnly:
+    """stand-in for a not-yet-computed conv output: NoiseInjection only needs its shape, dtype and device"""
+
+    def __init__(self, shape, like):
+        self.shape, self._like = shape, like
+
+    def new_empty(self, *size):
+        return self._like.new_empty(*size)
 
 
 class NoiseInjection(nn.Module):
@@ -268,8 +281,22 @@ class StyledConv(nn.Module):
         self.activate = FusedLeakyReLU(out_channel)
 
     def forward(self, input, style, noise=None):
-        out = self.conv(input, style)
-        act = self.activate
+        conv, act = self.conv, self.activate
+        if not (conv.upsample or conv.downsample):
+            # plain 3x3: noise + bias + activation ride in the conv kernel's epilogue
+            x = conv.modulated_input(input, style)
+            w = conv.filter()
+            if not self.use_noise:
+                return conv2d_bias_act(x, w, act.bias, padding=conv.padding, negative_slope=act.negative_slope,
+                                       scale=act.scale)
+            shape = torch.Size((x.shape[0], conv.out_channel, x.shape[2], x.shape[3]))
+            z = self.noise.resolve_noise(_ShapeOnly(shape, x), noise)
+            if z.shape[0] == x.shape[0] and z.shape[1] == 1 and z.shape[2:] == x.shape[2:]:
+                return conv2d_noise_bias_act(x, w, z, self.noise.weight, act.bias, padding=conv.padding,
+                                             negative_slope=act.negative_slope, scale=act.scale)
+            out = conv2d(x, w, padding=conv.padding)
+            return act(out + self.noise.weight * z)        # broadcast noise: unfused
+        out = conv(input, style)
         if not self.use_noise:
             return act(out)
         z = self.noise.resolve_noise(out, noise)
@@ -394,6 +421,19 @@ class ConvLayer(nn.Sequential):
             layers.append(("Act", FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2)))
         super().__init__(OrderedDict(layers))
 
+    def forward(self, x):
+        mods = self._modules
+        for name in ("Blur", "RefPad"):
+            if name in mods:
+                x = mods[name](x)
+        conv, act = mods["Conv"], mods.get("Act")
+        if isinstance(act, FusedLeakyReLU) and conv.bias is None:
+            # bias + leaky-ReLU applied in the conv kernel's epilogue
+            return conv2d_bias_act(x, conv.weight * conv.scale, act.bias, stride=conv.stride, padding=conv.padding,
+                                   negative_slope=act.negative_slope, scale=act.scale)
+        x = conv(x)
+        return act(x) if act is not None else x
+
 
 class ResBlock(nn.Module):
     """conv1 (3x3) -> conv2 (blur + 3x3 stride 2) plus 1x1 skip, summed and divided by sqrt(2) (reference :672-693)."""
@@ -409,6 +449,12 @@ class ResBlock(nn.Module):
 
     def forward(self, input):
         out = self.conv2(self.conv1(input))
+        mods = self.skip._modules
+        conv = mods["Conv"]
+        if conv.bias is None and "Act" not in mods and "RefPad" not in mods:
+            # skip branch: [Blur] -> 1x1 conv whose epilogue performs the residual merge
+            h = mods["Blur"](input) if "Blur" in mods else input
+            return conv2d_residual(h, conv.weight * conv.scale, out, 1.0 / _SQRT2, stride=conv.stride, padding=conv.padding)
         return add_scale(out, self.skip(input), 1.0 / _SQRT2)
 
 

@@ -11,6 +11,7 @@ Weights enter in the reference's parameter layout ``[Cout, Cin, R, S]`` and are 
 ``[K, R, S, C]`` by a (differentiable) torch permute of the small filter tensor.
 """
 import torch
+import torch.nn.functional as F
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
@@ -84,16 +85,134 @@ class _ConvWgrad(Function):
         return d_dy, d_x, None
 
 
-def conv2d(input, weight, bias=None, stride=1, padding=0):
-    """``F.conv2d(input, weight, bias, stride, padding)`` for NCHW-shaped input, [Cout,Cin,R,S] weight."""
+class _ConvBiasAct(Function):
+    """lrelu(conv(x, w) + b) * gain with the bias / activation applied in the conv kernel's epilogue (no separate
+    pass over the output).  Backward = the differentiable masked-gradient Function of fused_act.py followed by
+    dgrad / wgrad, so the discriminators' R1 double backward flows through it (EqualConv2d + FusedLeakyReLU,
+    stylegan2_layers.py:136-142 + fused_act.py:89-96)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, g, negative_slope, gain):
+        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g), bias=bias.contiguous(),
+                                                 act=3, alpha=negative_slope, gain=gain))
+        ctx.g, ctx.cfg = g, (negative_slope, gain)
+        ctx.save_for_backward(x, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .fused_act import FusedLeakyReLUFunctionBackward
+        x, w, out = ctx.saved_tensors
+        gi, gb = FusedLeakyReLUFunctionBackward.apply(dy, out, *ctx.cfg)
+        dx = _ConvDgrad.apply(gi, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dw = _ConvWgrad.apply(gi, x, ctx.g) if ctx.needs_input_grad[1] else None
+        return dx, dw, gb, None, None, None
+
+
+class _ConvNoiseBiasAct(Function):
+    """StyledConv tail fused into the conv epilogue: lrelu(conv(x, w) + nw * noise + b) * gain
+    (stylegan2_layers.py:398-405).  Generator only, hence once-differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, w, noise, noise_weight, bias, g, negative_slope, gain):
+        noise_flat = noise.reshape(-1).contiguous()
+        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, bias=bias.contiguous(), act=3,
+                                                 alpha=negative_slope, gain=gain, noise=noise_flat,
+                                                 noise_weight=noise_weight.contiguous()))
+        ctx.g, ctx.cfg = g, (negative_slope, gain, tuple(noise.shape))
+        ctx.save_for_backward(x, w, out, noise_flat, noise_weight)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, out, noise_flat, noise_weight = ctx.saved_tensors
+        negative_slope, gain, noise_shape = ctx.cfg
+        k = backend.kernels()
+        gi, gb, gnw = k.bias_act_backward(_nhwc(dy), _nhwc(out), negative_slope, gain, want_bias=True, noise=noise_flat)
+        dx = _nchw(k.conv_dgrad(gi, w.contiguous(), ctx.g)) if ctx.needs_input_grad[0] else None
+        dw = k.conv_wgrad(gi, _nhwc(x), ctx.g) if ctx.needs_input_grad[1] else None
+        g_noise = None
+        if ctx.needs_input_grad[2]:
+            g_noise = (gi.sum(dim=3) * noise_weight).reshape(noise_shape)
+        return dx, dw, g_noise, gnw, gb, None, None, None
+
+
+class _ConvResidual(Function):
+    """(conv(x, w) + res) * scale — the ResBlock merge "(out + skip) / sqrt(2)" (stylegan2_layers.py:691) folded into
+    the skip convolution's epilogue.  Linear in (x, res) and bilinear with w: backward reuses the differentiable
+    primitives, so it is valid under double backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, res, g, scale):
+        ctx.g, ctx.scale = g, scale
+        ctx.save_for_backward(x, w)
+        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, residual=_nhwc(res), res_scale=scale))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        gs = _AddScale.apply(dy, None, ctx.scale)
+        dx = _ConvDgrad.apply(gs, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dw = _ConvWgrad.apply(gs, x, ctx.g) if ctx.needs_input_grad[1] else None
+        return dx, dw, (gs if ctx.needs_input_grad[2] else None), None, None
+
+
+def _pad4(input, weight):
+    """RGB tensors (3 channels) are zero-padded to 4 so rows are 16-byte aligned and the kernels keep their vector
+    / TMA paths (the pad and the matching slice are differentiable torch ops on tiny tensors).  Returns
+    (input, weight, original Cout or None)."""
+    cin = input.shape[1]
+    if cin % 4 != 0:
+        extra = 4 - cin % 4
+        input = F.pad(input, (0, 0, 0, 0, 0, extra))
+        weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
+    cout = weight.shape[0]
+    if cout % 4 != 0:
+        weight = F.pad(weight, (0, 0, 0, 0, 0, 0, 0, 4 - cout % 4))
+        return input, weight, cout
+    return input, weight, None
+
+
+def _geom_for(input, weight, stride, padding):
     n, c, h, w_ = input.shape
     k, c2, r, s = weight.shape
     assert c == c2, "channel mismatch: input %d vs weight %d" % (c, c2)
     if (h + 2 * padding - r) < 0 or (w_ + 2 * padding - s) < 0:
         # same failure the reference hits at 64x64 with default options (SURVEY.md §0.5)
         raise RuntimeError("Kernel size can't be greater than actual input size")
-    g = make_geom(n, h, w_, c, k, r, s, stride, padding, padding)
+    return make_geom(n, h, w_, c, k, r, s, stride, padding, padding)
+
+
+def conv2d_bias_act(input, weight, bias, stride=1, padding=0, negative_slope=0.2, scale=2 ** 0.5):
+    """fused_leaky_relu(F.conv2d(input, weight, stride=stride, padding=padding), bias) in one kernel"""
+    input, weight, cout = _pad4(input, weight)
+    if cout is not None:
+        bias = F.pad(bias, (0, weight.shape[0] - cout))
+    g = _geom_for(input, weight, stride, padding)
+    out = _ConvBiasAct.apply(input, weight.permute(0, 2, 3, 1), bias, g, negative_slope, scale)
+    return out if cout is None else out[:, :cout]
+
+
+def conv2d_noise_bias_act(input, weight, noise, noise_weight, bias, padding=0, negative_slope=0.2, scale=2 ** 0.5):
+    """fused_leaky_relu(F.conv2d(input, weight, padding=padding) + noise_weight * noise, bias) in one kernel"""
+    g = _geom_for(input, weight, 1, padding)
+    return _ConvNoiseBiasAct.apply(input, weight.permute(0, 2, 3, 1), noise, noise_weight, bias, g, negative_slope, scale)
+
+
+def conv2d_residual(input, weight, residual, scale, stride=1, padding=0):
+    """(F.conv2d(input, weight, stride=stride, padding=padding) + residual) * scale in one kernel"""
+    g = _geom_for(input, weight, stride, padding)
+    return _ConvResidual.apply(input, weight.permute(0, 2, 3, 1), residual, g, scale)
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0):
+    """``F.conv2d(input, weight, bias, stride, padding)`` for NCHW-shaped input, [Cout,Cin,R,S] weight."""
+    input, weight, cout = _pad4(input, weight)
+    g = _geom_for(input, weight, stride, padding)
     out = _ConvFprop.apply(input, weight.permute(0, 2, 3, 1), g)
+    if cout is not None:
+        out = out[:, :cout]
     if bias is not None:
         out = out + bias.view(1, -1, 1, 1)
     return out
