@@ -139,7 +139,7 @@ def conv_roofline(trainer, images, device):
             out = fn(a, b, g, **kw)
             e1.record()
             flops = 2.0 * g.N * g.P * g.Q * g.K * g.R * g.S * g.C
-            records.append((e0, e1, flops, k.conv_impl_for(g, direction), g.key()))
+            records.append((e0, e1, flops, k.conv_impl_for(g, direction), g.key(), name))
             return out
         return timed
     try:
@@ -152,11 +152,24 @@ def conv_roofline(trainer, images, device):
         for n, fn in orig.items():
             setattr(k, n, fn)
     tot = {1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0]}
-    for e0, e1, flops, impl, _ in records:
+    per_shape = {}
+    for e0, e1, flops, impl, key, name in records:
         t = tot.setdefault(impl, [0.0, 0.0, 0])
+        sec = e0.elapsed_time(e1) * 1e-3
         t[0] += flops
-        t[1] += e0.elapsed_time(e1) * 1e-3
+        t[1] += sec
         t[2] += 1
+        ps = per_shape.setdefault((name, impl) + key, [0.0, 0.0, 0])
+        ps[0] += flops
+        ps[1] += sec
+        ps[2] += 1
+    dump = os.environ.get("SAE_BENCH_CONV_TABLE")
+    if dump:
+        with open(dump, "w") as f:
+            f.write("dir impl N H W C K R S P Q stride pad_t pad_l | calls ms TFLOP/s\n")
+            for kk, v in sorted(per_shape.items(), key=lambda kv: -kv[1][1]):
+                f.write("%s %s | %d %.3f %.1f\n" % (kk[0], " ".join(str(x) for x in kk[1:]), v[2], v[1] * 1e3,
+                                                  v[0] / max(v[1], 1e-12) / 1e12))
     return tot
 
 

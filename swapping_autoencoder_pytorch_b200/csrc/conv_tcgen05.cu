@@ -72,7 +72,8 @@ struct TcParams {
 };
 
 template <int BLOCK_N>
-constexpr int tc_stages() { return BLOCK_N >= 256 ? 4 : (BLOCK_N == 128 ? 4 : 6); }
+constexpr int tc_stages() { return BLOCK_N >= 128 ? 3 : 4; }   // <= 96 KB of ring per CTA: two CTAs co-reside on an SM,
+                                                                // one runs its epilogue while the other feeds the tensor core
 
 template <int BLOCK_N>
 constexpr size_t tc_smem_bytes() {
@@ -83,7 +84,7 @@ constexpr size_t tc_smem_bytes() {
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_out, const TcParams p) {
     constexpr int STAGES = tc_stages<BLOCK_N>();

@@ -32,9 +32,11 @@ struct WgParams {
     int stride, pad_t, pad_l;
     int R, S;
     int Ko, C;                       // channels of dy / x
-    int group_taps;                  // taps per tap group (<= 3); group g covers taps [g*group_taps, ...)
+    int group_taps;                  // taps per CTA (tap group); group y covers taps [y*group_taps, ...)
     int ntaps;
     int n_tiles_c;                   // number of 128-wide tiles along C
+    int cpt;                         // 32-channel sub-tiles per tap inside an accumulator: min(C,128)/32
+                                     // (narrow layers pack 4/cpt taps side by side into the 128 N-columns)
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
@@ -70,11 +72,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const int tile_o = blockIdx.x / p.n_tiles_c, tile_c = blockIdx.x % p.n_tiles_c;
     const int o0 = tile_o * 128, c0 = tile_c * 128;
     const int tap0 = blockIdx.y * p.group_taps;
-    const int ntap = min(p.group_taps, p.ntaps - tap0);
+    const int ntap = min(p.group_taps, p.ntaps - tap0);       // taps handled by this CTA
+    const int tpa = 4 / p.cpt;                                 // taps per accumulator
+    const int nacc = (ntap + tpa - 1) / tpa;                   // accumulators in use (<= 3)
+    const int nslots = ntap * p.cpt;                           // valid 32-column B sub-tiles
     const int chunk_begin = blockIdx.z * p.chunks_per_split;
     const int chunk_end = min(chunk_begin + p.chunks_per_split, p.chunks_total);
     const int KB = chunk_end - chunk_begin;
-    const uint32_t stage_tx = (uint32_t)WG_OPER * (1 + ntap);
+    const uint32_t stage_tx = (uint32_t)WG_OPER + (uint32_t)nslots * WG_SUB;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
@@ -111,14 +116,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         tma_load_4d(sa + i * WG_SUB, &map_dy, bar_full + 8 * s, o0 + 32 * i, q0, p0, n0);
-                    for (int g = 0; g < ntap; ++g) {
-                        const int tap = tap0 + g;
+                    for (int q = 0; q < nslots; ++q) {
+                        // slot q = (accumulator q/4, 32-column group q%4) holds tap q/cpt, channels 32*(q%cpt)
+                        const int tap = tap0 + q / p.cpt;
                         const int r = tap / p.S, sx = tap - r * p.S;
-                        const uint32_t sb = sa + (uint32_t)(1 + g) * WG_OPER;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            tma_load_4d(sb + i * WG_SUB, &map_x, bar_full + 8 * s, c0 + 32 * i,
-                                        q0 * p.stride - p.pad_l + sx, p0 * p.stride - p.pad_t + r, n0);
+                        tma_load_4d(sa + WG_OPER + (uint32_t)q * WG_SUB, &map_x, bar_full + 8 * s, c0 + 32 * (q % p.cpt),
+                                    q0 * p.stride - p.pad_l + sx, p0 * p.stride - p.pad_t + r, n0);
                     }
                 }
             }
@@ -131,7 +134,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
                     const uint64_t da = make_desc_mn_sw128(sa);
-                    for (int g = 0; g < ntap; ++g) {
+                    for (int g = 0; g < nacc; ++g) {
                         const uint64_t db = make_desc_mn_sw128(sa + (uint32_t)(1 + g) * WG_OPER);
 #pragma unroll
                         for (int k = 0; k < WG_KPIX / 8; ++k) {
@@ -151,14 +154,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             mbar_wait(bar_acc, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t ld = (int64_t)p.ntaps * p.C;
-            for (int g = 0; g < ntap; ++g) {
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
+            for (int q = 0; q < nslots; ++q) {
+                {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * 128 + ch * 32), v);
-                    const int c = c0 + ch * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(q * 32), v);
+                    const int c = c0 + 32 * (q % p.cpt);
                     if (o < p.Ko && c < p.C) {
-                        float* dst = dw + (int64_t)o * ld + (int64_t)(tap0 + g) * p.C + c;
+                        float* dst = dw + (int64_t)o * ld + (int64_t)(tap0 + q / p.cpt) * p.C + c;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j]),
@@ -203,12 +205,17 @@ int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
     p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l; p.R = g->R; p.S = g->S;
     p.Ko = g->K; p.C = g->C;
     p.ntaps = g->R * g->S;
-    p.group_taps = p.ntaps < WG_MAX_GROUP ? p.ntaps : WG_MAX_GROUP;
+    p.cpt = (g->C >= 128 ? 128 : g->C) / 32;                       // C is a multiple of 32 here: 1, 2, 3 or 4
+    if (p.cpt == 3) p.cpt = 4;                                      // C = 96: keep one tap per accumulator (4th slot is OOB zero)
+    p.group_taps = WG_MAX_GROUP * (4 / p.cpt);
+    if (p.group_taps > p.ntaps) p.group_taps = p.ntaps;
     const int groups = (p.ntaps + p.group_taps - 1) / p.group_taps;
     const int tiles_o = (g->K + 127) / 128;
     p.n_tiles_c = (g->C + 127) / 128;
     const int tiles = tiles_o * p.n_tiles_c * groups;
-    int splits = (sm_count() + tiles - 1) / tiles;                  // one CTA per SM (192 KB of shared memory each)
+    // One CTA per SM (192 KB of shared memory each): choose the pixel split so the whole grid is ONE wave
+    // (tiles * splits <= SM count); a second, nearly empty wave would double the kernel time.
+    int splits = sm_count() / tiles;
     if (splits > p.chunks_total) splits = p.chunks_total;
     if (splits < 1) splits = 1;
     p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
