@@ -234,6 +234,174 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair kernel
+// Same algorithm with tcgen05 cta_group::2: two CTAs of a cluster (two consecutive pixel tiles, same output-channel
+// block) act as one 256-row MMA.  Each CTA loads its own A tile and HALF of the B (filter) tile; the pair's leader
+// issues M = 256 instructions that read A and B from both CTAs' shared memory, so per CTA the L2->SM traffic per MAC
+// halves on the filter side:  (16 KB A + BLOCK_N/2 * 128 B) per 128 x BLOCK_N x 32 MACs.  With BLOCK_N = 256 that is
+// 64 B/clk/SM at full tensor rate (the 1-CTA 128x128 tile needs 128 B/clk/SM and is L2-feed bound at ~45 %).
+template <int BLOCK_N>
+constexpr int tc2_stages() { return 4; }
+
+template <int BLOCK_N>
+constexpr size_t tc2_smem_bytes() {
+    size_t ring = (size_t)tc2_stages<BLOCK_N>() * (TC_A_BYTES + (BLOCK_N / 2) * 128);
+    size_t epi = (size_t)(BLOCK_N / 32) * TC_A_BYTES;
+    return (ring > epi ? ring : epi) + 1024 + 256;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks) {
+    constexpr int STAGES = tc2_stages<BLOCK_N>();
+    constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_HALF_BYTES;                 // per CTA
+    constexpr uint32_t TMEM_COLS = BLOCK_N;
+    // D fp32, A/B tf32 K-major, N = BLOCK_N, M = 256 (128 rows from each CTA)
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t RING = (uint32_t)STAGES * STAGE_BYTES;
+    constexpr uint32_t EPI = (uint32_t)(BLOCK_N / 32) * TC_A_BYTES;
+    constexpr uint32_t BAR_OFF = RING > EPI ? RING : EPI;
+    const uint32_t bar_full = base + BAR_OFF;
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_acc = bar_empty + 8 * STAGES;
+    const uint32_t tmem_slot = bar_acc + 8;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    // linear CTA id -> (pair of consecutive pixel tiles, output-channel block); the channel block is the fast index so
+    // the CTAs that re-read one activation tile run at the same time and hit it in L2
+    const int pair_id = blockIdx.x >> 1;
+    const int nblk = pair_id % n_blocks;
+    int tile = (pair_id / n_blocks) * 2 + (int)rank;
+    const int tq = tile % p.tiles_w; tile /= p.tiles_w;
+    const int tp = tile % p.tiles_h; tile /= p.tiles_h;
+    const int q0 = tq * p.tw, p0 = tp * p.th, n0 = tile * p.tn;          // beyond the batch for the padding tile: all OOB
+    const int col0 = nblk * BLOCK_N;
+    const int KB = p.ntaps * p.num_cblk;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                      // both CTAs' barriers exist before any remote complete_tx / commit arrives
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        if (elect_one()) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                const int t = kb / p.num_cblk, cb = kb - t * p.num_cblk;
+                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+                if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
+                tma2_load_4d(sa, &map_src, bar_full + 8 * s, cb * TC_BK, q0 * p.stride + p.ox[t], p0 * p.stride + p.oy[t], n0);
+                tma2_load_2d(sb, &map_w, bar_full + 8 * s, p.wk[t] + cb * TC_BK, col0 + (int)rank * (BLOCK_N / 2));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (leader && elect_one()) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(bar_full + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)
+                    umma2_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                umma2_commit(bar_empty + 8 * s);          // frees stage s in both CTAs
+            }
+            umma2_commit(bar_acc);                        // accumulators complete in both CTAs
+        }
+    } else {
+        // ===================================================== epilogue: identical to the 1-CTA kernel (own 128 rows)
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const int iw = row % p.tw, ih = (row / p.tw) % p.th, in_ = row / (p.tw * p.th);
+        const int n = n0 + in_, pp = p0 + ih, qq = q0 + iw;
+        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
+        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float nz = 0.f;
+        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+            const int colb = col0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float t = v[j];
+                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
+                t += nz;
+                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
+                t *= p.epi.gain;
+                v[j] = t;
+            }
+            if (p.epi.residual && valid) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 r = __ldg(r4 + j);
+                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
+                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
+                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
+                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
+                }
+            }
+            if (p.epi.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+            }
+            uint8_t* stg = smem_gen + (size_t)ch * TC_A_BYTES + (size_t)row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                tma_store_4d(&map_out, base + (uint32_t)ch * TC_A_BYTES, colb, q0, p0, n0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                      // nobody leaves (or frees TMEM) while the peer may still touch this CTA
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle) {
@@ -262,9 +430,7 @@ static bool tc_shape_ok(int src_c, int ncol, int ntaps, int stride, int ow) {
     return true;
 }
 
-template <int BLOCK_N>
-static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
-    TcParams p;
+static void tc_fill_params(const TcProblem& pr, const EpiParams& e, TcParams& p) {
     p.num_cblk = pr.SC / 32;
     p.ntaps = pr.ntaps;
     p.stride = pr.stride;
@@ -280,22 +446,23 @@ static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
     for (int t = 0; t < pr.ntaps; ++t) { p.oy[t] = (signed char)pr.oy[t]; p.ox[t] = (signed char)pr.ox[t]; p.wk[t] = pr.wk[t]; }
     p.o_mul = pr.o_mul; p.o_offy = pr.o_offy; p.o_offx = pr.o_offx; p.FH = pr.FH; p.FW = pr.FW;
     p.epi = e;
+}
 
-    CUtensorMap msrc, mw, mout;
+static int tc_encode_maps(const TcProblem& pr, const TcParams& p, int b_rows, CUtensorMap* msrc, CUtensorMap* mw, CUtensorMap* mout) {
     {
         cuuint64_t dims[4] = {(cuuint64_t)pr.SC, (cuuint64_t)pr.SW, (cuuint64_t)pr.SH, (cuuint64_t)pr.SN};
         cuuint64_t strides[3] = {(cuuint64_t)pr.SC * 4, (cuuint64_t)pr.SW * pr.SC * 4, (cuuint64_t)pr.SH * pr.SW * pr.SC * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)(p.tw * pr.stride), (cuuint32_t)(p.th * pr.stride), (cuuint32_t)p.tn};
         cuuint32_t es[4] = {1, (cuuint32_t)pr.stride, (cuuint32_t)pr.stride, 1};
-        int rc = encode_map(&msrc, pr.src, 4, dims, strides, box, es);
+        int rc = encode_map(msrc, pr.src, 4, dims, strides, box, es);
         if (rc) return rc;
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)pr.Ktot, (cuuint64_t)pr.Ncol};
         cuuint64_t strides[1] = {(cuuint64_t)pr.Ktot * 4};
-        cuuint32_t box[2] = {32, (cuuint32_t)BLOCK_N};
+        cuuint32_t box[2] = {32, (cuuint32_t)b_rows};
         cuuint32_t es[2] = {1, 1};
-        int rc = encode_map(&mw, pr.wmat, 2, dims, strides, box, es);
+        int rc = encode_map(mw, pr.wmat, 2, dims, strides, box, es);
         if (rc) return rc;
     }
     {
@@ -304,9 +471,19 @@ static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
                                  (cuuint64_t)pr.FH * pr.FW * pr.Ncol * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
         cuuint32_t es[4] = {1, 1, 1, 1};
-        int rc = encode_map(&mout, pr.out + ((int64_t)pr.o_offy * pr.FW + pr.o_offx) * pr.Ncol, 4, dims, strides, box, es);
+        int rc = encode_map(mout, pr.out + ((int64_t)pr.o_offy * pr.FW + pr.o_offx) * pr.Ncol, 4, dims, strides, box, es);
         if (rc) return rc;
     }
+    return SAE_OK;
+}
+
+template <int BLOCK_N>
+static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    TcParams p;
+    tc_fill_params(pr, e, p);
+    CUtensorMap msrc, mw, mout;
+    int rc = tc_encode_maps(pr, p, BLOCK_N, &msrc, &mw, &mout);
+    if (rc) return rc;
     constexpr size_t smem = tc_smem_bytes<BLOCK_N>();
     static bool attr_done = false;
     if (!attr_done) {
@@ -318,7 +495,55 @@ static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
     return check_launch("conv_tc");
 }
 
+// CTA-pair (cta_group::2) launch: cluster of 2 along x
+template <int BLOCK_N>
+static int tc2_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    TcParams p;
+    tc_fill_params(pr, e, p);
+    CUtensorMap msrc, mw, mout;
+    int rc = tc_encode_maps(pr, p, BLOCK_N / 2, &msrc, &mw, &mout);
+    if (rc) return rc;
+    constexpr size_t smem = tc2_smem_bytes<BLOCK_N>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int pairs = (tiles + 1) / 2;
+    const int n_blocks = pr.Ncol / BLOCK_N;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pairs * n_blocks * 2), 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks));
+    return check_launch("conv_tc2");
+}
+
+static int g_pair_mode = -1;     // -1 unread, 0 off, 1 on
+static bool pair_enabled() {
+    if (g_pair_mode < 0) {
+        const char* v = getenv("SAE_TC_PAIR");
+        g_pair_mode = (v && v[0] == '0') ? 0 : 1;
+    }
+    return g_pair_mode == 1;
+}
+
 static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    if (pair_enabled()) {
+        // enough pixel tiles to make pairs worthwhile; 256-wide channel blocks when the layer has them
+        const int64_t pixels = (int64_t)pr.SN * pr.OH * pr.OW;
+        if (pixels >= 2 * 128) {
+            if (pr.Ncol % 256 == 0) return tc2_launch<256>(pr, e, st);
+            if (pr.Ncol % 128 == 0) return tc2_launch<128>(pr, e, st);
+        }
+    }
     if (pr.Ncol % 128 == 0) return tc_launch<128>(pr, e, st);
     if (pr.Ncol % 64 == 0) return tc_launch<64>(pr, e, st);
     return tc_launch<32>(pr, e, st);
