@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 4
+#define SAE_ABI_VERSION 5
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -104,6 +104,15 @@ int sae_modulate_backward(const float* dy, const float* x, const float* s, float
  * sae_round_tf32: out = rna_tf32(x) (used on the small filter tensors before a tensor-core conv). */
 int sae_add_scale(const float* a, const float* b, float* out, int64_t n, float scale, int round_tf32, void* stream);
 int sae_round_tf32(const float* x, float* out, int64_t n, void* stream);
+
+/* out[n,2h,2w,c] = (bilinear_x2(skip[n,h,w,c]) + res) * scale — the generator's skip branch
+ * F.interpolate(skip, scale_factor=2, mode='bilinear', align_corners=False) followed by (skip + res) / sqrt(2)
+ * (models/networks/generator.py:51-53) in one pass; sae_upsample2x_backward is the adjoint of the interpolation
+ * times scale (gradient w.r.t. skip; the gradient w.r.t. res is sae_add_scale(dy, NULL, scale)). c % 4 == 0. */
+int sae_upsample2x_add_scale(const float* skip, const float* res, float* out, int n, int h, int w, int c, float scale,
+                             int round_tf32, void* stream);
+int sae_upsample2x_backward(const float* dy, float* dskip, int n, int h, int w, int c, float scale, int round_tf32,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * conv2d — dense implicit-GEMM convolution family on NHWC fp32 activations, TF32 tensor cores,

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Achieved HBM bandwidth of the memory-bound kernels at hot-path shapes (CUDA-event timed, L2 flushed).
+GB/s are ALGORITHMIC bytes: FIR 4*(N_in+N_out), bias-act fwd 8N / bwd 12N, modulate 8N, add_scale 12N."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from swapping_autoencoder_pytorch_b200 import backend  # noqa: E402
+
+
+def timeit(fn, flush, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    k = backend.kernels()
+    dev = torch.device("cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    k4 = torch.tensor([1., 3., 3., 1.], device=dev)
+    k4 = torch.outer(k4, k4) / 64
+    k3 = torch.tensor([1., 2., 1.], device=dev)
+    k3 = torch.outer(k3, k3) / 16
+    print("%-46s %9s %9s" % ("kernel / shape", "ms", "GB/s"))
+    for n, h, c in ((32, 256, 128), (32, 128, 256), (32, 64, 512), (256, 128, 32), (32, 256, 32)):
+        x = torch.randn(n, h, h, c, device=dev)
+        for name, kern, pad in (("fir4 pad(2,2)", k4, (2, 2)), ("fir4 pad(1,1)", k4, (1, 1)), ("fir3 pad(0,0)", k3, (0, 0))):
+            ms = timeit(lambda: k.upfirdn2d(x, kern, 1, 1, 1, 1, pad[0], pad[1], pad[0], pad[1]), flush)
+            oh = h + pad[0] + pad[1] - kern.shape[0] + 1
+            gb = 4.0 * (x.numel() + n * oh * oh * c) / 1e9
+            print("%-46s %9.3f %9.0f" % ("%s [%d,%d,%d,%d]" % (name, n, h, h, c), ms, gb / ms * 1e3))
+        b = torch.randn(c, device=dev)
+        ms = timeit(lambda: k.bias_act(x, b, None, 3, 0, 0.2, 1.414), flush)
+        print("%-46s %9.3f %9.0f" % ("bias_act fwd [%d,%d,%d,%d]" % (n, h, h, c), ms, 8.0 * x.numel() / 1e9 / ms * 1e3))
+        ms = timeit(lambda: k.bias_act_backward(x, x, 0.2, 1.414), flush)
+        print("%-46s %9.3f %9.0f" % ("bias_act bwd [%d,%d,%d,%d]" % (n, h, h, c), ms, 12.0 * x.numel() / 1e9 / ms * 1e3))
+        s = torch.randn(n, c, device=dev)
+        ms = timeit(lambda: k.modulate(x, s), flush)
+        print("%-46s %9.3f %9.0f" % ("modulate [%d,%d,%d,%d]" % (n, h, h, c), ms, 8.0 * x.numel() / 1e9 / ms * 1e3))
+        ms = timeit(lambda: k.modulate_backward(x, x, s), flush)
+        print("%-46s %9.3f %9.0f" % ("modulate bwd [%d,%d,%d,%d]" % (n, h, h, c), ms, 12.0 * x.numel() / 1e9 / ms * 1e3))
+        ms = timeit(lambda: k.add_scale(x, x, 0.7), flush)
+        print("%-46s %9.3f %9.0f" % ("add_scale [%d,%d,%d,%d]" % (n, h, h, c), ms, 12.0 * x.numel() / 1e9 / ms * 1e3))
+        if h <= 128:
+            r = torch.randn(n, 2 * h, 2 * h, c, device=dev)
+            ms = timeit(lambda: k.upsample2x_add_scale(x, r, 0.7), flush)
+            print("%-46s %9.3f %9.0f" % ("upsample2x_add [%d,%d,%d,%d]" % (n, h, h, c), ms, (4.0 * x.numel() + 8.0 * r.numel()) / 1e9 / ms * 1e3))
+            ms = timeit(lambda: k.upsample2x_backward(r, 0.7), flush)
+            print("%-46s %9.3f %9.0f" % ("upsample2x_bwd [%d,%d,%d,%d]" % (n, h, h, c), ms, (4.0 * x.numel() + 4.0 * r.numel()) / 1e9 / ms * 1e3))
+            del r
+        del x
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,27 @@ class CudaKernels:
                   "sae_add_scale")
         return out
 
+    def upsample2x_add_scale(self, skip, res, scale):
+        """(bilinear_x2(skip) + res) * scale;  skip [N,h,w,C], res [N,2h,2w,C]"""
+        _need_cuda(skip, res)
+        n, h, w, c = skip.shape
+        assert tuple(res.shape) == (n, 2 * h, 2 * w, c)
+        out = torch.empty_like(res)
+        with torch.cuda.device(res.device):
+            check(self.lib.sae_upsample2x_add_scale(_ptr(skip), _ptr(res), _ptr(out), n, h, w, c, scale,
+                                                    int(self.round_tf32), _stream()), "sae_upsample2x_add_scale")
+        return out
+
+    def upsample2x_backward(self, dy, scale):
+        """adjoint of the x2 bilinear interpolation times scale: dy [N,2h,2w,C] -> [N,h,w,C]"""
+        _need_cuda(dy)
+        n, oh, ow, c = dy.shape
+        out = torch.empty((n, oh // 2, ow // 2, c), device=dy.device, dtype=dy.dtype)
+        with torch.cuda.device(dy.device):
+            check(self.lib.sae_upsample2x_backward(_ptr(dy), _ptr(out), n, oh // 2, ow // 2, c, scale,
+                                                   int(self.round_tf32), _stream()), "sae_upsample2x_backward")
+        return out
+
     def _filter(self, w):
         """contiguous copy of a (small) filter tensor, rounded to TF32 when the policy says so"""
         w = w.contiguous()

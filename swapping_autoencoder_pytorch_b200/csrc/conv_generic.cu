@@ -58,7 +58,13 @@ conv_gather_kernel(const float* __restrict__ src, const float* __restrict__ wmat
 
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
-    const int KB = (p.K + BK - 1) / BK;
+    const int KB_total = (p.K + BK - 1) / BK;
+    // split-K (gridDim.z > 1, small-M GEMMs such as the style / head linears): this CTA reduces k-blocks
+    // [kb_begin, kb_begin + KB) and adds its partial tile to the zero-initialised output with fp32 atomics
+    const int kb_per = (KB_total + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int kb_begin = (int)blockIdx.z * kb_per;
+    const int KB = max(0, min(kb_per, KB_total - kb_begin));
+    const bool split = gridDim.z > 1;
 
     // per-thread row bookkeeping for the vector loader: rows (tid>>3) + j*32, j = 0..3
     int row_oy[4], row_ox[4];
@@ -80,7 +86,8 @@ conv_gather_kernel(const float* __restrict__ src, const float* __restrict__ wmat
         }
     }
 
-    auto load_stage = [&](int stage, int kb) {
+    auto load_stage = [&](int stage, int kb_rel) {
+        const int kb = kb_begin + kb_rel;
         float* as = As + stage * BM * LDS_K;
         float* bs = Bs + stage * BN * LDS_K;
         if (VEC) {
@@ -195,6 +202,56 @@ conv_gather_kernel(const float* __restrict__ src, const float* __restrict__ wmat
     cp_async_wait<0>();
 
     // epilogue
+    if (split) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int64_t m = m0 + wm * WM + i * 16 + g + h * 8;
+                if (m >= p.M) continue;
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        int col = n0 + wn * 32 + j * 8 + 2 * t + u;
+                        if (col < p.Ncol) atomicAdd(out + m * p.Ncol + col, acc[i][j][h * 2 + u]);
+                    }
+            }
+        return;
+    }
+    if (p.Ncol % 4 == 0) {
+        // stage the tile in shared memory (the pipeline buffers are free now) and write whole rows with float4 stores:
+        // the m16n8 fragment layout would otherwise scatter 8-byte stores over 8 rows per instruction
+        constexpr int LDC = BN + 4;
+        __syncthreads();
+        float* cs = smem;
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = wm * WM + i * 16 + g + h * 8;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int c = wn * 32 + j * 8 + 2 * t;
+                    *reinterpret_cast<float2*>(cs + r * LDC + c) = make_float2(acc[i][j][h * 2], acc[i][j][h * 2 + 1]);
+                }
+            }
+        __syncthreads();
+        constexpr int C4 = BN / 4;
+        for (int f = tid; f < BM * C4; f += NTHREADS) {
+            const int r = f / C4, c4 = f - r * C4;
+            const int64_t m = m0 + r;
+            const int col = n0 + c4 * 4;
+            if (m >= p.M || col >= p.Ncol) continue;
+            float4 v = *reinterpret_cast<const float4*>(cs + r * LDC + c4 * 4);
+            v.x = apply_epi(e, v.x, m, col, p.Ncol);
+            v.y = apply_epi(e, v.y, m, col + 1, p.Ncol);
+            v.z = apply_epi(e, v.z, m, col + 2, p.Ncol);
+            v.w = apply_epi(e, v.w, m, col + 3, p.Ncol);
+            *reinterpret_cast<float4*>(out + m * p.Ncol + col) = v;
+        }
+        return;
+    }
     const bool even = (p.Ncol % 2 == 0);
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
@@ -403,6 +460,17 @@ static int launch_gather(const float* src, const float* wmat, float* out, const 
         attr_done = true;
     }
     dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.Ncol + BN - 1) / BN));
+    // small-M, deep-K problems (linears): split K so more than a handful of SMs work on them
+    const int kblocks = (p.K + BK - 1) / BK;
+    const bool plain = !e.bias && !e.noise && !e.residual && e.act == 1 && e.gain == 1.f;
+    if (plain && grid.x * grid.y <= 16 && kblocks >= 16) {
+        unsigned z = (unsigned)(kblocks / 4);
+        if (z > 32) z = 32;
+        if (z > 1) {
+            grid.z = z;
+            SAE_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)p.M * p.Ncol * sizeof(float), st));
+        }
+    }
     conv_gather_kernel<BN, VEC><<<grid, NTHREADS, smem, st>>>(src, wmat, out, p, e);
     return check_launch("conv_gather");
 }

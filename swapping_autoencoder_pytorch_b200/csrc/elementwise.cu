@@ -245,6 +245,80 @@ add_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, float
     }
 }
 
+// ------------------------------------------------------------ bilinear x2 upsample fused with the residual merge
+// out[n,y,x,c] = (bilinear2x(skip)[n,y,x,c] + res[n,y,x,c]) * scale   (align_corners = False, the generator's skip
+// branch: F.interpolate(..., scale_factor=2, mode='bilinear') followed by (skip + res) / sqrt(2), generator.py:51-53)
+__device__ __forceinline__ void bilin_src(int d, int in_size, int& i0, int& i1, float& l0, float& l1) {
+    float src = 0.5f * (d + 0.5f) - 0.5f;          // area_pixel_compute_source_index, scale 1/2
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_add_kernel(const float4* __restrict__ skip, const float4* __restrict__ res, float4* __restrict__ out,
+                      int64_t total_v, int h, int w, int cv, float scale, int round_tf32) {
+    const int oh = 2 * h, ow = 2 * w;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_v; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv);
+        int64_t t = i / cv;
+        const int x = (int)(t % ow); t /= ow;
+        const int y = (int)(t % oh);
+        const int64_t n = t / oh;
+        int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+        bilin_src(y, h, y0, y1, ly0, ly1);
+        bilin_src(x, w, x0, x1, lx0, lx1);
+        const float4* sb = skip + n * (int64_t)h * w * cv + c;
+        const float4 a = __ldg(sb + ((int64_t)y0 * w + x0) * cv), b = __ldg(sb + ((int64_t)y0 * w + x1) * cv);
+        const float4 d = __ldg(sb + ((int64_t)y1 * w + x0) * cv), e = __ldg(sb + ((int64_t)y1 * w + x1) * cv);
+        const float4 r = ldg_stream(res + i);
+        float4 o;
+        o.x = (ly0 * (lx0 * a.x + lx1 * b.x) + ly1 * (lx0 * d.x + lx1 * e.x) + r.x) * scale;
+        o.y = (ly0 * (lx0 * a.y + lx1 * b.y) + ly1 * (lx0 * d.y + lx1 * e.y) + r.y) * scale;
+        o.z = (ly0 * (lx0 * a.z + lx1 * b.z) + ly1 * (lx0 * d.z + lx1 * e.z) + r.z) * scale;
+        o.w = (ly0 * (lx0 * a.w + lx1 * b.w) + ly1 * (lx0 * d.w + lx1 * e.w) + r.w) * scale;
+        if (round_tf32) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
+        out[i] = o;
+    }
+}
+
+// adjoint of the x2 bilinear interpolation, times scale: one thread per low-resolution element gathers the (up to 5x5)
+// high-resolution gradients whose interpolation stencil touches it — no atomics
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dskip, int64_t total_v, int h, int w, int cv,
+                      float scale, int round_tf32) {
+    const int oh = 2 * h, ow = 2 * w;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_v; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv);
+        int64_t t = i / cv;
+        const int x = (int)(t % w); t /= w;
+        const int y = (int)(t % h);
+        const int64_t n = t / h;
+        const float4* gb = dy + n * (int64_t)oh * ow * cv + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int yy = max(2 * y - 2, 0); yy <= min(2 * y + 2, oh - 1); ++yy) {
+            int y0, y1; float ly0, ly1;
+            bilin_src(yy, h, y0, y1, ly0, ly1);
+            const float wy = (y0 == y ? ly0 : 0.f) + (y1 == y ? ly1 : 0.f);
+            if (wy == 0.f) continue;
+            for (int xx = max(2 * x - 2, 0); xx <= min(2 * x + 2, ow - 1); ++xx) {
+                int x0, x1; float lx0, lx1;
+                bilin_src(xx, w, x0, x1, lx0, lx1);
+                const float wx = (x0 == x ? lx0 : 0.f) + (x1 == x ? lx1 : 0.f);
+                if (wx == 0.f) continue;
+                const float4 g = __ldg(gb + ((int64_t)yy * ow + xx) * cv);
+                const float ww = wy * wx;
+                acc.x = fmaf(ww, g.x, acc.x); acc.y = fmaf(ww, g.y, acc.y); acc.z = fmaf(ww, g.z, acc.z); acc.w = fmaf(ww, g.w, acc.w);
+            }
+        }
+        acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+        if (round_tf32) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
+        dskip[i] = acc;
+    }
+}
+
 // --------------------------------------------------------------------------- bucket pack/unpack
 __global__ void __launch_bounds__(256)
 bucket_copy_kernel(float* const* __restrict__ ptrs, const int64_t* __restrict__ offsets,
@@ -373,6 +447,31 @@ extern "C" int sae_add_scale(const float* a, const float* b, float* out, int64_t
     if (n % 4 == 0 && al % 16 == 0) add_scale_kernel<4><<<grid_for(n / 4, 256), 256, 0, st>>>(a, b, out, n / 4, scale, round_tf32);
     else add_scale_kernel<1><<<grid_for(n, 256), 256, 0, st>>>(a, b, out, n, scale, round_tf32);
     return check_launch("add_scale");
+}
+
+extern "C" int sae_upsample2x_add_scale(const float* skip, const float* res, float* out, int n, int h, int w, int c, float scale,
+                                        int round_tf32, void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!skip || !res || !out || n < 0 || h <= 0 || w <= 0 || c <= 0 || c % 4 != 0)
+        return fail(SAE_E_INVALID, "upsample2x_add_scale: bad arguments (channels must be a multiple of 4)");
+    if (((reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
+        return fail(SAE_E_INVALID, "upsample2x_add_scale: pointers must be 16-byte aligned");
+    int64_t tv = (int64_t)n * 4 * h * w * (c / 4);
+    upsample2x_add_kernel<<<grid_for(tv, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(skip), reinterpret_cast<const float4*>(res), reinterpret_cast<float4*>(out), tv, h, w, c / 4,
+        scale, round_tf32);
+    return check_launch("upsample2x_add_scale");
+}
+
+extern "C" int sae_upsample2x_backward(const float* dy, float* dskip, int n, int h, int w, int c, float scale, int round_tf32,
+                                       void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!dy || !dskip || n < 0 || h <= 0 || w <= 0 || c <= 0 || c % 4 != 0)
+        return fail(SAE_E_INVALID, "upsample2x_backward: bad arguments (channels must be a multiple of 4)");
+    int64_t tv = (int64_t)n * h * w * (c / 4);
+    upsample2x_bwd_kernel<<<grid_for(tv, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dskip), tv, h, w, c / 4, scale, round_tf32);
+    return check_launch("upsample2x_backward");
 }
 
 extern "C" int sae_round_tf32(const float* x, float* out, int64_t n, void* stream) {

@@ -7,7 +7,7 @@ import torch.nn.functional as F
 
 from .. import util
 from ..stylegan2_layers import ConvLayer, EqualLinear, StyledConv, ToRGB
-from ..stylegan2_op import add_scale
+from ..stylegan2_op import add_scale, upsample2x_add_scale
 from .base_network import BaseNetwork
 
 _INV_SQRT2 = 1.0 / math.sqrt(2.0)
@@ -52,8 +52,11 @@ class UpsamplingResnetBlock(torch.nn.Module):
         self.skip = ConvLayer(inch, outch, 1, activate=True, bias=True) if inch != outch else torch.nn.Identity()
 
     def forward(self, x, style):
-        skip = F.interpolate(self.skip(x), scale_factor=2, mode='bilinear', align_corners=False)
         res = self.conv2(self.conv1(x, style), style)
+        skip = self.skip(x)
+        if skip.shape[1] % 4 == 0:
+            return upsample2x_add_scale(skip, res, _INV_SQRT2)      # bilinear x2 + merge in one kernel
+        skip = F.interpolate(skip, scale_factor=2, mode='bilinear', align_corners=False)
         return add_scale(skip, res, _INV_SQRT2)
 
 

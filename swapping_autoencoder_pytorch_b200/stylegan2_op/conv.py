@@ -283,3 +283,26 @@ class _AddScale(Function):
 
 def add_scale(a, b, scale):
     return _AddScale.apply(a, b, scale)
+
+
+class _Upsample2xAddScale(Function):
+    """(bilinear_x2(skip) + res) * scale in one kernel — the generator's upsampling-block merge
+    (generator.py:51-53).  Generator only: once-differentiable."""
+
+    @staticmethod
+    def forward(ctx, skip, res, scale):
+        ctx.scale = scale
+        return _nchw(backend.kernels().upsample2x_add_scale(_nhwc(skip), _nhwc(res), scale))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        k = backend.kernels()
+        g = _nhwc(dy)
+        d_skip = _nchw(k.upsample2x_backward(g, ctx.scale)) if ctx.needs_input_grad[0] else None
+        d_res = _nchw(k.add_scale(g, None, ctx.scale)) if ctx.needs_input_grad[1] else None
+        return d_skip, d_res, None
+
+
+def upsample2x_add_scale(skip, res, scale):
+    return _Upsample2xAddScale.apply(skip, res, scale)

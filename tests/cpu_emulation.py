@@ -76,6 +76,18 @@ class EmulatedKernels:
     def add_scale(self, a, b, scale):
         return (a + b) * scale if b is not None else a * scale
 
+    def upsample2x_add_scale(self, skip, res, scale):
+        up = F.interpolate(_nchw(skip), scale_factor=2, mode="bilinear", align_corners=False)
+        return (_nhwc(up) + res) * scale
+
+    def upsample2x_backward(self, dy, scale):
+        n, oh, ow, c = dy.shape
+        x0 = torch.zeros(n, c, oh // 2, ow // 2, dtype=dy.dtype, requires_grad=True)
+        with torch.enable_grad():
+            up = F.interpolate(x0, scale_factor=2, mode="bilinear", align_corners=False)
+        g, = torch.autograd.grad(up, x0, _nchw(dy).detach())
+        return _nhwc(g) * scale
+
     def _epilogue(self, y, bias=None, act=1, alpha=0.2, gain=1.0, noise=None, noise_weight=None, residual=None,
                   res_scale=1.0, round_tf32=None):
         if bias is not None:

@@ -73,6 +73,12 @@ class ShadowKernels:
     def add_scale(self, a, b, scale):
         return self._both("add_scale", "x%s" % (tuple(a.shape),), (a, b, scale), {})
 
+    def upsample2x_add_scale(self, skip, res, scale):
+        return self._both("upsample2x_add_scale", "x%s" % (tuple(skip.shape),), (skip, res, scale), {})
+
+    def upsample2x_backward(self, dy, scale):
+        return self._both("upsample2x_backward", "x%s" % (tuple(dy.shape),), (dy, scale), {})
+
     def _impl_name(self, g, d, impl):
         return impl if impl is not None else self.real.conv_impl_for(g, d)
 

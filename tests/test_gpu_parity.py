@@ -143,6 +143,21 @@ def test_modulate_and_add_scale(exact_fp32):
         assert rel_err(ga, x * 0.7071) < TOL_FP32 and rel_err(gb, x * 0.7071) < TOL_FP32
 
 
+def test_upsample2x_add_scale(exact_fp32):
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import upsample2x_add_scale
+    for shape in ((2, 8, 5, 7), (3, 128, 16, 16), (1, 256, 1, 3)):
+        skip, res = rnd(1, *shape), rnd(2, shape[0], shape[1], 2 * shape[2], 2 * shape[3])
+        sr, rr = skip.clone().requires_grad_(), res.clone().requires_grad_()
+        ref = (F.interpolate(sr, scale_factor=2, mode="bilinear", align_corners=False) + rr) * 0.7071
+        w = rnd(3, *ref.shape)
+        gs_r, gr_r = torch.autograd.grad((ref * w).sum(), [sr, rr])
+        sg, rg = cuda(skip).requires_grad_(), cuda(res).requires_grad_()
+        out = upsample2x_add_scale(sg, rg, 0.7071)
+        assert rel_err(out, ref) < TOL_FP32
+        gs, gr = torch.autograd.grad((out * cuda(w)).sum(), [sg, rg])
+        assert rel_err(gs, gs_r) < TOL_FP32 and rel_err(gr, gr_r) < TOL_FP32
+
+
 def test_tf32_rounding_policy():
     """with the policy on, every stored value is the nearest TF32 number of the exact fp32 result"""
     from swapping_autoencoder_pytorch_b200.stylegan2_op import add_scale, fused_leaky_relu
