@@ -57,8 +57,30 @@ class CudaKernels:
         # as fp32): the tensor cores ignore the low 13 mantissa bits of their operands, so rounding in the producer
         # makes that truncation exact and unbiased.  Set False for bit-exact fp32 results from the pointwise kernels.
         self.round_tf32 = True
+        self._sep_cache = {}
 
     # ------------------------------------------------------------------ FIR
+    def _separable_taps(self, kernel):
+        """1-D factors (ctypes float arrays) of a rank-1 FIR kernel, or None.  Decided once per kernel buffer (one
+        device->host read at first use, then cached on (pointer, version, shape))."""
+        key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
+        hit = self._sep_cache.get(key, False)
+        if hit is not False:
+            return hit
+        k = kernel.detach().double().cpu()
+        res = None
+        kh, kw = k.shape
+        if kh == kw and kh <= 4 and float(k.abs().max()) > 0:
+            flat = int(k.abs().argmax())
+            i0, j0 = flat // kw, flat % kw
+            col, row = k[:, j0].clone(), k[i0, :] / k[i0, j0]
+            if float((torch.outer(col, row) - k).abs().max()) <= 1e-7 * float(k.abs().max()):
+                res = ((ctypes.c_float * kh)(*[float(v) for v in col]), (ctypes.c_float * kw)(*[float(v) for v in row]))
+        if len(self._sep_cache) > 256:
+            self._sep_cache.clear()
+        self._sep_cache[key] = res
+        return res
+
     def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
         _need_cuda(x, kernel)
         n, h, w, c = x.shape
@@ -66,6 +88,15 @@ class CudaKernels:
         oh = (h * up_y + pad_y0 + pad_y1 - kh) // down_y + 1
         ow = (w * up_x + pad_x0 + pad_x1 - kw) // down_x + 1
         out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
+        if up_x == up_y == down_x == down_y == 1 and c % 4 == 0 and n * ((oh + 15) // 16) * ow * (c // 4) < 2 ** 32 \
+                and x.data_ptr() % 16 == 0 and n > 0:
+            taps = self._separable_taps(kernel)
+            if taps is not None:
+                with torch.cuda.device(x.device):
+                    check(self.lib.sae_upfirdn2d_separable(_ptr(x), taps[0], taps[1], _ptr(out), n, h, w, c, kh, kw, pad_x0,
+                                                           pad_x1, pad_y0, pad_y1, int(self.round_tf32), _stream()),
+                          "sae_upfirdn2d_separable")
+                return out
         with torch.cuda.device(x.device):
             check(self.lib.sae_upfirdn2d(_ptr(x), _ptr(kernel), _ptr(out), n, h, w, c, kh, kw, up_x, up_y,
                                          down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, int(self.round_tf32), _stream()),

@@ -241,17 +241,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
 // halves on the filter side:  (16 KB A + BLOCK_N/2 * 128 B) per 128 x BLOCK_N x 32 MACs.  With BLOCK_N = 256 that is
 // 64 B/clk/SM at full tensor rate (the 1-CTA 128x128 tile needs 128 B/clk/SM and is L2-feed bound at ~45 %).
 template <int BLOCK_N>
-constexpr int tc2_stages() { return 4; }
+constexpr int tc2_stages() { return 3; }      // <= 96 KB per CTA: two pair-CTAs co-reside per SM (2 x 256 TMEM columns),
+                                              // one drains its accumulators while the other feeds the tensor core
 
 template <int BLOCK_N>
 constexpr size_t tc2_smem_bytes() {
-    size_t ring = (size_t)tc2_stages<BLOCK_N>() * (TC_A_BYTES + (BLOCK_N / 2) * 128);
-    size_t epi = (size_t)(BLOCK_N / 32) * TC_A_BYTES;
-    return (ring > epi ? ring : epi) + 1024 + 256;
+    // the epilogue staging cycles through the ring's 16 KB slots (see NBUF below), so the ring size is all that counts
+    return (size_t)tc2_stages<BLOCK_N>() * (TC_A_BYTES + (BLOCK_N / 2) * 128) + 1024 + 256;
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks) {
     constexpr int STAGES = tc2_stages<BLOCK_N>();
@@ -264,8 +264,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t RING = (uint32_t)STAGES * STAGE_BYTES;
-    constexpr uint32_t EPI = (uint32_t)(BLOCK_N / 32) * TC_A_BYTES;
-    constexpr uint32_t BAR_OFF = RING > EPI ? RING : EPI;
+    constexpr uint32_t BAR_OFF = RING;
+    constexpr int NCHUNK = BLOCK_N / 32;
+    constexpr int NBUF = (int)(RING / TC_A_BYTES) < NCHUNK ? (int)(RING / TC_A_BYTES) : NCHUNK;   // 16 KB staging slots
     const uint32_t bar_full = base + BAR_OFF;
     const uint32_t bar_empty = bar_full + 8 * STAGES;
     const uint32_t bar_acc = bar_empty + 8 * STAGES;
@@ -351,7 +352,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         float nz = 0.f;
         if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
 #pragma unroll 1
-        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+            if (NBUF < NCHUNK && ch >= NBUF) {
+                // staging slot (ch % NBUF) is still being read by the TMA store of chunk ch - NBUF: wait for it
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
             const int colb = col0 + ch * 32;
@@ -379,7 +385,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
             }
-            uint8_t* stg = smem_gen + (size_t)ch * TC_A_BYTES + (size_t)row * 128;
+            uint8_t* stg = smem_gen + (size_t)(ch % NBUF) * TC_A_BYTES + (size_t)row * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -388,7 +394,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && lane == 0) {
-                tma_store_4d(&map_out, base + (uint32_t)ch * TC_A_BYTES, colb, q0, p0, n0);
+                tma_store_4d(&map_out, base + (uint32_t)(ch % NBUF) * TC_A_BYTES, colb, q0, p0, n0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }

@@ -17,18 +17,17 @@ static inline unsigned grid_for(int64_t work_items, int threads, int per_sm = 8)
 }
 
 // ----------------------------------------------------------------------------- bias_act forward
-template <int VEC>
+template <int VEC, typename IDX>
 __global__ void __launch_bounds__(256)
 bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ ref,
-                float* __restrict__ out, int64_t size_v, int64_t step_b, int size_b,
+                float* __restrict__ out, IDX size_v, IDX step_b, int size_b,
                 int act, int grad, float alpha, float scale,
                 const float* __restrict__ noise, const float* __restrict__ noise_weight, int64_t noise_div,
                 int round_tf32) {
     const float nw = noise ? __ldg(noise_weight) : 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < size_v;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (IDX i = blockIdx.x * (IDX)blockDim.x + threadIdx.x; i < size_v; i += (IDX)gridDim.x * blockDim.x) {
         float v[VEC], r[VEC];
-        const int64_t e0 = i * VEC;
+        const IDX e0 = i * VEC;
         if (VEC == 4) {
             float4 t = ldg_stream(reinterpret_cast<const float4*>(x) + i);
             v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
@@ -41,11 +40,18 @@ bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, const 
             if (ref) r[0] = ref[e0];
         }
         float nz = 0.f;
-        if (noise) nz = nw * __ldg(noise + e0 / noise_div);
+        if (noise) nz = nw * __ldg(noise + e0 / (IDX)noise_div);
+        // channel of element e0 (+j): one division per vector when channels are innermost (step_b == 1)
+        const int cb = b ? (int)((step_b == 1 ? e0 : e0 / step_b) % (IDX)size_b) : 0;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float t = v[j];
-            if (b) t += __ldg(b + (int)(((e0 + j) / step_b) % size_b));
+            if (b) {
+                int ci = cb;
+                if (step_b == 1) { ci = cb + j; if (ci >= size_b) ci -= size_b; }
+                else if (j > 0) ci = (int)(((e0 + j) / step_b) % (IDX)size_b);
+                t += __ldg(b + ci);
+            }
             t += nz;
             float y;
             if (act == 3) {
@@ -126,13 +132,14 @@ bias_act_bwd_kernel(const float* __restrict__ go, const float* __restrict__ outp
 }
 
 // ------------------------------------------------------------------------------------ modulate
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 modulate_kernel(const float4* __restrict__ x, const float4* __restrict__ s, float4* __restrict__ out,
-                int64_t total_v, int64_t hw, int cv, int round_tf32) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_v;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv);
-        int64_t n = (i / cv) / hw;
+                IDX total_v, IDX hw, int cv, int round_tf32) {
+    for (IDX i = blockIdx.x * (IDX)blockDim.x + threadIdx.x; i < total_v; i += (IDX)gridDim.x * blockDim.x) {
+        const IDX pix = i / (IDX)cv;
+        const int c = (int)(i - pix * (IDX)cv);
+        const IDX n = pix / hw;
         float4 v = ldg_stream(x + i);
         float4 m = __ldg(s + n * cv + c);
         v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
@@ -352,13 +359,22 @@ extern "C" int sae_fused_bias_act(const float* x, const float* bias, const float
     cudaStream_t st = (cudaStream_t)stream;
     uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ref);
     bool vec = (size_x % 4 == 0) && (al % 16 == 0) && (!noise || noise_div % 4 == 0);
+    const bool small = size_x < ((int64_t)1 << 31) && step_b < ((int64_t)1 << 31);      // 32-bit index arithmetic
     if (vec) {
         int64_t nv = size_x / 4;
-        bias_act_kernel<4><<<grid_for(nv, 256), 256, 0, st>>>(x, bias, ref, out, nv, step_b, size_b, act, grad, alpha,
-                                                             scale, noise, noise_weight, noise_div, round_tf32);
+        if (small)
+            bias_act_kernel<4, uint32_t><<<grid_for(nv, 256, 16), 256, 0, st>>>(x, bias, ref, out, (uint32_t)nv, (uint32_t)step_b, size_b, act,
+                                                                               grad, alpha, scale, noise, noise_weight, noise_div, round_tf32);
+        else
+            bias_act_kernel<4, int64_t><<<grid_for(nv, 256, 16), 256, 0, st>>>(x, bias, ref, out, nv, step_b, size_b, act, grad, alpha,
+                                                                              scale, noise, noise_weight, noise_div, round_tf32);
     } else {
-        bias_act_kernel<1><<<grid_for(size_x, 256), 256, 0, st>>>(x, bias, ref, out, size_x, step_b, size_b, act, grad,
-                                                                 alpha, scale, noise, noise_weight, noise_div, round_tf32);
+        if (small)
+            bias_act_kernel<1, uint32_t><<<grid_for(size_x, 256, 16), 256, 0, st>>>(x, bias, ref, out, (uint32_t)size_x, (uint32_t)step_b, size_b,
+                                                                                   act, grad, alpha, scale, noise, noise_weight, noise_div, round_tf32);
+        else
+            bias_act_kernel<1, int64_t><<<grid_for(size_x, 256, 16), 256, 0, st>>>(x, bias, ref, out, size_x, step_b, size_b, act, grad,
+                                                                                  alpha, scale, noise, noise_weight, noise_div, round_tf32);
     }
     return check_launch("fused_bias_act");
 }
@@ -408,8 +424,12 @@ extern "C" int sae_modulate(const float* x, const float* s, float* out, int n, i
     uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(s);
     if (c % 4 == 0 && al % 16 == 0) {
         int64_t tv = (int64_t)n * hw * (c / 4);
-        modulate_kernel<<<grid_for(tv, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s),
-                                                          reinterpret_cast<float4*>(out), tv, hw, c / 4, round_tf32);
+        if (tv < ((int64_t)1 << 32))
+            modulate_kernel<uint32_t><<<grid_for(tv, 256, 16), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s),
+                                                                            reinterpret_cast<float4*>(out), (uint32_t)tv, (uint32_t)hw, c / 4, round_tf32);
+        else
+            modulate_kernel<int64_t><<<grid_for(tv, 256, 16), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s),
+                                                                           reinterpret_cast<float4*>(out), tv, hw, c / 4, round_tf32);
     } else {
         int64_t t = (int64_t)n * hw * c;
         modulate_scalar_kernel<<<grid_for(t, 256), 256, 0, st>>>(x, s, out, t, hw, c, round_tf32);

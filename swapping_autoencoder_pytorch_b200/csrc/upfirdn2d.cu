@@ -172,6 +172,79 @@ fir_strip_kernel(const float* __restrict__ x, const float* __restrict__ k, float
     }
 }
 
+// Separable variant of the strip kernel (every FIR of the networks is an outer product of 1-D taps): the horizontal
+// pass runs on the KW loads of the incoming row, the vertical pass on a rolling window of KH already-filtered rows —
+// KH float4 of state instead of KH*KW, i.e. ~45 registers instead of 122 and 4-5x the resident warps to hide HBM
+// latency.  Taps arrive by value (host arrays), already flipped.
+struct SepTaps { float y[8]; float x[8]; };
+
+template <int KH, int KW, int ROWS>
+__global__ void __launch_bounds__(256)
+fir_sep_strip_kernel(const float* __restrict__ x, float* __restrict__ out, FirParams p, SepTaps taps) {
+    const int cv = p.minor >> 2;
+    const int strips = (p.out_h + ROWS - 1) / ROWS;
+    const uint32_t total = (uint32_t)(p.major * strips * p.out_w * cv);      // host guarantees < 2^32
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const uint32_t c = idx % cv;
+        uint32_t t = idx / cv;
+        const int ox = (int)(t % p.out_w);
+        t /= p.out_w;
+        const int strip = (int)(t % strips);
+        const int64_t n = t / strips;
+        const int oy0 = strip * ROWS;
+        const int ix0 = ox - p.pad_x0;
+        const float* xn = x + n * (int64_t)p.in_h * p.in_w * p.minor + (int64_t)c * 4;
+        float4 win[KH];
+
+        auto hrow = [&](int iy) -> float4 {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy < 0 || iy >= p.in_h) return a;
+            const float* row = xn + (int64_t)iy * p.in_w * p.minor;
+#pragma unroll
+            for (int b = 0; b < KW; ++b) {
+                const int ix = ix0 + b;
+                if (ix >= 0 && ix < p.in_w) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(row + (int64_t)ix * p.minor));
+                    a.x = fmaf(v.x, taps.x[b], a.x); a.y = fmaf(v.y, taps.x[b], a.y);
+                    a.z = fmaf(v.z, taps.x[b], a.z); a.w = fmaf(v.w, taps.x[b], a.w);
+                }
+            }
+            return a;
+        };
+#pragma unroll
+        for (int a = 0; a < KH - 1; ++a) win[a] = hrow(oy0 - p.pad_y0 + a);
+#pragma unroll 4
+        for (int r = 0; r < ROWS; ++r) {
+            const int oy = oy0 + r;
+            if (oy >= p.out_h) break;
+            win[KH - 1] = hrow(oy - p.pad_y0 + KH - 1);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < KH; ++a) {
+                acc.x = fmaf(win[a].x, taps.y[a], acc.x); acc.y = fmaf(win[a].y, taps.y[a], acc.y);
+                acc.z = fmaf(win[a].z, taps.y[a], acc.z); acc.w = fmaf(win[a].w, taps.y[a], acc.w);
+            }
+            if (p.round_tf32) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
+            float* dst = out + ((n * p.out_h + oy) * (int64_t)p.out_w + ox) * p.minor + (int64_t)c * 4;
+            *reinterpret_cast<float4*>(dst) = acc;
+#pragma unroll
+            for (int a = 0; a < KH - 1; ++a) win[a] = win[a + 1];
+        }
+    }
+}
+
+template <int KH, int KW>
+static void launch_sep(const float* x, float* out, const FirParams& p, const SepTaps& taps, cudaStream_t st) {
+    constexpr int ROWS = 16;
+    const int strips = (p.out_h + ROWS - 1) / ROWS;
+    int64_t total = p.major * (int64_t)strips * p.out_w * (p.minor / 4);
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    fir_sep_strip_kernel<KH, KW, ROWS><<<(unsigned)blocks, 256, 0, st>>>(x, out, p, taps);
+}
+
 template <int KH, int KW>
 static void launch_strip(const float* x, const float* k, float* out, const FirParams& p, cudaStream_t st) {
     constexpr int ROWS = 8;
@@ -227,4 +300,38 @@ extern "C" int sae_upfirdn2d(const float* input, const float* kernel, float* out
         else     fir_generic_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(input, kernel, out, p);
     }
     return check_launch("upfirdn2d");
+}
+
+
+// Separable fast path: kernel2d[a][b] == taps_y[a] * taps_x[b] (host arrays, NOT flipped — flipping happens here).
+// Restricted to up = down = 1, taps <= 4, minor % 4 == 0, < 2^32 work items; callers fall back to sae_upfirdn2d otherwise.
+extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, const float* taps_x, float* out,
+                                       int64_t major, int in_h, int in_w, int minor, int kernel_h, int kernel_w,
+                                       int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_tf32, void* stream) {
+    using namespace sae;
+    if (major == 0) return SAE_OK;
+    if (!input || !taps_y || !taps_x || !out) return fail(SAE_E_INVALID, "upfirdn2d_separable: null pointer");
+    if (kernel_h < 1 || kernel_h > 4 || kernel_w != kernel_h) return fail(SAE_E_UNSUPPORTED, "upfirdn2d_separable: taps must be 1..4, square");
+    if (minor % 4 != 0 || ((reinterpret_cast<uintptr_t>(input) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
+        return fail(SAE_E_UNSUPPORTED, "upfirdn2d_separable: needs minor %% 4 == 0 and 16-byte aligned pointers");
+    FirParams p;
+    p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
+    p.up_x = p.up_y = p.down_x = p.down_y = 1; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.round_tf32 = round_tf32;
+    p.out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
+    p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
+    if (p.out_h <= 0 || p.out_w <= 0) return fail(SAE_E_INVALID, "upfirdn2d_separable: kernel larger than padded input");
+    if (major * (int64_t)((p.out_h + 15) / 16) * p.out_w * (minor / 4) >= (int64_t)1 << 32)
+        return fail(SAE_E_UNSUPPORTED, "upfirdn2d_separable: too many work items for 32-bit indexing");
+    SepTaps t;
+    for (int i = 0; i < 8; ++i) { t.y[i] = 0.f; t.x[i] = 0.f; }
+    for (int i = 0; i < kernel_h; ++i) t.y[i] = taps_y[kernel_h - 1 - i];
+    for (int i = 0; i < kernel_w; ++i) t.x[i] = taps_x[kernel_w - 1 - i];
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kernel_h) {
+        case 1: launch_sep<1, 1>(input, out, p, t, st); break;
+        case 2: launch_sep<2, 2>(input, out, p, t, st); break;
+        case 3: launch_sep<3, 3>(input, out, p, t, st); break;
+        default: launch_sep<4, 4>(input, out, p, t, st); break;
+    }
+    return check_launch("upfirdn2d_separable");
 }
