@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 6
+#define SAE_ABI_VERSION 7
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -120,6 +120,13 @@ int sae_upsample2x_add_scale(const float* skip, const float* res, float* out, in
                              int round_tf32, void* stream);
 int sae_upsample2x_backward(const float* dy, float* dskip, int n, int h, int w, int c, float scale, int round_tf32,
                             void* stream);
+
+/* nn.ReflectionPad2d((pad_l, pad_r, pad_t, pad_b)) on NHWC data and its adjoint (the encoder's ReflectionPad2d,
+ * stylegan2_layers.py:104,642); c % 4 == 0. */
+int sae_reflect_pad(const float* x, float* out, int n, int h, int w, int c, int pad_l, int pad_r, int pad_t, int pad_b,
+                    void* stream);
+int sae_reflect_pad_backward(const float* dy, float* dx, int n, int h, int w, int c, int pad_l, int pad_r, int pad_t,
+                             int pad_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * conv2d — dense implicit-GEMM convolution family on NHWC fp32 activations, TF32 tensor cores,

@@ -9,7 +9,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import swapping_autoencoder_pytorch_b200 as S  # noqa: E402
-from swapping_autoencoder_pytorch_b200.stylegan2_op import conv, fused_act, upfirdn2d  # noqa: E402
+import importlib  # noqa: E402
+conv = importlib.import_module("swapping_autoencoder_pytorch_b200.stylegan2_op.conv")
+fused_act = importlib.import_module("swapping_autoencoder_pytorch_b200.stylegan2_op.fused_act")
+upfirdn2d = importlib.import_module("swapping_autoencoder_pytorch_b200.stylegan2_op.upfirdn2d")
 
 log = collections.Counter()
 

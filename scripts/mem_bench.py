@@ -36,8 +36,9 @@ def main():
     print("%-46s %9s %9s" % ("kernel / shape", "ms", "GB/s"))
     for n, h, c in ((32, 256, 128), (32, 128, 256), (32, 64, 512), (256, 128, 32), (32, 256, 32)):
         x = torch.randn(n, h, h, c, device=dev)
-        for name, kern, pad in (("fir4 pad(2,2)", k4, (2, 2)), ("fir4 pad(1,1)", k4, (1, 1)), ("fir3 pad(0,0)", k3, (0, 0))):
-            ms = timeit(lambda: k.upfirdn2d(x, kern, 1, 1, 1, 1, pad[0], pad[1], pad[0], pad[1]), flush)
+        t4, t3 = (0.125, 0.375, 0.375, 0.125), (0.25, 0.5, 0.25)
+        for name, kern, pad, tp in (("fir4 pad(2,2)", k4, (2, 2), t4), ("fir4 pad(1,1)", k4, (1, 1), t4), ("fir3 pad(0,0)", k3, (0, 0), t3)):
+            ms = timeit(lambda: k.upfirdn2d(x, kern, 1, 1, 1, 1, pad[0], pad[1], pad[0], pad[1], taps=(tp, tp)), flush)
             oh = h + pad[0] + pad[1] - kern.shape[0] + 1
             gb = 4.0 * (x.numel() + n * oh * oh * c) / 1e9
             print("%-46s %9.3f %9.0f" % ("%s [%d,%d,%d,%d]" % (name, n, h, h, c), ms, gb / ms * 1e3))

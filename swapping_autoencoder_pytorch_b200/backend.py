@@ -57,31 +57,11 @@ class CudaKernels:
         # as fp32): the tensor cores ignore the low 13 mantissa bits of their operands, so rounding in the producer
         # makes that truncation exact and unbiased.  Set False for bit-exact fp32 results from the pointwise kernels.
         self.round_tf32 = True
-        self._sep_cache = {}
 
     # ------------------------------------------------------------------ FIR
-    def _separable_taps(self, kernel):
-        """1-D factors (ctypes float arrays) of a rank-1 FIR kernel, or None.  Decided once per kernel buffer (one
-        device->host read at first use, then cached on (pointer, version, shape))."""
-        key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
-        hit = self._sep_cache.get(key, False)
-        if hit is not False:
-            return hit
-        k = kernel.detach().double().cpu()
-        res = None
-        kh, kw = k.shape
-        if kh == kw and kh <= 4 and float(k.abs().max()) > 0:
-            flat = int(k.abs().argmax())
-            i0, j0 = flat // kw, flat % kw
-            col, row = k[:, j0].clone(), k[i0, :] / k[i0, j0]
-            if float((torch.outer(col, row) - k).abs().max()) <= 1e-7 * float(k.abs().max()):
-                res = ((ctypes.c_float * kh)(*[float(v) for v in col]), (ctypes.c_float * kw)(*[float(v) for v in row]))
-        if len(self._sep_cache) > 256:
-            self._sep_cache.clear()
-        self._sep_cache[key] = res
-        return res
-
-    def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+    def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, taps=None):
+        """taps: optional host-side 1-D factors (taps_y, taps_x) with kernel == outer(taps_y, taps_x); supplied by
+        the Blur modules, which build their kernels from 1-D tap lists — selects the separable fast path."""
         _need_cuda(x, kernel)
         n, h, w, c = x.shape
         kh, kw = kernel.shape
@@ -90,10 +70,11 @@ class CudaKernels:
         out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
         if up_x == up_y == down_x == down_y == 1 and c % 4 == 0 and n * ((oh + 15) // 16) * ow * (c // 4) < 2 ** 32 \
                 and x.data_ptr() % 16 == 0 and n > 0:
-            taps = self._separable_taps(kernel)
-            if taps is not None:
+            if taps is not None and len(taps[0]) == kh and len(taps[1]) == kw and kh == kw and kh <= 4:
+                ty = (ctypes.c_float * kh)(*taps[0])
+                tx = (ctypes.c_float * kw)(*taps[1])
                 with torch.cuda.device(x.device):
-                    check(self.lib.sae_upfirdn2d_separable(_ptr(x), taps[0], taps[1], _ptr(out), n, h, w, c, kh, kw, pad_x0,
+                    check(self.lib.sae_upfirdn2d_separable(_ptr(x), ty, tx, _ptr(out), n, h, w, c, kh, kw, pad_x0,
                                                            pad_x1, pad_y0, pad_y1, int(self.round_tf32), _stream()),
                           "sae_upfirdn2d_separable")
                 return out
@@ -178,6 +159,26 @@ class CudaKernels:
             check(self.lib.sae_upsample2x_backward(_ptr(dy), _ptr(out), n, oh // 2, ow // 2, c, scale,
                                                    int(self.round_tf32), _stream()), "sae_upsample2x_backward")
         return out
+
+    def reflect_pad(self, x, pads):
+        """x [N,H,W,C] -> [N, H+pt+pb, W+pl+pr, C]; pads = (left, right, top, bottom)"""
+        _need_cuda(x)
+        n, h, w, c = x.shape
+        pl, pr, pt, pb = pads
+        out = torch.empty((n, h + pt + pb, w + pl + pr, c), device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_reflect_pad(_ptr(x), _ptr(out), n, h, w, c, pl, pr, pt, pb, _stream()), "sae_reflect_pad")
+        return out
+
+    def reflect_pad_backward(self, dy, pads):
+        _need_cuda(dy)
+        n, oh, ow, c = dy.shape
+        pl, pr, pt, pb = pads
+        dx = torch.empty((n, oh - pt - pb, ow - pl - pr, c), device=dy.device, dtype=dy.dtype)
+        with torch.cuda.device(dy.device):
+            check(self.lib.sae_reflect_pad_backward(_ptr(dy), _ptr(dx), n, oh - pt - pb, ow - pl - pr, c, pl, pr, pt, pb,
+                                                    _stream()), "sae_reflect_pad_backward")
+        return dx
 
     def _filter(self, w):
         """contiguous copy of a (small) filter tensor, rounded to TF32 when the policy says so"""

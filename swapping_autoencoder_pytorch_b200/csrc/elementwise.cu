@@ -326,6 +326,55 @@ upsample2x_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dskip,
     }
 }
 
+// ------------------------------------------------------------------------------------ reflection padding (NHWC)
+// nn.ReflectionPad2d of the encoder (stylegan2_layers.py:104,642) in one pass over channels-last data; the backward
+// gathers, for every input pixel, the (at most 3 x 3) padded positions that mirror onto it — no atomics.
+__device__ __forceinline__ int reflect_idx(int i, int len) {
+    if (i < 0) i = -i;
+    if (i >= len) i = 2 * (len - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256)
+reflect_pad_kernel(const float4* __restrict__ x, float4* __restrict__ out, uint32_t total_v, int h, int w, int cv, int oh, int ow,
+                   int pl, int pt) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += gridDim.x * blockDim.x) {
+        const uint32_t c = i % cv;
+        uint32_t t = i / cv;
+        const int ox = (int)(t % ow); t /= ow;
+        const int oy = (int)(t % oh);
+        const uint32_t n = t / oh;
+        const int iy = reflect_idx(oy - pt, h), ix = reflect_idx(ox - pl, w);
+        out[i] = ldg_stream(x + (((int64_t)n * h + iy) * w + ix) * cv + c);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reflect_pad_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, uint32_t total_v, int h, int w, int cv, int oh, int ow,
+                       int pl, int pr, int pt, int pb) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += gridDim.x * blockDim.x) {
+        const uint32_t c = i % cv;
+        uint32_t t = i / cv;
+        const int ix = (int)(t % w); t /= w;
+        const int iy = (int)(t % h);
+        const uint32_t n = t / h;
+        int ys[3], xs[3], ny = 0, nx = 0;
+        ys[ny++] = iy + pt;
+        if (iy >= 1 && iy <= pt) ys[ny++] = pt - iy;
+        if (iy <= h - 2 && iy >= h - 1 - pb) ys[ny++] = pt + 2 * (h - 1) - iy;
+        xs[nx++] = ix + pl;
+        if (ix >= 1 && ix <= pl) xs[nx++] = pl - ix;
+        if (ix <= w - 2 && ix >= w - 1 - pr) xs[nx++] = pl + 2 * (w - 1) - ix;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < ny; ++a)
+            for (int b = 0; b < nx; ++b) {
+                const float4 g = __ldg(dy + (((int64_t)n * oh + ys[a]) * ow + xs[b]) * cv + c);
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            }
+        dx[i] = acc;
+    }
+}
+
 // --------------------------------------------------------------------------- bucket pack/unpack
 __global__ void __launch_bounds__(256)
 bucket_copy_kernel(float* const* __restrict__ ptrs, const int64_t* __restrict__ offsets,
@@ -492,6 +541,34 @@ extern "C" int sae_upsample2x_backward(const float* dy, float* dskip, int n, int
     upsample2x_bwd_kernel<<<grid_for(tv, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dskip), tv, h, w, c / 4, scale, round_tf32);
     return check_launch("upsample2x_backward");
+}
+
+extern "C" int sae_reflect_pad(const float* x, float* out, int n, int h, int w, int c, int pad_l, int pad_r, int pad_t, int pad_b,
+                               void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!x || !out || n < 0 || h <= 0 || w <= 0 || c <= 0 || c % 4 != 0) return fail(SAE_E_INVALID, "reflect_pad: bad arguments (c %% 4 == 0)");
+    if (pad_l < 0 || pad_r < 0 || pad_t < 0 || pad_b < 0 || pad_l >= w || pad_r >= w || pad_t >= h || pad_b >= h)
+        return fail(SAE_E_INVALID, "reflect_pad: padding must be non-negative and smaller than the input");
+    const int oh = h + pad_t + pad_b, ow = w + pad_l + pad_r;
+    int64_t tv = (int64_t)n * oh * ow * (c / 4);
+    if (tv >= ((int64_t)1 << 32)) return fail(SAE_E_UNSUPPORTED, "reflect_pad: tensor too large for 32-bit indexing");
+    reflect_pad_kernel<<<grid_for(tv, 256, 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out),
+                                                                               (uint32_t)tv, h, w, c / 4, oh, ow, pad_l, pad_t);
+    return check_launch("reflect_pad");
+}
+
+extern "C" int sae_reflect_pad_backward(const float* dy, float* dx, int n, int h, int w, int c, int pad_l, int pad_r, int pad_t,
+                                        int pad_b, void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!dy || !dx || n < 0 || h <= 0 || w <= 0 || c <= 0 || c % 4 != 0) return fail(SAE_E_INVALID, "reflect_pad_backward: bad arguments");
+    if (pad_l < 0 || pad_r < 0 || pad_t < 0 || pad_b < 0 || pad_l >= w || pad_r >= w || pad_t >= h || pad_b >= h)
+        return fail(SAE_E_INVALID, "reflect_pad_backward: padding must be non-negative and smaller than the input");
+    const int oh = h + pad_t + pad_b, ow = w + pad_l + pad_r;
+    int64_t tv = (int64_t)n * h * w * (c / 4);
+    if ((int64_t)n * oh * ow * (c / 4) >= ((int64_t)1 << 32)) return fail(SAE_E_UNSUPPORTED, "reflect_pad_backward: tensor too large");
+    reflect_pad_bwd_kernel<<<grid_for(tv, 256, 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx),
+                                                                                   (uint32_t)tv, h, w, c / 4, oh, ow, pad_l, pad_r, pad_t, pad_b);
+    return check_launch("reflect_pad_backward");
 }
 
 extern "C" int sae_round_tf32(const float* x, float* out, int64_t n, void* stream) {

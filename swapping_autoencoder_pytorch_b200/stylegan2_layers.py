@@ -20,7 +20,8 @@ from torch import nn
 from torch.nn import functional as F
 
 from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv2d_bias_act, conv2d_noise_bias_act, conv2d_residual,
-                           conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, modulate, upfirdn2d)
+                           conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, modulate, reflect_pad,
+                           upfirdn2d)
 
 _SQRT2 = math.sqrt(2.0)
 
@@ -40,6 +41,18 @@ def make_kernel(k):
     return k / k.sum()
 
 
+def _taps_1d(k, gain=1.0):
+    """host-side 1-D factors of make_kernel(k) * gain when k is a 1-D tap list: outer(t, t) == make_kernel(k) * gain"""
+    try:
+        vals = [float(v) for v in k]
+    except TypeError:
+        return None
+    tot = sum(vals)
+    g = math.sqrt(gain)
+    t = tuple(v / tot * g for v in vals)
+    return (t, t)
+
+
 def _split_pad(p, extra0=0, extra1=0):
     return (p + 1) // 2 + extra0, p // 2 + extra1
 
@@ -51,10 +64,11 @@ class Upsample(nn.Module):
         super().__init__()
         self.factor = factor
         self.register_buffer('kernel', make_kernel(kernel) * (factor ** 2))
+        self.taps = _taps_1d(kernel, factor ** 2)
         self.pad = _split_pad(self.kernel.shape[0] - factor, extra0=factor - 1)
 
     def forward(self, input):
-        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad)
+        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad, taps=self.taps)
 
 
 class Downsample(nn.Module):
@@ -64,6 +78,7 @@ class Downsample(nn.Module):
         super().__init__()
         self.factor = factor
         self.register_buffer('kernel', make_kernel(kernel))
+        self.taps = _taps_1d(kernel)
         self.reflection = reflection_pad
         self.pad = _split_pad(self.kernel.shape[0] - factor if pad is None else pad)
 
@@ -72,7 +87,7 @@ class Downsample(nn.Module):
         if self.reflection:
             input = F.pad(input, (pad[0], pad[1], pad[0], pad[1]), mode='reflect')
             pad = (0, 0)
-        return upfirdn2d(input, self.kernel, up=1, down=self.factor, pad=pad)
+        return upfirdn2d(input, self.kernel, up=1, down=self.factor, pad=pad, taps=self.taps)
 
 
 class Blur(nn.Module):
@@ -80,6 +95,7 @@ class Blur(nn.Module):
 
     def __init__(self, kernel, pad, upsample_factor=1, reflection_pad=False):
         super().__init__()
+        self.taps = _taps_1d(kernel, upsample_factor ** 2 if upsample_factor > 1 else 1.0)
         kernel = make_kernel(kernel)
         if upsample_factor > 1:
             kernel = kernel * (upsample_factor ** 2)
@@ -92,8 +108,8 @@ class Blur(nn.Module):
 
     def forward(self, input):
         if self.reflection:
-            input = self.reflection_pad(input)
-        return upfirdn2d(input, self.kernel, pad=self.pad)
+            input = reflect_pad(input, self.reflection_pad.padding)
+        return upfirdn2d(input, self.kernel, pad=self.pad, taps=self.taps)
 
 
 class EqualConv2d(nn.Module):
@@ -423,9 +439,10 @@ class ConvLayer(nn.Sequential):
 
     def forward(self, x):
         mods = self._modules
-        for name in ("Blur", "RefPad"):
-            if name in mods:
-                x = mods[name](x)
+        if "Blur" in mods:
+            x = mods["Blur"](x)
+        if "RefPad" in mods:
+            x = reflect_pad(x, mods["RefPad"].padding)
         conv, act = mods["Conv"], mods.get("Act")
         if isinstance(act, FusedLeakyReLU) and conv.bias is None:
             # bias + leaky-ReLU applied in the conv kernel's epilogue

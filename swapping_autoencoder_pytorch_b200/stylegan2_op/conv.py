@@ -285,6 +285,39 @@ def add_scale(a, b, scale):
     return _AddScale.apply(a, b, scale)
 
 
+class _ReflectPad(Function):
+    """nn.ReflectionPad2d on channels-last data in one pass.  Linear: its backward is the adjoint kernel, whose backward
+    is the padding again — closed under differentiation like the FIR pair."""
+
+    @staticmethod
+    def forward(ctx, x, pads):
+        ctx.pads = pads
+        return _nchw(backend.kernels().reflect_pad(_nhwc(x), pads))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _ReflectPadAdjoint.apply(dy, ctx.pads), None
+
+
+class _ReflectPadAdjoint(Function):
+    @staticmethod
+    def forward(ctx, dy, pads):
+        ctx.pads = pads
+        return _nchw(backend.kernels().reflect_pad_backward(_nhwc(dy), pads))
+
+    @staticmethod
+    def backward(ctx, ddx):
+        return _ReflectPad.apply(ddx, ctx.pads), None
+
+
+def reflect_pad(x, pads):
+    """pads = (left, right, top, bottom), the nn.ReflectionPad2d convention"""
+    pads = tuple(int(p) for p in pads)
+    if x.shape[1] % 4 != 0:
+        return F.pad(x, pads, mode="reflect")
+    return _ReflectPad.apply(x, pads)
+
+
 class _Upsample2xAddScale(Function):
     """(bilinear_x2(skip) + res) * scale in one kernel — the generator's upsampling-block merge
     (generator.py:51-53).  Generator only: once-differentiable."""

@@ -37,7 +37,9 @@ class EmulatedKernels:
     conv_impl = 0
     round_tf32 = False
 
-    def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+    def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, taps=None):
+        if taps is not None:      # the module-supplied factors must reproduce the 2-D kernel
+            assert torch.allclose(torch.outer(torch.tensor(taps[0]), torch.tensor(taps[1])).to(kernel.dtype), kernel, atol=1e-6)
         y = O.fir_numpy(_nchw(x).numpy(), kernel.numpy(), (up_x, up_y), (down_x, down_y), (pad_x0, pad_x1, pad_y0, pad_y1))
         return _nhwc(torch.from_numpy(np.ascontiguousarray(y)))
 
@@ -87,6 +89,18 @@ class EmulatedKernels:
             up = F.interpolate(x0, scale_factor=2, mode="bilinear", align_corners=False)
         g, = torch.autograd.grad(up, x0, _nchw(dy).detach())
         return _nhwc(g) * scale
+
+    def reflect_pad(self, x, pads):
+        return _nhwc(F.pad(_nchw(x), tuple(pads), mode="reflect"))
+
+    def reflect_pad_backward(self, dy, pads):
+        n, oh, ow, c = dy.shape
+        pl, pr, pt, pb = pads
+        x0 = torch.zeros(n, c, oh - pt - pb, ow - pl - pr, dtype=dy.dtype, requires_grad=True)
+        with torch.enable_grad():
+            y = F.pad(x0, tuple(pads), mode="reflect")
+        g, = torch.autograd.grad(y, x0, _nchw(dy).detach())
+        return _nhwc(g)
 
     def _epilogue(self, y, bias=None, act=1, alpha=0.2, gain=1.0, noise=None, noise_weight=None, residual=None,
                   res_scale=1.0, round_tf32=None):

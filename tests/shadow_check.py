@@ -44,6 +44,8 @@ class ShadowKernels:
     def _both(self, name, desc, args, kwargs):
         out = getattr(self.real, name)(*args, **kwargs)
         kw = {k: _cpu(v) for k, v in kwargs.items() if k != "round_tf32"}
+        if "taps" in kw:
+            kw["taps"] = kwargs["taps"]
         ref = getattr(self.emu, name)(*[_cpu(a) for a in args], **kw)
         outs = out if isinstance(out, tuple) else (out,)
         refs = ref if isinstance(ref, tuple) else (ref,)
@@ -53,8 +55,9 @@ class ShadowKernels:
             self.log.append((name, "%s out%d" % (desc, i), _err(o, r)))
         return out
 
-    def upfirdn2d(self, x, kernel, *cfg):
-        return self._both("upfirdn2d", "x%s k%s cfg%s" % (tuple(x.shape), tuple(kernel.shape), cfg), (x, kernel) + cfg, {})
+    def upfirdn2d(self, x, kernel, *cfg, taps=None):
+        return self._both("upfirdn2d", "x%s k%s cfg%s sep%s" % (tuple(x.shape), tuple(kernel.shape), cfg, taps is not None),
+                          (x, kernel) + cfg, dict(taps=taps))
 
     def bias_act(self, x, bias, ref, act, grad, alpha, scale, noise=None, noise_weight=None):
         return self._both("bias_act", "x%s act%d grad%d noise%s" % (tuple(x.shape), act, grad, noise is not None),
@@ -78,6 +81,12 @@ class ShadowKernels:
 
     def upsample2x_backward(self, dy, scale):
         return self._both("upsample2x_backward", "x%s" % (tuple(dy.shape),), (dy, scale), {})
+
+    def reflect_pad(self, x, pads):
+        return self._both("reflect_pad", "x%s pads%s" % (tuple(x.shape), pads), (x, pads), {})
+
+    def reflect_pad_backward(self, dy, pads):
+        return self._both("reflect_pad_backward", "x%s pads%s" % (tuple(dy.shape), pads), (dy, pads), {})
 
     def _impl_name(self, g, d, impl):
         return impl if impl is not None else self.real.conv_impl_for(g, d)

@@ -71,9 +71,18 @@ def test_fir_hot_path_shapes(taps, pad, c, h, exact_fp32):
     k = O.make_kernel(taps, torch.float64)
     x = rnd(5, 3, c, h, h + 1)
     y_ref = O.upfirdn2d(x, k, pad=pad)
-    y = upfirdn2d(cuda(x), cuda(k), pad=pad)
+    y = upfirdn2d(cuda(x), cuda(k), pad=pad)                  # generic / 2-D strip kernels
     assert y.shape == y_ref.shape
     assert rel_err(y, y_ref) < TOL_FP32
+    t1 = tuple(v / sum(taps) for v in taps)
+    xg = cuda(x).requires_grad_()
+    ys = upfirdn2d(xg, cuda(k), pad=pad, taps=(t1, t1))       # separable strip kernel (what the Blur modules use)
+    assert rel_err(ys, y_ref) < TOL_FP32
+    w = rnd(6, *y_ref.shape)
+    xr = x.clone().requires_grad_()
+    g_ref, = torch.autograd.grad((O.upfirdn2d(xr, k, pad=pad) * w).sum(), xr)
+    g, = torch.autograd.grad((ys * cuda(w)).sum(), xg)
+    assert rel_err(g, g_ref) < TOL_FP32
 
 
 def test_fir_edge_cases(exact_fp32):
@@ -156,6 +165,21 @@ def test_upsample2x_add_scale(exact_fp32):
         assert rel_err(out, ref) < TOL_FP32
         gs, gr = torch.autograd.grad((out * cuda(w)).sum(), [sg, rg])
         assert rel_err(gs, gs_r) < TOL_FP32 and rel_err(gr, gr_r) < TOL_FP32
+
+
+def test_reflect_pad(exact_fp32):
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import reflect_pad
+    for shape, pads in (((2, 8, 9, 7), (1, 1, 1, 1)), ((3, 32, 16, 16), (2, 1, 2, 1)), ((1, 4, 5, 6), (0, 3, 2, 0))):
+        x = rnd(1, *shape)
+        xr = x.clone().requires_grad_()
+        ref = F.pad(xr, pads, mode="reflect")
+        w = rnd(2, *ref.shape)
+        g_ref, = torch.autograd.grad((ref * w).sum(), xr)
+        xg = cuda(x).requires_grad_()
+        out = reflect_pad(xg, pads)
+        assert torch.equal(out.cpu().double(), ref.detach().float().double())
+        g, = torch.autograd.grad((out * cuda(w)).sum(), xg)
+        assert rel_err(g, g_ref) < TOL_FP32
 
 
 def test_tf32_rounding_policy():
