@@ -304,17 +304,21 @@ upsample2x_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dskip,
         const int y = (int)(t % h);
         const int64_t n = t / h;
         const float4* gb = dy + n * (int64_t)oh * ow * cv + c;
+        // low-res pixel y is touched by high-res rows 2y-1, 2y, 2y+1, 2y+2 with weights 1/4, 3/4, 3/4, 1/4; the clamped
+        // border rows (0 and 2h-1) put their whole weight on the first / last low-res row
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int yy = max(2 * y - 2, 0); yy <= min(2 * y + 2, oh - 1); ++yy) {
-            int y0, y1; float ly0, ly1;
-            bilin_src(yy, h, y0, y1, ly0, ly1);
-            const float wy = (y0 == y ? ly0 : 0.f) + (y1 == y ? ly1 : 0.f);
-            if (wy == 0.f) continue;
-            for (int xx = max(2 * x - 2, 0); xx <= min(2 * x + 2, ow - 1); ++xx) {
-                int x0, x1; float lx0, lx1;
-                bilin_src(xx, w, x0, x1, lx0, lx1);
-                const float wx = (x0 == x ? lx0 : 0.f) + (x1 == x ? lx1 : 0.f);
-                if (wx == 0.f) continue;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = 2 * y - 1 + a;
+            if (yy < 0 || yy >= oh) continue;
+            float wy = (a == 0 || a == 3) ? 0.25f : 0.75f;
+            if (yy == 0 || yy == oh - 1) wy = 1.0f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int xx = 2 * x - 1 + b;
+                if (xx < 0 || xx >= ow) continue;
+                float wx = (b == 0 || b == 3) ? 0.25f : 0.75f;
+                if (xx == 0 || xx == ow - 1) wx = 1.0f;
                 const float4 g = __ldg(gb + ((int64_t)yy * ow + xx) * cv);
                 const float ww = wy * wx;
                 acc.x = fmaf(ww, g.x, acc.x); acc.y = fmaf(ww, g.y, acc.y); acc.z = fmaf(ww, g.z, acc.z); acc.w = fmaf(ww, g.w, acc.w);

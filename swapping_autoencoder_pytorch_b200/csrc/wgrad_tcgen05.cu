@@ -37,7 +37,12 @@ struct WgParams {
     int n_tiles_c;                   // number of 128-wide tiles along C
     int cpt;                         // 32-channel sub-tiles per tap inside an accumulator: min(C,128)/32
                                      // (narrow layers pack 4/cpt taps side by side into the 128 N-columns)
+    int shared_b;                    // 1: the 3 horizontal taps of a filter row read ONE 40-pixel x window per sub-tile
+                                     //    (descriptor start shifted by s pixel rows) instead of 3 separate 32-pixel boxes
 };
+
+constexpr int WG_WIN = 40;                         // pixels per shared window (32 + 2 halo, rounded up to a multiple of 8)
+constexpr int WG_WSUB = WG_WIN * 128;              // 5 KB per 32-channel sub-tile
 
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
     // MN-major 32-bit operands have exactly one legal shared-memory layout on tcgen05: the 128-byte swizzle with
@@ -48,6 +53,19 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
     d |= (uint64_t)(WG_SUB >> 4) << 16;
     d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+
+__device__ __forceinline__ uint64_t make_desc_mn_win(uint32_t saddr) {
+    // same layout, sub-tiles WG_WSUB apart, start address on an arbitrary 128-byte pixel row: the swizzle is a function
+    // of the absolute shared-memory address, the descriptor's base-offset field carries the row phase of the start
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(WG_WSUB >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)((saddr >> 7) & 7) << 49;
     d |= (uint64_t)1 << 61;
     return d;
 }
@@ -79,7 +97,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const int chunk_begin = blockIdx.z * p.chunks_per_split;
     const int chunk_end = min(chunk_begin + p.chunks_per_split, p.chunks_total);
     const int KB = chunk_end - chunk_begin;
-    const uint32_t stage_tx = (uint32_t)WG_OPER + (uint32_t)nslots * WG_SUB;
+    const uint32_t stage_tx = p.shared_b ? (uint32_t)(WG_OPER + 4 * WG_WSUB) : (uint32_t)WG_OPER + (uint32_t)nslots * WG_SUB;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
@@ -116,6 +134,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         tma_load_4d(sa + i * WG_SUB, &map_dy, bar_full + 8 * s, o0 + 32 * i, q0, p0, n0);
+                    if (p.shared_b) {
+                        // one window of WG_WIN pixels starting at the s = 0 tap position, per 32-channel sub-tile
+                        const int r = tap0 / p.S;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_4d(sa + WG_OPER + (uint32_t)i * WG_WSUB, &map_x, bar_full + 8 * s, c0 + 32 * i,
+                                        q0 - p.pad_l, p0 - p.pad_t + r, n0);
+                    } else
                     for (int q = 0; q < nslots; ++q) {
                         // slot q = (accumulator q/4, 32-column group q%4) holds tap q/cpt, channels 32*(q%cpt)
                         const int tap = tap0 + q / p.cpt;
@@ -135,6 +161,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                     const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
                     const uint64_t da = make_desc_mn_sw128(sa);
                     for (int g = 0; g < nacc; ++g) {
+                        if (p.shared_b) {
+#pragma unroll
+                            for (int k = 0; k < WG_KPIX / 8; ++k) {
+                                // tap s = g reads window rows [g + 8k, g + 8k + 8)
+                                const uint64_t db = make_desc_mn_win(sa + WG_OPER + (uint32_t)(g + 8 * k) * 128u);
+                                umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                            }
+                            continue;
+                        }
                         const uint64_t db = make_desc_mn_sw128(sa + (uint32_t)(1 + g) * WG_OPER);
 #pragma unroll
                         for (int k = 0; k < WG_KPIX / 8; ++k) {
@@ -221,6 +256,10 @@ int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
     p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
     splits = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
 
+    static int win_mode = -1;
+    if (win_mode < 0) { const char* v = getenv("SAE_WGRAD_WINDOW"); win_mode = (v && v[0] == '1') ? 1 : 0; }
+    p.shared_b = (win_mode == 1 && p.tw == 32 && g->stride == 1 && g->S == 3 && p.cpt == 4 && p.group_taps == 3) ? 1 : 0;
+
     CUtensorMap mdy, mx;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g->K, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N};
@@ -234,6 +273,7 @@ int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
         cuuint64_t dims[4] = {(cuuint64_t)g->C, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N};
         cuuint64_t strides[3] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)(p.tw * g->stride), (cuuint32_t)(p.th * g->stride), (cuuint32_t)p.tn};
+        if (p.shared_b) box[1] = WG_WIN;
         cuuint32_t es[4] = {1, (cuuint32_t)g->stride, (cuuint32_t)g->stride, 1};
         int rc = encode_map(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
