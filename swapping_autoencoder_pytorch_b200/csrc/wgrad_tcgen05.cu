@@ -57,7 +57,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ uint64_t make_desc_mn_win(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_desc_mn_win(uint32_t saddr, int use_base_offset) {
     // same layout, sub-tiles WG_WSUB apart, start address on an arbitrary 128-byte pixel row: the swizzle is a function
     // of the absolute shared-memory address, the descriptor's base-offset field carries the row phase of the start
     uint64_t d = 0;
@@ -65,7 +65,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_win(uint32_t saddr) {
     d |= (uint64_t)(WG_WSUB >> 4) << 16;
     d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)((saddr >> 7) & 7) << 49;
+    if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7) << 49;
     d |= (uint64_t)1 << 61;
     return d;
 }
@@ -165,7 +165,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 #pragma unroll
                             for (int k = 0; k < WG_KPIX / 8; ++k) {
                                 // tap s = g reads window rows [g + 8k, g + 8k + 8)
-                                const uint64_t db = make_desc_mn_win(sa + WG_OPER + (uint32_t)(g + 8 * k) * 128u);
+                                const uint64_t db = make_desc_mn_win(sa + WG_OPER + (uint32_t)(g + 8 * k) * 128u, p.shared_b == 1);
                                 umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
                             }
                             continue;
@@ -257,8 +257,8 @@ int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
     splits = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
 
     static int win_mode = -1;
-    if (win_mode < 0) { const char* v = getenv("SAE_WGRAD_WINDOW"); win_mode = (v && v[0] == '1') ? 1 : 0; }
-    p.shared_b = (win_mode == 1 && p.tw == 32 && g->stride == 1 && g->S == 3 && p.cpt == 4 && p.group_taps == 3) ? 1 : 0;
+    if (win_mode < 0) { const char* v = getenv("SAE_WGRAD_WINDOW"); win_mode = v ? atoi(v) : 0; }   // 1: base-offset field, 2: plain address
+    p.shared_b = (win_mode >= 1 && p.tw == 32 && g->stride == 1 && g->S == 3 && p.cpt == 4 && p.group_taps == 3) ? win_mode : 0;
 
     CUtensorMap mdy, mx;
     {
