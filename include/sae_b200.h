@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 7
+#define SAE_ABI_VERSION 8
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -120,6 +120,14 @@ int sae_upsample2x_add_scale(const float* skip, const float* res, float* out, in
                              int round_tf32, void* stream);
 int sae_upsample2x_backward(const float* dy, float* dskip, int n, int h, int w, int c, float scale, int round_tf32,
                             void* stream);
+
+/* Filter preparation: parameter layout [K,C,R,S] -> out_krsc [K,R,S,C] (and out_crsk [C,R,S,K] when non-NULL), times
+ * `scale` (the equalised-lr factor of EqualConv2d / EqualLinear / ModulatedConv2d, stylegan2_layers.py:122,164,246),
+ * rounded to TF32 when round_tf32 — one pass instead of mul + permute + copy + round.  sae_filter_unprep is its adjoint
+ * (d_w[k,c,r,s] = scale * d_krsc[k,r,s,c]) for the weight gradient. */
+int sae_filter_prep(const float* w, float* out_krsc, float* out_crsk, int k, int c, int r, int s, float scale,
+                    int round_tf32, void* stream);
+int sae_filter_unprep(const float* d_krsc, float* d_w, int k, int c, int r, int s, float scale, void* stream);
 
 /* nn.ReflectionPad2d((pad_l, pad_r, pad_t, pad_b)) on NHWC data and its adjoint (the encoder's ReflectionPad2d,
  * stylegan2_layers.py:104,642); c % 4 == 0. */

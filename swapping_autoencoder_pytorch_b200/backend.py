@@ -180,6 +180,26 @@ class CudaKernels:
                                                     _stream()), "sae_reflect_pad_backward")
         return dx
 
+    def filter_prep(self, w_oihw, scale, want_crsk=True):
+        """[K,C,R,S] parameter -> ([K,R,S,C], [C,R,S,K] or None), scaled and TF32-rounded, in one kernel"""
+        _need_cuda(w_oihw)
+        k, c, r, s = w_oihw.shape
+        krsc = torch.empty((k, r, s, c), device=w_oihw.device, dtype=w_oihw.dtype)
+        crsk = torch.empty((c, r, s, k), device=w_oihw.device, dtype=w_oihw.dtype) if want_crsk else None
+        with torch.cuda.device(w_oihw.device):
+            check(self.lib.sae_filter_prep(_ptr(w_oihw), _ptr(krsc), _ptr(crsk), k, c, r, s, scale, int(self.round_tf32),
+                                           _stream()), "sae_filter_prep")
+        return krsc, crsk
+
+    def filter_unprep(self, d_krsc, scale):
+        """adjoint of filter_prep: [K,R,S,C] gradient -> [K,C,R,S] * scale"""
+        _need_cuda(d_krsc)
+        k, r, s, c = d_krsc.shape
+        out = torch.empty((k, c, r, s), device=d_krsc.device, dtype=d_krsc.dtype)
+        with torch.cuda.device(d_krsc.device):
+            check(self.lib.sae_filter_unprep(_ptr(d_krsc), _ptr(out), k, c, r, s, scale, _stream()), "sae_filter_unprep")
+        return out
+
     def _filter(self, w):
         """contiguous copy of a (small) filter tensor, rounded to TF32 when the policy says so"""
         w = w.contiguous()
@@ -203,10 +223,11 @@ class CudaKernels:
         e.round_tf32 = int(self.round_tf32 if round_tf32 is None else round_tf32)
         return e
 
-    def conv_fprop(self, x, w_krsc, g, impl=None, **epi):
-        """x [N,H,W,C], w [K,R,S,C] -> y [N,P,Q,K]"""
-        _need_cuda(x, w_krsc)
-        w_krsc = self._filter(w_krsc)
+    def conv_fprop(self, x, w_krsc, g, impl=None, prepared=False, **epi):
+        """x [N,H,W,C], w [K,R,S,C] -> y [N,P,Q,K].  prepared: w is already contiguous and TF32-rounded (filter_prep)"""
+        _need_cuda(x, w_krsc if prepared else None)
+        if not prepared:
+            w_krsc = self._filter(w_krsc)
         assert tuple(x.shape) == (g.N, g.H, g.W, g.C) and tuple(w_krsc.shape) == (g.K, g.R, g.S, g.C), \
             (tuple(x.shape), tuple(w_krsc.shape), g.key())
         y = torch.empty((g.N, g.P, g.Q, g.K), device=x.device, dtype=x.dtype)
@@ -216,12 +237,13 @@ class CudaKernels:
                                             self.conv_impl if impl is None else impl, _stream()), "sae_conv2d_fprop")
         return y
 
-    def conv_dgrad(self, dy, w_krsc, g, impl=None, **epi):
-        """dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C] (also the forward of the transposed convolution)."""
-        _need_cuda(dy, w_krsc)
+    def conv_dgrad(self, dy, w_krsc, g, impl=None, w_crsk=None, **epi):
+        """dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C] (also the forward of the transposed convolution).
+        w_crsk: the same filter already transposed to [C,R,S,K] and rounded (filter_prep), if the caller has it."""
+        _need_cuda(dy)
         assert tuple(dy.shape) == (g.N, g.P, g.Q, g.K) and tuple(w_krsc.shape) == (g.K, g.R, g.S, g.C), \
             (tuple(dy.shape), tuple(w_krsc.shape), g.key())
-        wt = self._filter(w_krsc.permute(3, 1, 2, 0))     # [C,R,S,K]: tiny, stays in L2
+        wt = w_crsk if w_crsk is not None else self._filter(w_krsc.permute(3, 1, 2, 0))     # [C,R,S,K]
         dx = torch.empty((g.N, g.H, g.W, g.C), device=dy.device, dtype=dy.dtype)
         e = self._epi(**epi)
         with torch.cuda.device(dy.device):

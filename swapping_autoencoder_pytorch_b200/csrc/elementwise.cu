@@ -379,6 +379,40 @@ reflect_pad_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, u
     }
 }
 
+// ------------------------------------------------------------------------------------------ filter preparation
+// One pass from the parameter layout [K, C, R, S] to the kernels' layouts: out_krsc[k,r,s,c] (fprop / wgrad) and,
+// optionally, out_crsk[c,r,s,k] (dgrad), multiplied by the equalised-lr scale and rounded to TF32 — replaces the
+// reference's per-call `weight * scale` (stylegan2_layers.py:138) plus the permute / contiguous / round passes.
+__global__ void __launch_bounds__(256)
+filter_prep_kernel(const float* __restrict__ w, float* __restrict__ krsc, float* __restrict__ crsk, int K, int C, int RS,
+                   float scale, int round_tf32) {
+    const int total = K * C * RS;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        // i enumerates the OUTPUT krsc order (c fastest) so the big write is coalesced
+        const int c = i % C;
+        int t = i / C;
+        const int rs = t % RS;
+        const int k = t / RS;
+        float v = __ldg(w + ((size_t)k * C + c) * RS + rs) * scale;
+        if (round_tf32) v = rna_tf32(v);
+        krsc[i] = v;
+        if (crsk) crsk[((size_t)c * RS + rs) * K + k] = v;
+    }
+}
+
+// adjoint: d_w[k,c,r,s] = scale * d_krsc[k,r,s,c]
+__global__ void __launch_bounds__(256)
+filter_unprep_kernel(const float* __restrict__ g, float* __restrict__ dw, int K, int C, int RS, float scale) {
+    const int total = K * C * RS;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % C;
+        int t = i / C;
+        const int rs = t % RS;
+        const int k = t / RS;
+        dw[((size_t)k * C + c) * RS + rs] = __ldg(g + i) * scale;
+    }
+}
+
 // --------------------------------------------------------------------------- bucket pack/unpack
 __global__ void __launch_bounds__(256)
 bucket_copy_kernel(float* const* __restrict__ ptrs, const int64_t* __restrict__ offsets,
@@ -573,6 +607,22 @@ extern "C" int sae_reflect_pad_backward(const float* dy, float* dx, int n, int h
     reflect_pad_bwd_kernel<<<grid_for(tv, 256, 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx),
                                                                                    (uint32_t)tv, h, w, c / 4, oh, ow, pad_l, pad_r, pad_t, pad_b);
     return check_launch("reflect_pad_backward");
+}
+
+extern "C" int sae_filter_prep(const float* w, float* out_krsc, float* out_crsk, int k, int c, int r, int s_, float scale,
+                               int round_tf32, void* stream) {
+    if (!w || !out_krsc || k <= 0 || c <= 0 || r <= 0 || s_ <= 0) return fail(SAE_E_INVALID, "filter_prep: bad arguments");
+    if ((int64_t)k * c * r * s_ >= ((int64_t)1 << 31)) return fail(SAE_E_UNSUPPORTED, "filter_prep: filter too large");
+    filter_prep_kernel<<<grid_for((int64_t)k * c * r * s_, 256), 256, 0, (cudaStream_t)stream>>>(w, out_krsc, out_crsk, k, c, r * s_, scale,
+                                                                                               round_tf32);
+    return check_launch("filter_prep");
+}
+
+extern "C" int sae_filter_unprep(const float* d_krsc, float* d_w, int k, int c, int r, int s_, float scale, void* stream) {
+    if (!d_krsc || !d_w || k <= 0 || c <= 0 || r <= 0 || s_ <= 0) return fail(SAE_E_INVALID, "filter_unprep: bad arguments");
+    if ((int64_t)k * c * r * s_ >= ((int64_t)1 << 31)) return fail(SAE_E_UNSUPPORTED, "filter_unprep: filter too large");
+    filter_unprep_kernel<<<grid_for((int64_t)k * c * r * s_, 256), 256, 0, (cudaStream_t)stream>>>(d_krsc, d_w, k, c, r * s_, scale);
+    return check_launch("filter_unprep");
 }
 
 extern "C" int sae_round_tf32(const float* x, float* out, int64_t n, void* stream) {

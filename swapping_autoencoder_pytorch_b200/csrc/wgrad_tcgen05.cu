@@ -257,7 +257,10 @@ int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
     splits = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
 
     static int win_mode = -1;
-    if (win_mode < 0) { const char* v = getenv("SAE_WGRAD_WINDOW"); win_mode = v ? atoi(v) : 0; }   // 1: base-offset field, 2: plain address
+    // shared-window mode on by default (2 = plain start address: the swizzle is a function of the absolute shared-memory
+    // address, verified on hardware; 1 = additionally set the descriptor's base-offset field — produces wrong results;
+    // 0 = off, three separate boxes)
+    if (win_mode < 0) { const char* v = getenv("SAE_WGRAD_WINDOW"); win_mode = v ? atoi(v) : 2; }
     p.shared_b = (win_mode >= 1 && p.tw == 32 && g->stride == 1 && g->S == 3 && p.cpt == 4 && p.group_taps == 3) ? win_mode : 0;
 
     CUtensorMap mdy, mx;

@@ -124,7 +124,7 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
     def forward(self, input):
-        return conv2d(input, self.weight * self.scale, bias=self.bias, stride=self.stride, padding=self.padding)
+        return conv2d(input, self.weight, bias=self.bias, stride=self.stride, padding=self.padding, wscale=self.scale)
 
     def __repr__(self):
         o, i, k, _ = self.weight.shape
@@ -143,11 +143,10 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
 
     def forward(self, input):
-        w = self.weight * self.scale
         if input.dim() > 2:
-            out = conv2d(input, w[:, :, None, None])
+            out = conv2d(input, self.weight[:, :, None, None], wscale=self.scale)
         else:
-            out = linear(input, w)
+            out = linear(input, self.weight, wscale=self.scale)
         if self.activation:
             return fused_leaky_relu(out, self.bias * self.lr_mul)
         if self.bias is not None:
@@ -446,8 +445,8 @@ class ConvLayer(nn.Sequential):
         conv, act = mods["Conv"], mods.get("Act")
         if isinstance(act, FusedLeakyReLU) and conv.bias is None:
             # bias + leaky-ReLU applied in the conv kernel's epilogue
-            return conv2d_bias_act(x, conv.weight * conv.scale, act.bias, stride=conv.stride, padding=conv.padding,
-                                   negative_slope=act.negative_slope, scale=act.scale)
+            return conv2d_bias_act(x, conv.weight, act.bias, stride=conv.stride, padding=conv.padding,
+                                   negative_slope=act.negative_slope, scale=act.scale, wscale=conv.scale)
         x = conv(x)
         return act(x) if act is not None else x
 
@@ -471,7 +470,8 @@ class ResBlock(nn.Module):
         if conv.bias is None and "Act" not in mods and "RefPad" not in mods:
             # skip branch: [Blur] -> 1x1 conv whose epilogue performs the residual merge
             h = mods["Blur"](input) if "Blur" in mods else input
-            return conv2d_residual(h, conv.weight * conv.scale, out, 1.0 / _SQRT2, stride=conv.stride, padding=conv.padding)
+            return conv2d_residual(h, conv.weight, out, 1.0 / _SQRT2, stride=conv.stride, padding=conv.padding,
+                                   wscale=conv.scale)
         return add_scale(out, self.skip(input), 1.0 / _SQRT2)
 
 

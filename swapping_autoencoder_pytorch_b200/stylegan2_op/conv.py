@@ -34,38 +34,72 @@ def _impl(g):
     return 1 if (g.H == 1 and g.W == 1 and g.P == 1 and g.Q == 1) else None
 
 
-class _ConvFprop(Function):
-    """y = conv(x, w)   x: logical NCHW, w: [K,R,S,C]"""
+class _PrepFilter(Function):
+    """[K,C,R,S] parameter * scale -> ([K,R,S,C], [C,R,S,K]) in the kernels' layouts, TF32-rounded, in ONE kernel
+    (the reference spends a `weight * scale` pass per call, stylegan2_layers.py:138; the layouts and rounding would cost
+    three more).  Linear, so its backward is the adjoint kernel and the pair is closed under differentiation.  The second
+    output is an auxiliary copy for the dgrad kernel and carries no gradient."""
 
     @staticmethod
-    def forward(ctx, x, w, g):
+    def forward(ctx, w_oihw, scale):
+        ctx.scale = scale
+        krsc, crsk = backend.kernels().filter_prep(w_oihw.contiguous(), scale)
+        ctx.mark_non_differentiable(crsk)
+        return krsc, crsk
+
+    @staticmethod
+    def backward(ctx, d_krsc, _unused):
+        return _UnprepFilter.apply(d_krsc, ctx.scale), None
+
+
+class _UnprepFilter(Function):
+    @staticmethod
+    def forward(ctx, d_krsc, scale):
+        ctx.scale = scale
+        return backend.kernels().filter_unprep(d_krsc.contiguous(), scale)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return _PrepFilter.apply(gg, ctx.scale)[0], None
+
+
+def prep_filter(weight, scale=1.0):
+    """returns (w_krsc, w_crsk) for the conv Functions below"""
+    return _PrepFilter.apply(weight, float(scale))
+
+
+class _ConvFprop(Function):
+    """y = conv(x, w)   x: logical NCHW, w: [K,R,S,C]; wt: the same filter as [C,R,S,K] (from prep_filter) or None"""
+
+    @staticmethod
+    def forward(ctx, x, w, wt, g):
         ctx.g = g
-        ctx.save_for_backward(x, w)
-        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g)))
+        ctx.save_for_backward(x, w, wt)
+        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g), prepared=wt is not None))
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
-        dx = _ConvDgrad.apply(dy, w, ctx.g) if ctx.needs_input_grad[0] else None
+        x, w, wt = ctx.saved_tensors
+        dx = _ConvDgrad.apply(dy, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
         dw = _ConvWgrad.apply(dy, x, ctx.g) if ctx.needs_input_grad[1] else None
-        return dx, dw, None
+        return dx, dw, None, None
 
 
 class _ConvDgrad(Function):
     """dx = conv^T(dy, w)   (also the forward of a transposed convolution)"""
 
     @staticmethod
-    def forward(ctx, dy, w, g):
+    def forward(ctx, dy, w, wt, g):
         ctx.g = g
-        ctx.save_for_backward(dy, w)
-        return _nchw(backend.kernels().conv_dgrad(_nhwc(dy), w.contiguous(), g, impl=_impl(g)))
+        ctx.save_for_backward(dy, w, wt)
+        return _nchw(backend.kernels().conv_dgrad(_nhwc(dy), w.contiguous(), g, impl=_impl(g), w_crsk=wt))
 
     @staticmethod
     def backward(ctx, ddx):
-        dy, w = ctx.saved_tensors
-        d_dy = _ConvFprop.apply(ddx, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dy, w, wt = ctx.saved_tensors
+        d_dy = _ConvFprop.apply(ddx, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
         d_w = _ConvWgrad.apply(dy, ddx, ctx.g) if ctx.needs_input_grad[1] else None
-        return d_dy, d_w, None
+        return d_dy, d_w, None, None
 
 
 class _ConvWgrad(Function):
@@ -80,8 +114,8 @@ class _ConvWgrad(Function):
     @staticmethod
     def backward(ctx, ddw):
         dy, x = ctx.saved_tensors
-        d_dy = _ConvFprop.apply(x, ddw, ctx.g) if ctx.needs_input_grad[0] else None
-        d_x = _ConvDgrad.apply(dy, ddw, ctx.g) if ctx.needs_input_grad[1] else None
+        d_dy = _ConvFprop.apply(x, ddw, None, ctx.g) if ctx.needs_input_grad[0] else None
+        d_x = _ConvDgrad.apply(dy, ddw, None, ctx.g) if ctx.needs_input_grad[1] else None
         return d_dy, d_x, None
 
 
@@ -92,21 +126,21 @@ class _ConvBiasAct(Function):
     stylegan2_layers.py:136-142 + fused_act.py:89-96)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, g, negative_slope, gain):
-        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g), bias=bias.contiguous(),
-                                                 act=3, alpha=negative_slope, gain=gain))
+    def forward(ctx, x, w, wt, bias, g, negative_slope, gain):
+        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g), prepared=wt is not None,
+                                                 bias=bias.contiguous(), act=3, alpha=negative_slope, gain=gain))
         ctx.g, ctx.cfg = g, (negative_slope, gain)
-        ctx.save_for_backward(x, w, out)
+        ctx.save_for_backward(x, w, wt, out)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         from .fused_act import FusedLeakyReLUFunctionBackward
-        x, w, out = ctx.saved_tensors
+        x, w, wt, out = ctx.saved_tensors
         gi, gb = FusedLeakyReLUFunctionBackward.apply(dy, out, *ctx.cfg)
-        dx = _ConvDgrad.apply(gi, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dx = _ConvDgrad.apply(gi, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
         dw = _ConvWgrad.apply(gi, x, ctx.g) if ctx.needs_input_grad[1] else None
-        return dx, dw, gb, None, None, None
+        return dx, dw, None, gb, None, None, None
 
 
 class _ConvNoiseBiasAct(Function):
@@ -114,28 +148,28 @@ class _ConvNoiseBiasAct(Function):
     (stylegan2_layers.py:398-405).  Generator only, hence once-differentiable."""
 
     @staticmethod
-    def forward(ctx, x, w, noise, noise_weight, bias, g, negative_slope, gain):
+    def forward(ctx, x, w, wt, noise, noise_weight, bias, g, negative_slope, gain):
         noise_flat = noise.reshape(-1).contiguous()
-        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, bias=bias.contiguous(), act=3,
-                                                 alpha=negative_slope, gain=gain, noise=noise_flat,
+        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, prepared=wt is not None, bias=bias.contiguous(),
+                                                 act=3, alpha=negative_slope, gain=gain, noise=noise_flat,
                                                  noise_weight=noise_weight.contiguous()))
         ctx.g, ctx.cfg = g, (negative_slope, gain, tuple(noise.shape))
-        ctx.save_for_backward(x, w, out, noise_flat, noise_weight)
+        ctx.save_for_backward(x, w, wt, out, noise_flat, noise_weight)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, w, out, noise_flat, noise_weight = ctx.saved_tensors
+        x, w, wt, out, noise_flat, noise_weight = ctx.saved_tensors
         negative_slope, gain, noise_shape = ctx.cfg
         k = backend.kernels()
         gi, gb, gnw = k.bias_act_backward(_nhwc(dy), _nhwc(out), negative_slope, gain, want_bias=True, noise=noise_flat)
-        dx = _nchw(k.conv_dgrad(gi, w.contiguous(), ctx.g)) if ctx.needs_input_grad[0] else None
+        dx = _nchw(k.conv_dgrad(gi, w.contiguous(), ctx.g, w_crsk=wt)) if ctx.needs_input_grad[0] else None
         dw = k.conv_wgrad(gi, _nhwc(x), ctx.g) if ctx.needs_input_grad[1] else None
         g_noise = None
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[3]:
             g_noise = (gi.sum(dim=3) * noise_weight).reshape(noise_shape)
-        return dx, dw, g_noise, gnw, gb, None, None, None
+        return dx, dw, None, g_noise, gnw, gb, None, None, None
 
 
 class _ConvResidual(Function):
@@ -144,18 +178,19 @@ class _ConvResidual(Function):
     primitives, so it is valid under double backward."""
 
     @staticmethod
-    def forward(ctx, x, w, res, g, scale):
+    def forward(ctx, x, w, wt, res, g, scale):
         ctx.g, ctx.scale = g, scale
-        ctx.save_for_backward(x, w)
-        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, residual=_nhwc(res), res_scale=scale))
+        ctx.save_for_backward(x, w, wt)
+        return _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, prepared=wt is not None, residual=_nhwc(res),
+                                                 res_scale=scale))
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        x, w, wt = ctx.saved_tensors
         gs = _AddScale.apply(dy, None, ctx.scale)
-        dx = _ConvDgrad.apply(gs, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dx = _ConvDgrad.apply(gs, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
         dw = _ConvWgrad.apply(gs, x, ctx.g) if ctx.needs_input_grad[1] else None
-        return dx, dw, (gs if ctx.needs_input_grad[2] else None), None, None
+        return dx, dw, None, (gs if ctx.needs_input_grad[3] else None), None, None
 
 
 def _pad4(input, weight):
@@ -184,33 +219,38 @@ def _geom_for(input, weight, stride, padding):
     return make_geom(n, h, w_, c, k, r, s, stride, padding, padding)
 
 
-def conv2d_bias_act(input, weight, bias, stride=1, padding=0, negative_slope=0.2, scale=2 ** 0.5):
-    """fused_leaky_relu(F.conv2d(input, weight, stride=stride, padding=padding), bias) in one kernel"""
+def conv2d_bias_act(input, weight, bias, stride=1, padding=0, negative_slope=0.2, scale=2 ** 0.5, wscale=1.0):
+    """fused_leaky_relu(F.conv2d(input, weight * wscale, stride=stride, padding=padding), bias) in one kernel"""
     input, weight, cout = _pad4(input, weight)
     if cout is not None:
         bias = F.pad(bias, (0, weight.shape[0] - cout))
     g = _geom_for(input, weight, stride, padding)
-    out = _ConvBiasAct.apply(input, weight.permute(0, 2, 3, 1), bias, g, negative_slope, scale)
+    w, wt = prep_filter(weight, wscale)
+    out = _ConvBiasAct.apply(input, w, wt, bias, g, negative_slope, scale)
     return out if cout is None else out[:, :cout]
 
 
-def conv2d_noise_bias_act(input, weight, noise, noise_weight, bias, padding=0, negative_slope=0.2, scale=2 ** 0.5):
-    """fused_leaky_relu(F.conv2d(input, weight, padding=padding) + noise_weight * noise, bias) in one kernel"""
+def conv2d_noise_bias_act(input, weight, noise, noise_weight, bias, padding=0, negative_slope=0.2, scale=2 ** 0.5,
+                          wscale=1.0):
+    """fused_leaky_relu(F.conv2d(input, weight * wscale, padding=padding) + noise_weight * noise, bias) in one kernel"""
     g = _geom_for(input, weight, 1, padding)
-    return _ConvNoiseBiasAct.apply(input, weight.permute(0, 2, 3, 1), noise, noise_weight, bias, g, negative_slope, scale)
+    w, wt = prep_filter(weight, wscale)
+    return _ConvNoiseBiasAct.apply(input, w, wt, noise, noise_weight, bias, g, negative_slope, scale)
 
 
-def conv2d_residual(input, weight, residual, scale, stride=1, padding=0):
-    """(F.conv2d(input, weight, stride=stride, padding=padding) + residual) * scale in one kernel"""
+def conv2d_residual(input, weight, residual, scale, stride=1, padding=0, wscale=1.0):
+    """(F.conv2d(input, weight * wscale, stride=stride, padding=padding) + residual) * scale in one kernel"""
     g = _geom_for(input, weight, stride, padding)
-    return _ConvResidual.apply(input, weight.permute(0, 2, 3, 1), residual, g, scale)
+    w, wt = prep_filter(weight, wscale)
+    return _ConvResidual.apply(input, w, wt, residual, g, scale)
 
 
-def conv2d(input, weight, bias=None, stride=1, padding=0):
-    """``F.conv2d(input, weight, bias, stride, padding)`` for NCHW-shaped input, [Cout,Cin,R,S] weight."""
+def conv2d(input, weight, bias=None, stride=1, padding=0, wscale=1.0):
+    """``F.conv2d(input, weight * wscale, bias, stride, padding)`` for NCHW-shaped input, [Cout,Cin,R,S] weight."""
     input, weight, cout = _pad4(input, weight)
     g = _geom_for(input, weight, stride, padding)
-    out = _ConvFprop.apply(input, weight.permute(0, 2, 3, 1), g)
+    w, wt = prep_filter(weight, wscale)
+    out = _ConvFprop.apply(input, w, wt, g)
     if cout is not None:
         out = out[:, :cout]
     if bias is not None:
@@ -218,7 +258,7 @@ def conv2d(input, weight, bias=None, stride=1, padding=0):
     return out
 
 
-def conv_transpose2d(input, weight, stride=2, padding=0):
+def conv_transpose2d(input, weight, stride=2, padding=0, wscale=1.0):
     """``F.conv_transpose2d(input, weight[Cin,Cout,R,S], stride, padding)`` — computed as the data-gradient of
     the strided convolution whose filter is ``weight`` read as [K=Cin, C=Cout, R, S]."""
     n, cin, h, w_ = input.shape
@@ -227,15 +267,17 @@ def conv_transpose2d(input, weight, stride=2, padding=0):
     oh = (h - 1) * stride - 2 * padding + r
     ow = (w_ - 1) * stride - 2 * padding + s
     g = make_geom(n, oh, ow, cout, cin, r, s, stride, padding, padding, P=h, Q=w_)
-    return _ConvDgrad.apply(input, weight.permute(0, 2, 3, 1), g)
+    w, wt = prep_filter(weight, wscale)
+    return _ConvDgrad.apply(input, w, wt, g)
 
 
-def linear(input, weight, bias=None):
-    """``F.linear`` for [B, in] x [out, in]: a 1x1 convolution on a 1x1 map."""
+def linear(input, weight, bias=None, wscale=1.0):
+    """``F.linear(input, weight * wscale)`` for [B, in] x [out, in]: a 1x1 convolution on a 1x1 map."""
     b, cin = input.shape
     cout = weight.shape[0]
     g = make_geom(b, 1, 1, cin, cout, 1, 1, 1, 0, 0)
-    out = _ConvFprop.apply(input.view(b, cin, 1, 1), weight.view(cout, 1, 1, cin), g).reshape(b, cout)
+    w, wt = prep_filter(weight.view(cout, cin, 1, 1), wscale)
+    out = _ConvFprop.apply(input.reshape(b, cin, 1, 1), w, wt, g).reshape(b, cout)
     if bias is not None:
         out = out + bias
     return out

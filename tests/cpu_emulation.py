@@ -102,6 +102,13 @@ class EmulatedKernels:
         g, = torch.autograd.grad(y, x0, _nchw(dy).detach())
         return _nhwc(g)
 
+    def filter_prep(self, w_oihw, scale, want_crsk=True):
+        w = w_oihw * scale
+        return w.permute(0, 2, 3, 1).contiguous(), (w.permute(1, 2, 3, 0).contiguous() if want_crsk else None)
+
+    def filter_unprep(self, d_krsc, scale):
+        return d_krsc.permute(0, 3, 1, 2).contiguous() * scale
+
     def _epilogue(self, y, bias=None, act=1, alpha=0.2, gain=1.0, noise=None, noise_weight=None, residual=None,
                   res_scale=1.0, round_tf32=None):
         if bias is not None:
@@ -115,11 +122,13 @@ class EmulatedKernels:
             y = (y + residual) * res_scale
         return y
 
-    def conv_fprop(self, x, w_krsc, g, impl=None, **epi):
+    def conv_fprop(self, x, w_krsc, g, impl=None, prepared=False, **epi):
         y = _nhwc(_conv(g, _nchw(x), w_krsc))
         return self._epilogue(y, **epi)
 
-    def conv_dgrad(self, dy, w_krsc, g, impl=None, **epi):
+    def conv_dgrad(self, dy, w_krsc, g, impl=None, w_crsk=None, **epi):
+        if w_crsk is not None:
+            assert torch.equal(w_crsk, w_krsc.permute(3, 1, 2, 0))
         x0 = torch.zeros(g.N, g.C, g.H, g.W, dtype=dy.dtype, requires_grad=True)
         with torch.enable_grad():
             y = _conv(g, x0, w_krsc.detach())

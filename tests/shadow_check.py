@@ -91,12 +91,19 @@ class ShadowKernels:
     def _impl_name(self, g, d, impl):
         return impl if impl is not None else self.real.conv_impl_for(g, d)
 
-    def conv_fprop(self, x, w, g, impl=None, **epi):
-        return self._both("conv_fprop", "g%s impl%s epi%s" % (g.key(), self._impl_name(g, 0, impl), sorted(epi)), (x, w, g),
-                          dict(epi, impl=impl))
+    def filter_prep(self, w, scale, want_crsk=True):
+        return self._both("filter_prep", "w%s" % (tuple(w.shape),), (w, scale), dict(want_crsk=want_crsk))
 
-    def conv_dgrad(self, dy, w, g, impl=None, **epi):
-        return self._both("conv_dgrad", "g%s impl%s" % (g.key(), self._impl_name(g, 1, impl)), (dy, w, g), dict(epi, impl=impl))
+    def filter_unprep(self, d, scale):
+        return self._both("filter_unprep", "w%s" % (tuple(d.shape),), (d, scale), {})
+
+    def conv_fprop(self, x, w, g, impl=None, prepared=False, **epi):
+        return self._both("conv_fprop", "g%s impl%s epi%s" % (g.key(), self._impl_name(g, 0, impl), sorted(epi)), (x, w, g),
+                          dict(epi, impl=impl, prepared=prepared))
+
+    def conv_dgrad(self, dy, w, g, impl=None, w_crsk=None, **epi):
+        return self._both("conv_dgrad", "g%s impl%s" % (g.key(), self._impl_name(g, 1, impl)), (dy, w, g),
+                          dict(epi, impl=impl, w_crsk=w_crsk))
 
     def conv_wgrad(self, dy, x, g, impl=None):
         return self._both("conv_wgrad", "g%s impl%s" % (g.key(), self._impl_name(g, 2, impl)), (dy, x, g), dict(impl=impl))

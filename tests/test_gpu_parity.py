@@ -182,6 +182,17 @@ def test_reflect_pad(exact_fp32):
         assert rel_err(g, g_ref) < TOL_FP32
 
 
+def test_filter_prep(exact_fp32):
+    kern = backend.kernels()
+    for shape in ((64, 32, 3, 3), (3, 8, 1, 1), (512, 512, 3, 3), (8, 2048, 1, 1)):
+        w = rnd(1, *shape)
+        krsc, crsk = kern.filter_prep(cuda(w), 0.37)
+        assert rel_err(krsc, w.permute(0, 2, 3, 1) * 0.37) < TOL_FP32
+        assert rel_err(crsk, w.permute(1, 2, 3, 0) * 0.37) < TOL_FP32
+        d = rnd(2, shape[0], shape[2], shape[3], shape[1])
+        assert rel_err(kern.filter_unprep(cuda(d), 0.37), d.permute(0, 3, 1, 2) * 0.37) < TOL_FP32
+
+
 def test_tf32_rounding_policy():
     """with the policy on, every stored value is the nearest TF32 number of the exact fp32 result"""
     from swapping_autoencoder_pytorch_b200.stylegan2_op import add_scale, fused_leaky_relu
