@@ -1,11 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
+echo "==== conv tests (shared-window pair kernel)"
+timeout 300 python -m pytest tests -m gpu -q --timeout 120 -k "conv or shadow" 2>&1 | grep -v "^E   *+\|^E  *where" | tail -12
+echo ==== CONV BENCH
+timeout 300 python scripts/conv_bench.py --dirs fprop,dgrad 2>&1 | tee gpurun_out/conv_bench.txt | head -22
 echo ==== full tests
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | grep -v "^E   *+\|^E  *where" | tail -8
-echo ==== SMOKE
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | grep -v "^E   *+\|^E  *where" | tail -6
 echo ==== BENCH
-SAE_BENCH_CONV_TABLE=gpurun_out/conv_table.txt timeout 900 python bench.py --steps 8 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_r1.json | cut -c1-330
-echo ==== NCU launches
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 4000 --csv --log-file gpurun_out/launches_r1d.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-tail -1 gpurun_out/ncu_bench.log | cut -c1-120
+SAE_BENCH_CONV_TABLE=gpurun_out/conv_table.txt timeout 900 python bench.py --steps 8 --warmup 4 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_r1.json | cut -c1-330
