@@ -422,17 +422,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
 // L2->SM traffic per channel block drops from 9 x 16 KB (A) + 9 x B to 22.5 KB + 9 x B: with BLOCK_N = 256 in a CTA
 // pair that is ~36 B/clk/SM at full tensor rate — the kernel becomes tensor-bound.
 constexpr int TC3_NA = 2;                           // A-window ring slots
-constexpr int TC3_NB = 4;                           // B ring slots
+template <int BLOCK_N> constexpr int tc3_nb() { return BLOCK_N >= 256 ? 4 : 8; }   // B ring slots: 64 KB either way — deep
+                                                                                   // enough to cover L2 latency per tap
 constexpr int TC3_ASLOT = 23 * 1024;                // >= 18 * 10 * 128 B, multiple of 1024
 
 template <int BLOCK_N>
-constexpr size_t tc3_smem_bytes() { return (size_t)TC3_NB * (BLOCK_N / 2) * 128 + (size_t)TC3_NA * TC3_ASLOT + 1024 + 256; }
+constexpr size_t tc3_smem_bytes() { return (size_t)tc3_nb<BLOCK_N>() * (BLOCK_N / 2) * 128 + (size_t)TC3_NA * TC3_ASLOT + 1024 + 256; }
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks) {
     constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
+    constexpr int TC3_NB = tc3_nb<BLOCK_N>();
     constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
     constexpr uint32_t RING = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
     constexpr uint32_t TMEM_COLS = BLOCK_N;

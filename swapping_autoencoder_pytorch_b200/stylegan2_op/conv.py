@@ -199,7 +199,9 @@ def _pad4(input, weight):
     (input, weight, original Cout or None)."""
     cin = input.shape[1]
     if cin % 4 != 0:
-        extra = 4 - cin % 4
+        # RGB inputs go to 32 channels: one 128-byte TMA row per pixel, so FromRGB / the first Dpatch conv and their
+        # weight gradients run on the tensor-core kernels (the extra zero channels cost 1/4 of the 128-channel output)
+        extra = (32 - cin) if cin < 32 else 4 - cin % 4
         input = F.pad(input, (0, 0, 0, 0, 0, extra))
         weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
     cout = weight.shape[0]
