@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 8
+#define SAE_ABI_VERSION 9
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -60,12 +60,12 @@ int sae_upfirdn2d(const float* input, const float* kernel, float* out,
                   int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                   int round_tf32, void* stream);
 
-/* Fast path of the above for the FIRs the networks actually use (up = down = 1, kernel = outer(taps_y, taps_x) with
- * at most 4 taps, e.g. make_kernel([1,3,3,1]) of stylegan2_layers.py:27-35): taps are HOST arrays, unflipped.
- * Returns SAE_E_UNSUPPORTED when the restrictions (minor % 4, alignment, 32-bit work-item count) do not hold. */
+/* Fast path of the above for the FIRs the networks actually use: kernel = outer(taps_y, taps_x) with at most 4 taps
+ * (e.g. make_kernel([1,3,3,1]) of stylegan2_layers.py:27-35), (up, down) in {(1,1), (1,2), (2,1)}: taps are HOST arrays,
+ * unflipped.  Returns SAE_E_UNSUPPORTED when the restrictions (minor % 4, alignment, 32-bit work-item count) do not hold. */
 int sae_upfirdn2d_separable(const float* input, const float* taps_y, const float* taps_x, float* out,
                             int64_t major, int in_h, int in_w, int minor, int kernel_h, int kernel_w,
-                            int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_tf32, void* stream);
+                            int up, int down, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_tf32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * fused_bias_act — out = act(x + b[(i / step_b) % size_b]) * scale.

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsae_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-SAE_ABI_VERSION = 8
+SAE_ABI_VERSION = 9
 
 c_float_p = ctypes.c_void_p   # raw device pointers travel as integers
 c_stream = ctypes.c_void_p
@@ -47,7 +47,7 @@ SIGNATURES = {
     "sae_upfirdn2d_separable": (ctypes.c_int, [c_float_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_int64,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                               c_stream]),
+                                               ctypes.c_int, ctypes.c_int, c_stream]),
     "sae_fused_bias_act": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                           c_float_p, c_float_p, ctypes.c_int64, ctypes.c_int, c_stream]),

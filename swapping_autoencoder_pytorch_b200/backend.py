@@ -68,13 +68,14 @@ class CudaKernels:
         oh = (h * up_y + pad_y0 + pad_y1 - kh) // down_y + 1
         ow = (w * up_x + pad_x0 + pad_x1 - kw) // down_x + 1
         out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
-        if up_x == up_y == down_x == down_y == 1 and c % 4 == 0 and n * ((oh + 15) // 16) * ow * (c // 4) < 2 ** 32 \
-                and x.data_ptr() % 16 == 0 and n > 0:
+        ud = (up_x, down_x)
+        if up_x == up_y and down_x == down_y and ud in ((1, 1), (1, 2), (2, 1)) and c % 4 == 0 \
+                and n * oh * ow * (c // 4) < 2 ** 32 and x.data_ptr() % 16 == 0 and n > 0:
             if taps is not None and len(taps[0]) == kh and len(taps[1]) == kw and kh == kw and kh <= 4:
                 ty = (ctypes.c_float * kh)(*taps[0])
                 tx = (ctypes.c_float * kw)(*taps[1])
                 with torch.cuda.device(x.device):
-                    check(self.lib.sae_upfirdn2d_separable(_ptr(x), ty, tx, _ptr(out), n, h, w, c, kh, kw, pad_x0,
+                    check(self.lib.sae_upfirdn2d_separable(_ptr(x), ty, tx, _ptr(out), n, h, w, c, kh, kw, up_x, down_x, pad_x0,
                                                            pad_x1, pad_y0, pad_y1, int(self.round_tf32), _stream()),
                           "sae_upfirdn2d_separable")
                 return out

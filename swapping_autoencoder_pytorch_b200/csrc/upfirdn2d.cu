@@ -178,7 +178,7 @@ fir_strip_kernel(const float* __restrict__ x, const float* __restrict__ k, float
 // latency.  Taps arrive by value (host arrays), already flipped.
 struct SepTaps { float y[8]; float x[8]; };
 
-template <int KH, int KW, int ROWS>
+template <int KH, int KW, int ROWS, int DOWN>
 __global__ void __launch_bounds__(256)
 fir_sep_strip_kernel(const float* __restrict__ x, float* __restrict__ out, FirParams p, SepTaps taps) {
     const int cv = p.minor >> 2;
@@ -192,7 +192,7 @@ fir_sep_strip_kernel(const float* __restrict__ x, float* __restrict__ out, FirPa
         const int strip = (int)(t % strips);
         const int64_t n = t / strips;
         const int oy0 = strip * ROWS;
-        const int ix0 = ox - p.pad_x0;
+        const int ix0 = ox * DOWN - p.pad_x0;
         const float* xn = x + n * (int64_t)p.in_h * p.in_w * p.minor + (int64_t)c * 4;
         float4 win[KH];
 
@@ -211,13 +211,16 @@ fir_sep_strip_kernel(const float* __restrict__ x, float* __restrict__ out, FirPa
             }
             return a;
         };
+        // window rows a = 0..KH-1 hold input rows oy*DOWN - pad + a; each output advances the window by DOWN rows
+        constexpr int KEEP = KH > DOWN ? KH - DOWN : 0;
 #pragma unroll
-        for (int a = 0; a < KH - 1; ++a) win[a] = hrow(oy0 - p.pad_y0 + a);
+        for (int a = 0; a < KEEP; ++a) win[a] = hrow(oy0 * DOWN - p.pad_y0 + a);
 #pragma unroll 4
         for (int r = 0; r < ROWS; ++r) {
             const int oy = oy0 + r;
             if (oy >= p.out_h) break;
-            win[KH - 1] = hrow(oy - p.pad_y0 + KH - 1);
+#pragma unroll
+            for (int a = KEEP; a < KH; ++a) win[a] = hrow(oy * DOWN - p.pad_y0 + a);
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int a = 0; a < KH; ++a) {
@@ -228,21 +231,61 @@ fir_sep_strip_kernel(const float* __restrict__ x, float* __restrict__ out, FirPa
             float* dst = out + ((n * p.out_h + oy) * (int64_t)p.out_w + ox) * p.minor + (int64_t)c * 4;
             *reinterpret_cast<float4*>(dst) = acc;
 #pragma unroll
-            for (int a = 0; a < KH - 1; ++a) win[a] = win[a + 1];
+            for (int a = 0; a < KEEP; ++a) win[a] = win[a + DOWN];
         }
+    }
+}
+
+// zero-insert x2 upsampling FIR (the adjoint of the down = 2 filter): output (y, x) only sees the taps whose
+// up-sampled position is even — 2 of 4 per axis — so it is a 2 x 2 gather from the low-resolution input
+template <int KH, int KW>
+__global__ void __launch_bounds__(256)
+fir_sep_up2_kernel(const float* __restrict__ x, float* __restrict__ out, FirParams p, SepTaps taps) {
+    const int cv = p.minor >> 2;
+    const uint32_t total = (uint32_t)(p.major * p.out_h * p.out_w * cv);
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const uint32_t c = idx % cv;
+        uint32_t t = idx / cv;
+        const int ox = (int)(t % p.out_w); t /= p.out_w;
+        const int oy = (int)(t % p.out_h);
+        const int64_t n = t / p.out_h;
+        const float* xn = x + n * (int64_t)p.in_h * p.in_w * p.minor + (int64_t)c * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < KH; ++a) {
+            const int uy = oy + a - p.pad_y0;
+            if (uy < 0 || (uy & 1)) continue;
+            const int iy = uy >> 1;
+            if (iy >= p.in_h) continue;
+#pragma unroll
+            for (int b = 0; b < KW; ++b) {
+                const int ux = ox + b - p.pad_x0;
+                if (ux < 0 || (ux & 1)) continue;
+                const int ix = ux >> 1;
+                if (ix >= p.in_w) continue;
+                const float w = taps.y[a] * taps.x[b];
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xn + ((int64_t)iy * p.in_w + ix) * p.minor));
+                acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+            }
+        }
+        if (p.round_tf32) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
+        *reinterpret_cast<float4*>(out + (int64_t)idx * 4) = acc;
     }
 }
 
 template <int KH, int KW>
 static void launch_sep(const float* x, float* out, const FirParams& p, const SepTaps& taps, cudaStream_t st) {
     constexpr int ROWS = 16;
-    const int strips = (p.out_h + ROWS - 1) / ROWS;
-    int64_t total = p.major * (int64_t)strips * p.out_w * (p.minor / 4);
+    int64_t total;
+    if (p.up_x == 2) total = p.major * (int64_t)p.out_h * p.out_w * (p.minor / 4);
+    else total = p.major * (int64_t)((p.out_h + ROWS - 1) / ROWS) * p.out_w * (p.minor / 4);
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    fir_sep_strip_kernel<KH, KW, ROWS><<<(unsigned)blocks, 256, 0, st>>>(x, out, p, taps);
+    if (p.up_x == 2) fir_sep_up2_kernel<KH, KW><<<(unsigned)blocks, 256, 0, st>>>(x, out, p, taps);
+    else if (p.down_x == 2) fir_sep_strip_kernel<KH, KW, ROWS, 2><<<(unsigned)blocks, 256, 0, st>>>(x, out, p, taps);
+    else fir_sep_strip_kernel<KH, KW, ROWS, 1><<<(unsigned)blocks, 256, 0, st>>>(x, out, p, taps);
 }
 
 template <int KH, int KW>
@@ -307,7 +350,8 @@ extern "C" int sae_upfirdn2d(const float* input, const float* kernel, float* out
 // Restricted to up = down = 1, taps <= 4, minor % 4 == 0, < 2^32 work items; callers fall back to sae_upfirdn2d otherwise.
 extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, const float* taps_x, float* out,
                                        int64_t major, int in_h, int in_w, int minor, int kernel_h, int kernel_w,
-                                       int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_tf32, void* stream) {
+                                       int up, int down, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_tf32,
+                                       void* stream) {
     using namespace sae;
     if (major == 0) return SAE_OK;
     if (!input || !taps_y || !taps_x || !out) return fail(SAE_E_INVALID, "upfirdn2d_separable: null pointer");
@@ -316,11 +360,14 @@ extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, 
         return fail(SAE_E_UNSUPPORTED, "upfirdn2d_separable: needs minor %% 4 == 0 and 16-byte aligned pointers");
     FirParams p;
     p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
-    p.up_x = p.up_y = p.down_x = p.down_y = 1; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.round_tf32 = round_tf32;
-    p.out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
-    p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
-    if (p.out_h <= 0 || p.out_w <= 0) return fail(SAE_E_INVALID, "upfirdn2d_separable: kernel larger than padded input");
-    if (major * (int64_t)((p.out_h + 15) / 16) * p.out_w * (minor / 4) >= (int64_t)1 << 32)
+    if (!((up == 1 && (down == 1 || down == 2)) || (up == 2 && down == 1)))
+        return fail(SAE_E_UNSUPPORTED, "upfirdn2d_separable: (up, down) must be (1,1), (1,2) or (2,1)");
+    p.up_x = p.up_y = up; p.down_x = p.down_y = down; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.round_tf32 = round_tf32;
+    const int full_h = in_h * up + pad_y0 + pad_y1 - kernel_h, full_w = in_w * up + pad_x0 + pad_x1 - kernel_w;
+    if (full_h < 0 || full_w < 0) return fail(SAE_E_INVALID, "upfirdn2d_separable: kernel larger than padded input");
+    p.out_h = full_h / down + 1;
+    p.out_w = full_w / down + 1;
+    if (major * (int64_t)p.out_h * p.out_w * (minor / 4) >= (int64_t)1 << 32)
         return fail(SAE_E_UNSUPPORTED, "upfirdn2d_separable: too many work items for 32-bit indexing");
     SepTaps t;
     for (int i = 0; i < 8; ++i) { t.y[i] = 0.f; t.x[i] = 0.f; }

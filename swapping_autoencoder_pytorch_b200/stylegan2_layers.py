@@ -106,10 +106,12 @@ class Blur(nn.Module):
             self.reflection_pad = nn.ReflectionPad2d((pad[0], pad[1], pad[0], pad[1]))
             self.pad = (0, 0)
 
-    def forward(self, input):
+    def forward(self, input, down=1):
+        """``down`` (extension): decimate the blurred result — used when the consumer is a stride-2 1x1 convolution,
+        which only ever reads the even positions (blur-then-subsample == subsample-of-blur)."""
         if self.reflection:
             input = reflect_pad(input, self.reflection_pad.padding)
-        return upfirdn2d(input, self.kernel, pad=self.pad, taps=self.taps)
+        return upfirdn2d(input, self.kernel, down=down, pad=self.pad, taps=self.taps)
 
 
 class EqualConv2d(nn.Module):
@@ -413,6 +415,10 @@ class Generator(nn.Module):
         return (skip, latent) if return_latents else (skip, None)
 
 
+def _is_pointwise_stride2(conv):
+    return conv.weight.shape[2] == 1 and conv.weight.shape[3] == 1 and conv.stride == 2 and conv.padding == 0
+
+
 class ConvLayer(nn.Sequential):
     """[Blur | RefPad] -> Conv -> [Act] with the reference's sub-module names (reference :612-668)."""
 
@@ -438,16 +444,20 @@ class ConvLayer(nn.Sequential):
 
     def forward(self, x):
         mods = self._modules
+        conv, act = mods["Conv"], mods.get("Act")
+        stride = conv.stride
         if "Blur" in mods:
-            x = mods["Blur"](x)
+            if _is_pointwise_stride2(conv):
+                x, stride = mods["Blur"](x, down=2), 1       # the 1x1 stride-2 conv reads only the even blurred pixels
+            else:
+                x = mods["Blur"](x)
         if "RefPad" in mods:
             x = reflect_pad(x, mods["RefPad"].padding)
-        conv, act = mods["Conv"], mods.get("Act")
         if isinstance(act, FusedLeakyReLU) and conv.bias is None:
             # bias + leaky-ReLU applied in the conv kernel's epilogue
-            return conv2d_bias_act(x, conv.weight, act.bias, stride=conv.stride, padding=conv.padding,
+            return conv2d_bias_act(x, conv.weight, act.bias, stride=stride, padding=conv.padding,
                                    negative_slope=act.negative_slope, scale=act.scale, wscale=conv.scale)
-        x = conv(x)
+        x = conv2d(x, conv.weight, bias=conv.bias, stride=stride, padding=conv.padding, wscale=conv.scale)
         return act(x) if act is not None else x
 
 
@@ -469,9 +479,12 @@ class ResBlock(nn.Module):
         conv = mods["Conv"]
         if conv.bias is None and "Act" not in mods and "RefPad" not in mods:
             # skip branch: [Blur] -> 1x1 conv whose epilogue performs the residual merge
-            h = mods["Blur"](input) if "Blur" in mods else input
-            return conv2d_residual(h, conv.weight, out, 1.0 / _SQRT2, stride=conv.stride, padding=conv.padding,
-                                   wscale=conv.scale)
+            stride = conv.stride
+            if "Blur" in mods and _is_pointwise_stride2(conv):
+                h, stride = mods["Blur"](input, down=2), 1    # blur evaluated only where the 1x1 stride-2 conv samples it
+            else:
+                h = mods["Blur"](input) if "Blur" in mods else input
+            return conv2d_residual(h, conv.weight, out, 1.0 / _SQRT2, stride=stride, padding=conv.padding, wscale=conv.scale)
         return add_scale(out, self.skip(input), 1.0 / _SQRT2)
 
 

@@ -85,6 +85,28 @@ def test_fir_hot_path_shapes(taps, pad, c, h, exact_fp32):
     assert rel_err(g, g_ref) < TOL_FP32
 
 
+@pytest.mark.parametrize("pad,c,h", [((1, 1), 128, 32), ((1, 1), 32, 63), ((2, 2), 64, 17), ((0, 1), 8, 9)])
+def test_fir_decimating_separable(pad, c, h, exact_fp32):
+    """blur + decimate by 2 (skip branch of the ResBlocks) and its adjoint (zero-insert x2 FIR)"""
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
+    taps = [1, 3, 3, 1]
+    k = O.make_kernel(taps, torch.float64)
+    t1 = tuple(v / sum(taps) for v in taps)
+    x = rnd(5, 2, c, h, h + 2)
+    xr = x.clone().requires_grad_()
+    y_ref = O.upfirdn2d(xr, k, down=2, pad=pad)
+    w = rnd(6, *y_ref.shape)
+    g_ref, = torch.autograd.grad((y_ref * w).sum(), xr)
+    xg = cuda(x).requires_grad_()
+    y = upfirdn2d(xg, cuda(k), down=2, pad=pad, taps=(t1, t1))
+    assert y.shape == y_ref.shape and rel_err(y, y_ref) < TOL_FP32
+    g, = torch.autograd.grad((y * cuda(w)).sum(), xg)
+    assert rel_err(g, g_ref) < TOL_FP32
+    # blur-then-subsample equals subsample-of-blur: the identity the layer code relies on
+    full = O.upfirdn2d(x, k, pad=pad)
+    assert rel_err(y, full[:, :, ::2, ::2]) < TOL_FP32
+
+
 def test_fir_edge_cases(exact_fp32):
     from swapping_autoencoder_pytorch_b200.stylegan2_op import upfirdn2d
     k = cuda(O.make_kernel([1, 3, 3, 1], torch.float64))
