@@ -1043,7 +1043,7 @@ static int tc4_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
 
 static int tc4_mode() {
     static int mode = -1;
-    if (mode < 0) { const char* v = getenv("SAE_TC_PERSISTENT"); mode = (v && v[0] == '0') ? 0 : 1; }
+    if (mode < 0) { const char* v = getenv("SAE_TC_PERSISTENT"); mode = v ? atoi(v) : 1; }
     return mode;
 }
 
@@ -1074,13 +1074,20 @@ static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st)
         const int64_t pixels = (int64_t)pr.SN * pr.OH * pr.OW;
         if (pixels >= 2 * 128) {
             if (tc3_ok(pr)) {
-                if (tc4_mode()) {
+                // measured (profiles/r1_conv_bench.txt): with >= 128 output channels the one-tile-per-CTA kernel wins (fresh
+                // CTAs prefetch while their SM neighbour drains; the persistent loop serialises load -> MMA -> epilogue per
+                // CTA and the two co-resident CTAs tend to run in lock-step); the narrow 32/64-channel layers, whose
+                // main loop is ~1k cycles per tile, are faster persistent (setup cost amortised).  SAE_TC_PERSISTENT=2
+                // forces the persistent kernel everywhere, 0 disables it.
+                const int mode = tc4_mode();
+                if (pr.Ncol % 128 == 0 && mode != 2)
+                    return pr.Ncol % 256 == 0 ? tc3_launch<256>(pr, e, st) : tc3_launch<128>(pr, e, st);
+                if (mode) {
                     if (pr.Ncol % 256 == 0) return tc4_launch<256>(pr, e, st);
                     if (pr.Ncol % 128 == 0) return tc4_launch<128>(pr, e, st);
                     if (pr.Ncol % 64 == 0) return tc4_launch<64>(pr, e, st);
                     return tc4_launch<32>(pr, e, st);
                 }
-                if (pr.Ncol % 128 == 0) return pr.Ncol % 256 == 0 ? tc3_launch<256>(pr, e, st) : tc3_launch<128>(pr, e, st);
             }
             if (pr.Ncol % 256 == 0) return tc2_launch<256>(pr, e, st);
             if (pr.Ncol % 128 == 0) return tc2_launch<128>(pr, e, st);
