@@ -11,6 +11,7 @@ import os
 import torch
 
 from . import networks, util
+from .stylegan2_op import filter_reuse
 
 
 class BaseModel(torch.nn.Module):
@@ -83,7 +84,10 @@ class BaseModel(torch.nn.Module):
             raise ValueError(command)
         method = getattr(self, command)
         assert callable(method), "[%s] is not a method of %s" % (command, type(self).__name__)
-        return method(*args, **kwargs)
+        # one command = one loss evaluation on fixed parameters: derived filter tensors are shared between the
+        # several passes each network makes inside it (stylegan2_op/conv.py filter_reuse)
+        with filter_reuse():
+            return method(*args, **kwargs)
 
 
 class SwappingAutoencoderModel(BaseModel):

@@ -20,7 +20,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv2d_bias_act, conv2d_noise_bias_act, conv2d_residual,
-                           conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, modulate, reflect_pad,
+                           conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, memo, modulate, reflect_pad,
                            upfirdn2d)
 
 _SQRT2 = math.sqrt(2.0)
@@ -207,10 +207,13 @@ class ModulatedConv2d(nn.Module):
     def filter(self):
         """scale * W, demodulated per output channel: [Cout, Cin, k, k] (reference :285-292; identical for
         every sample, which is why no ``repeat(batch, ...)`` is needed)."""
-        w = self.weight[0] * self.scale
-        if self.demodulate:
-            w = w * torch.rsqrt(w.square().sum(dim=(1, 2, 3), keepdim=True) + 1e-8)
-        return w
+        def build():
+            w = self.weight[0] * self.scale
+            if self.demodulate:
+                w = w * torch.rsqrt(w.square().sum(dim=(1, 2, 3), keepdim=True) + 1e-8)
+            return w.transpose(0, 1) if self.upsample else w
+        # the filter does not depend on the style: built once per loss evaluation, shared by every call of the layer
+        return memo(self.weight, "demod", build)
 
     def modulated_input(self, input, style):
         """input * (RMS-normalised) style — reference :269-284"""
@@ -231,7 +234,7 @@ class ModulatedConv2d(nn.Module):
         input = self.modulated_input(input, style)
         w = self.filter()
         if self.upsample:
-            out = conv_transpose2d(input, w.transpose(0, 1), stride=2, padding=0)
+            out = conv_transpose2d(input, w, stride=2, padding=0)      # filter() already returns [Cin, Cout, k, k] here
             return self.blur(out)
         if self.downsample:
             return conv2d(self.blur(input), w, stride=2, padding=0)

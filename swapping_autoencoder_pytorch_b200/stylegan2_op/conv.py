@@ -10,6 +10,8 @@ so three primitives — fprop(x, w), dgrad(dy, w), wgrad(dy, x) — are closed u
 Weights enter in the reference's parameter layout ``[Cout, Cin, R, S]`` and are permuted to the kernels'
 ``[K, R, S, C]`` by a (differentiable) torch permute of the small filter tensor.
 """
+import contextlib
+
 import torch
 import torch.nn.functional as F
 from torch.autograd import Function
@@ -63,9 +65,44 @@ class _UnprepFilter(Function):
         return _PrepFilter.apply(gg, ctx.scale)[0], None
 
 
+class _FilterMemo:
+    """Per-loss-evaluation memo of derived filter tensors.  One loss command runs each network several times on the
+    same parameters (D on real / rec / mix, Dpatch on three crop sets, G on rec / mix): the scaled, demodulated, padded and
+    kernel-layout filters are functions of the parameters only, so inside ``filter_reuse()`` they are built once and the
+    same autograd node feeds every use (its gradient is the sum over the uses — exactly what separate copies give)."""
+    depth = 0
+    store = {}
+
+
+@contextlib.contextmanager
+def filter_reuse():
+    """Scope of one loss evaluation (model.SwappingAutoencoderModel.forward); nested scopes share the outermost memo."""
+    _FilterMemo.depth += 1
+    try:
+        yield
+    finally:
+        _FilterMemo.depth -= 1
+        if _FilterMemo.depth == 0:
+            _FilterMemo.store.clear()
+
+
+def memo(source, tag, build):
+    """``build()`` once per (source tensor identity and version, tag, grad mode) inside ``filter_reuse()``; outside a scope it
+    is always rebuilt.  The entry keeps ``source`` alive so its id cannot be recycled while the scope is open."""
+    if _FilterMemo.depth == 0:
+        return build()
+    key = (id(source), source._version, tag, torch.is_grad_enabled(), source.requires_grad)
+    hit = _FilterMemo.store.get(key)
+    if hit is None:
+        hit = (source, build())
+        _FilterMemo.store[key] = hit
+    return hit[1]
+
+
 def prep_filter(weight, scale=1.0):
     """returns (w_krsc, w_crsk) for the conv Functions below"""
-    return _PrepFilter.apply(weight, float(scale))
+    scale = float(scale)
+    return memo(weight, ("prep", scale), lambda: _PrepFilter.apply(weight, scale))
 
 
 class _ConvFprop(Function):
@@ -203,10 +240,10 @@ def _pad4(input, weight):
         # weight gradients run on the tensor-core kernels (the extra zero channels cost 1/4 of the 128-channel output)
         extra = (32 - cin) if cin < 32 else 4 - cin % 4
         input = F.pad(input, (0, 0, 0, 0, 0, extra))
-        weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
+        weight = memo(weight, ("pad_cin", extra), lambda w=weight: F.pad(w, (0, 0, 0, 0, 0, extra)))
     cout = weight.shape[0]
     if cout % 4 != 0:
-        weight = F.pad(weight, (0, 0, 0, 0, 0, 0, 0, 4 - cout % 4))
+        weight = memo(weight, "pad_cout", lambda w=weight: F.pad(w, (0, 0, 0, 0, 0, 0, 0, 4 - cout % 4)))
         return input, weight, cout
     return input, weight, None
 
@@ -278,7 +315,8 @@ def linear(input, weight, bias=None, wscale=1.0):
     b, cin = input.shape
     cout = weight.shape[0]
     g = make_geom(b, 1, 1, cin, cout, 1, 1, 1, 0, 0)
-    w, wt = prep_filter(weight.view(cout, cin, 1, 1), wscale)
+    wscale = float(wscale)
+    w, wt = memo(weight, ("linear", wscale), lambda: _PrepFilter.apply(weight.view(cout, cin, 1, 1), wscale))
     out = _ConvFprop.apply(input.reshape(b, cin, 1, 1), w, wt, g).reshape(b, cout)
     if bias is not None:
         out = out + bias

@@ -190,3 +190,32 @@ def test_train_steps_run_and_alternate(fp64_default):
     assert "G_L1" in g and "G_GAN_mix" in g and "L1_dist" in g
     changed2 = {k for k, v in model.state_dict().items() if not torch.equal(v, before[k])}
     assert any(k.startswith("G.") for k in changed2) and any(k.startswith("E.") for k in changed2)
+
+
+def test_filter_memo_shares_derived_filters(fp64_default):
+    """inside filter_reuse() a layer called twice builds its kernel-layout filter once, and the parameter gradient
+    equals the one of two independent evaluations"""
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import conv as C
+    layer = L.StyledConv(8, 8, 3, 16).double()
+    x1, x2, s = rnd(1, 2, 8, 8, 8), rnd(2, 2, 8, 8, 8), rnd(3, 2, 16)
+    z = rnd(4, 2, 1, 8, 8)
+
+    def loss():
+        return (layer(x1, s, noise=z) * 0.5 + layer(x2, s, noise=z)).square().sum()
+    ref = torch.autograd.grad(loss(), list(layer.parameters()))
+    calls = []
+    orig = C._PrepFilter.apply
+    C._PrepFilter.apply = staticmethod(lambda *a: (calls.append(1), orig(*a))[1])
+    try:
+        with C.filter_reuse():
+            got = torch.autograd.grad(loss(), list(layer.parameters()))
+        n_in = len(calls)
+        loss()
+        n_out = len(calls) - n_in
+    finally:
+        C._PrepFilter.apply = orig
+    assert n_out == 2 * n_in                       # outside a scope every call prepares its own filters
+    for a, b in zip(got, ref):
+        assert rel_err(a, b) < 1e-12
+    assert not C._FilterMemo.store
