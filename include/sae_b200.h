@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 9
+#define SAE_ABI_VERSION 10
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -135,6 +135,15 @@ int sae_reflect_pad(const float* x, float* out, int n, int h, int w, int c, int 
                     void* stream);
 int sae_reflect_pad_backward(const float* dy, float* dx, int n, int h, int w, int c, int pad_l, int pad_r, int pad_t,
                              int pad_b, void* stream);
+
+/* Zero-pad the channel dimension while converting to the kernels' NHWC layout: out[n, p, 0:c_out] = (x[n, 0:c_in, p], 0...)
+ * for the `pixels` positions of each image; x is addressed with element strides (stride_n, stride_c, stride_p), so the
+ * reference's NCHW image batches (stride_c = H*W, stride_p = 1) and channels-last tensors (stride_c = 1, stride_p = c_in)
+ * are both read in place.  Feeds the 3-channel inputs of FromRGB (ConvLayer(3, ch, 1), stylegan2_layers.py:716,
+ * encoder.py:38) and of the patch discriminator's first conv (patch_discriminator.py:111) to the tensor-core conv
+ * kernels, whose TMA rows are 32 channels; c_out % 4 == 0, c_in <= c_out. */
+int sae_pad_channels(const float* x, float* out, int64_t n, int64_t pixels, int c_in, int c_out,
+                     int64_t stride_n, int64_t stride_c, int64_t stride_p, int round_tf32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * conv2d — dense implicit-GEMM convolution family on NHWC fp32 activations, TF32 tensor cores,

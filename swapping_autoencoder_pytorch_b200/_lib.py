@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsae_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-SAE_ABI_VERSION = 9
+SAE_ABI_VERSION = 10
 
 c_float_p = ctypes.c_void_p   # raw device pointers travel as integers
 c_stream = ctypes.c_void_p
@@ -71,6 +71,8 @@ SIGNATURES = {
                                          ctypes.c_float, c_stream]),
     "sae_reflect_pad": (ctypes.c_int, [c_float_p, c_float_p] + [ctypes.c_int] * 8 + [c_stream]),
     "sae_reflect_pad_backward": (ctypes.c_int, [c_float_p, c_float_p] + [ctypes.c_int] * 8 + [c_stream]),
+    "sae_pad_channels": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_stream]),
     "sae_conv2d_fprop": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.POINTER(ConvGeom),
                                         ctypes.POINTER(ConvEpilogue), ctypes.c_int, c_stream]),
     "sae_conv2d_dgrad": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.POINTER(ConvGeom),

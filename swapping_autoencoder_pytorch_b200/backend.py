@@ -161,6 +161,19 @@ class CudaKernels:
                                                    int(self.round_tf32), _stream()), "sae_upsample2x_backward")
         return out
 
+    def pad_channels(self, x, c_out):
+        """x: logical [N, c_in, H, W] with any (n, c) strides and a flattenable pixel plane -> NHWC [N, H, W, c_out],
+        channels c_in.. zero (one kernel instead of F.pad + a layout copy)"""
+        _need_cuda(x)
+        n, c, h, w = x.shape
+        if h > 1 and x.stride(2) != w * x.stride(3):
+            x = x.contiguous()
+        out = torch.empty((n, h, w, c_out), device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_pad_channels(_ptr(x), _ptr(out), n, h * w, c, c_out, x.stride(0), x.stride(1), x.stride(3),
+                                            int(self.round_tf32), _stream()), "sae_pad_channels")
+        return out
+
     def reflect_pad(self, x, pads):
         """x [N,H,W,C] -> [N, H+pt+pb, W+pl+pr, C]; pads = (left, right, top, bottom)"""
         _need_cuda(x)

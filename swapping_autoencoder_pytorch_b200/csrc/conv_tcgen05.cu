@@ -66,7 +66,7 @@ struct TcParams {
     int src_c;                    // source channels
     int o_mul, o_offy, o_offx;    // output sub-grid -> full-resolution pixel (strided outputs of transposed conv)
     int FH, FW;                   // full-resolution output extent (for noise / residual addressing)
-    signed char oy[TC_MAX_TAPS], ox[TC_MAX_TAPS];
+    short oy[TC_MAX_TAPS], ox[TC_MAX_TAPS];   // source pixel = stride * output pixel + (oy, ox)
     int wk[TC_MAX_TAPS];          // K offset of the tap's filter slice inside a wmat row
     // shared-window kernel only: one (wh x ww)-pixel input window per channel block serves every tap
     int ww, wh, oy_min, ox_min;
@@ -851,7 +851,7 @@ static void tc_fill_params(const TcProblem& pr, const EpiParams& e, TcParams& p)
     p.tiles_h = (pr.OH + p.th - 1) / p.th;
     p.tiles_n = (pr.SN + p.tn - 1) / p.tn;
     p.ON = pr.SN; p.OH = pr.OH; p.OW = pr.OW; p.Ncol = pr.Ncol; p.src_c = pr.SC;
-    for (int t = 0; t < pr.ntaps; ++t) { p.oy[t] = (signed char)pr.oy[t]; p.ox[t] = (signed char)pr.ox[t]; p.wk[t] = pr.wk[t]; }
+    for (int t = 0; t < pr.ntaps; ++t) { p.oy[t] = (short)pr.oy[t]; p.ox[t] = (short)pr.ox[t]; p.wk[t] = pr.wk[t]; }
     p.o_mul = pr.o_mul; p.o_offy = pr.o_offy; p.o_offx = pr.o_offx; p.FH = pr.FH; p.FW = pr.FW;
     p.epi = e;
 }
@@ -1098,6 +1098,38 @@ static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st)
     return tc_launch<32>(pr, e, st);
 }
 
+// Sub-rectangle [r0, r1) x [c0, c1) of a problem's output grid as a problem of its own: the output placement moves
+// with it and the tap offsets absorb the shift of the origin.
+static TcProblem tc_subproblem(const TcProblem& pr, int r0, int r1, int c0, int c1) {
+    TcProblem s = pr;
+    s.OH = r1 - r0; s.OW = c1 - c0;
+    s.o_offy = pr.o_offy + pr.o_mul * r0; s.o_offx = pr.o_offx + pr.o_mul * c0;
+    for (int t = 0; t < pr.ntaps; ++t) { s.oy[t] = pr.oy[t] + r0 * pr.stride; s.ox[t] = pr.ox[t] + c0 * pr.stride; }
+    return s;
+}
+
+// The shared-window kernels tile the output in 16 x 8 pixel blocks.  The parity classes of a stride-2 data gradient are
+// (2^k + 1)-sized in the discriminators (blurred 65 / 129 / 257 maps): one extra row and column would cost a whole extra
+// row and column of mostly empty 128-pixel tiles (33 x 33 outputs -> 15 tiles instead of 8.5).  Such thin remainders are
+// split off and run as their own launches, whose tiles gather the strip across images (tn > 1) instead.
+static int tc_dispatch_split(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    static int mode = -1;
+    if (mode < 0) { const char* v = getenv("SAE_TC_SPLIT"); mode = (v && v[0] == '0') ? 0 : 1; }
+    if (!mode || !pair_enabled() || !tc3_ok(pr)) return tc_dispatch(pr, e, st);
+    const int rem_h = pr.OH % 16, rem_w = pr.OW % 8;
+    const int main_h = (rem_h >= 1 && rem_h <= 4 && pr.OH >= 32) ? pr.OH - rem_h : pr.OH;
+    const int main_w = (rem_w >= 1 && rem_w <= 2 && pr.OW >= 16) ? pr.OW - rem_w : pr.OW;
+    if (main_h == pr.OH && main_w == pr.OW) return tc_dispatch(pr, e, st);
+    int rc = tc_dispatch(tc_subproblem(pr, 0, main_h, 0, main_w), e, st);
+    if (rc) return rc;
+    if (main_w < pr.OW) {                                    // right strip, full height (takes the corner)
+        rc = tc_dispatch(tc_subproblem(pr, 0, pr.OH, main_w, pr.OW), e, st);
+        if (rc) return rc;
+    }
+    if (main_h < pr.OH) rc = tc_dispatch(tc_subproblem(pr, main_h, pr.OH, 0, main_w), e, st);
+    return rc;
+}
+
 static bool ptr_ok(const void* a, const void* b, const void* c) {
     return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
 }
@@ -1128,7 +1160,7 @@ int tc_fprop(const float* x, const float* w, float* y, const sae_conv_geom* g, c
             const int t = r * g->S + s;
             pr.oy[t] = r - g->pad_t; pr.ox[t] = s - g->pad_l; pr.wk[t] = t * g->C;
         }
-    return tc_dispatch(pr, e, st);
+    return tc_dispatch_split(pr, e, st);
 }
 
 int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g, const EpiParams& e, cudaStream_t st) {
@@ -1146,7 +1178,7 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
                 const int t = r * g->S + s;
                 pr.oy[t] = g->pad_t - r; pr.ox[t] = g->pad_l - s; pr.wk[t] = t * g->K;
             }
-        return tc_dispatch(pr, e, st);
+        return tc_dispatch_split(pr, e, st);
     }
     // stride 2 (the generator's transposed convolution and the data-gradient of the strided convs): the output
     // splits into 4 parity classes (ho, wo); class outputs x[2i+ho, 2j+wo] only see taps with r = (ho + pad_t) mod 2,
@@ -1177,7 +1209,7 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
                     ++nt;
                 }
             pr.ntaps = nt;
-            int rc = tc_dispatch(pr, e, st);
+            int rc = tc_dispatch_split(pr, e, st);
             if (rc) return rc;
         }
     return SAE_OK;

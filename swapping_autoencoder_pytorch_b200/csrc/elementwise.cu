@@ -330,6 +330,28 @@ upsample2x_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dskip,
     }
 }
 
+// out[n, p, 0:c_out] = (x[n, 0:c_in, p], 0 ...): channel zero-padding fused with the NCHW -> NHWC conversion.  One thread per
+// output float4; the input is a sliver (3 channels) next to the 32-channel output rows, so the writes set the pace.
+__global__ void __launch_bounds__(256)
+pad_channels_kernel(const float* __restrict__ x, float4* __restrict__ out, int64_t total_v, int64_t pixels, int c_in, int cv,
+                    int64_t sn, int64_t sc, int64_t sp, int round) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_v; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % cv);
+        const int64_t t = i / cv;
+        const int64_t pix = t % pixels, n = t / pixels;
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        const int c0 = v * 4;
+        if (c0 < c_in) {
+            const float* src = x + n * sn + pix * sp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < c_in) { const float f = __ldg(src + (int64_t)(c0 + j) * sc); r[j] = round ? rna_tf32(f) : f; }
+        }
+        out[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+
 // ------------------------------------------------------------------------------------ reflection padding (NHWC)
 // nn.ReflectionPad2d of the encoder (stylegan2_layers.py:104,642) in one pass over channels-last data; the backward
 // gathers, for every input pixel, the (at most 3 x 3) padded positions that mirror onto it — no atomics.
@@ -579,6 +601,19 @@ extern "C" int sae_upsample2x_backward(const float* dy, float* dskip, int n, int
     upsample2x_bwd_kernel<<<grid_for(tv, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dskip), tv, h, w, c / 4, scale, round_tf32);
     return check_launch("upsample2x_backward");
+}
+
+extern "C" int sae_pad_channels(const float* x, float* out, int64_t n, int64_t pixels, int c_in, int c_out,
+                                int64_t stride_n, int64_t stride_c, int64_t stride_p, int round_tf32, void* stream) {
+    using namespace sae;
+    if (n == 0 || pixels == 0) return SAE_OK;
+    if (!x || !out || n < 0 || pixels < 0 || c_in <= 0 || c_out < c_in || c_out % 4 != 0)
+        return fail(SAE_E_INVALID, "pad_channels: bad arguments (0 < c_in <= c_out, c_out %% 4 == 0)");
+    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(SAE_E_INVALID, "pad_channels: out must be 16-byte aligned");
+    const int64_t tv = n * pixels * (c_out / 4);
+    pad_channels_kernel<<<grid_for(tv, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<float4*>(out), tv, pixels, c_in,
+                                                                                 c_out / 4, stride_n, stride_c, stride_p, round_tf32);
+    return check_launch("pad_channels");
 }
 
 extern "C" int sae_reflect_pad(const float* x, float* out, int n, int h, int w, int c, int pad_l, int pad_r, int pad_t, int pad_b,

@@ -230,6 +230,21 @@ class _ConvResidual(Function):
         return dx, dw, None, (gs if ctx.needs_input_grad[3] else None), None, None
 
 
+class _PadChannels(Function):
+    """[N, c, H, W] (any layout) -> channels zero-padded to ``c_out``, stored NHWC: one kernel for what would be an F.pad
+    plus a layout copy of the 32-channel result.  Linear; its adjoint is a channel slice (a differentiable torch view),
+    so R1's gradient with respect to the image passes through and can be differentiated again."""
+
+    @staticmethod
+    def forward(ctx, x, c_out):
+        ctx.c_in = x.shape[1]
+        return _nchw(backend.kernels().pad_channels(x, c_out))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy[:, :ctx.c_in], None
+
+
 def _pad4(input, weight):
     """RGB tensors (3 channels) are zero-padded to 4 so rows are 16-byte aligned and the kernels keep their vector
     / TMA paths (the pad and the matching slice are differentiable torch ops on tiny tensors).  Returns
@@ -239,7 +254,7 @@ def _pad4(input, weight):
         # RGB inputs go to 32 channels: one 128-byte TMA row per pixel, so FromRGB / the first Dpatch conv and their
         # weight gradients run on the tensor-core kernels (the extra zero channels cost 1/4 of the 128-channel output)
         extra = (32 - cin) if cin < 32 else 4 - cin % 4
-        input = F.pad(input, (0, 0, 0, 0, 0, extra))
+        input = _PadChannels.apply(input, cin + extra)
         weight = memo(weight, ("pad_cin", extra), lambda w=weight: F.pad(w, (0, 0, 0, 0, 0, extra)))
     cout = weight.shape[0]
     if cout % 4 != 0:

@@ -90,6 +90,9 @@ class EmulatedKernels:
         g, = torch.autograd.grad(up, x0, _nchw(dy).detach())
         return _nhwc(g) * scale
 
+    def pad_channels(self, x, c_out):
+        return _nhwc(F.pad(x, (0, 0, 0, 0, 0, c_out - x.shape[1])))
+
     def reflect_pad(self, x, pads):
         return _nhwc(F.pad(_nchw(x), tuple(pads), mode="reflect"))
 

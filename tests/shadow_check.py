@@ -82,6 +82,9 @@ class ShadowKernels:
     def upsample2x_backward(self, dy, scale):
         return self._both("upsample2x_backward", "x%s" % (tuple(dy.shape),), (dy, scale), {})
 
+    def pad_channels(self, x, c_out):
+        return self._both("pad_channels", "x%s -> %d" % (tuple(x.shape), c_out), (x, c_out), {})
+
     def reflect_pad(self, x, pads):
         return self._both("reflect_pad", "x%s pads%s" % (tuple(x.shape), pads), (x, pads), {})
 

@@ -204,6 +204,27 @@ def test_reflect_pad(exact_fp32):
         assert rel_err(g, g_ref) < TOL_FP32
 
 
+def test_pad_channels(exact_fp32):
+    """channel zero-padding fused with the NCHW -> NHWC conversion: bit-exact copy, zero tail, slice adjoint"""
+    from swapping_autoencoder_pytorch_b200.stylegan2_op.conv import _PadChannels
+    for shape, c_out, cl in (((2, 3, 9, 7), 32, False), ((3, 3, 16, 16), 32, True), ((1, 5, 4, 6), 8, False), ((2, 3, 1, 1), 4, False)):
+        x = rnd(1, *shape).float()
+        xg = x.to(DEV)
+        if cl:
+            xg = xg.contiguous(memory_format=torch.channels_last)
+        xg.requires_grad_()
+        out = _PadChannels.apply(xg, c_out)
+        assert out.shape == (shape[0], c_out) + shape[2:] and out.permute(0, 2, 3, 1).is_contiguous()
+        assert torch.equal(out[:, :shape[1]].cpu(), x) and float(out[:, shape[1]:].abs().max()) == 0.0
+        w = torch.randn_like(out)
+        g, = torch.autograd.grad((out * w).sum(), xg)
+        assert torch.equal(g, w[:, :shape[1]])
+    # a sliced (non-flattenable) view falls back to a contiguous copy first
+    x = rnd(2, 2, 3, 8, 8).float().to(DEV)[:, :, 1:7, 2:6]
+    out = _PadChannels.apply(x, 32)
+    assert torch.equal(out[:, :3], x)
+
+
 def test_filter_prep(exact_fp32):
     kern = backend.kernels()
     for shape in ((64, 32, 3, 3), (3, 8, 1, 1), (512, 512, 3, 3), (8, 2048, 1, 1)):
@@ -243,6 +264,9 @@ CONV_CASES = [
     (1, 64, 64, 256, 256, 3, 1, 1),
     (2, 32, 32, 512, 256, 1, 1, 0),          # generator skip 1x1
     (2, 33, 33, 128, 256, 3, 2, 0),
+    (2, 65, 65, 64, 128, 3, 2, 0),           # dgrad parity classes 33 x 33 / 33 x 32: thin remainder strips split off
+    (3, 34, 34, 128, 128, 3, 1, 1),          # stride 1 with a 2-row / 2-column remainder beyond the 16 x 8 tiling
+    (2, 37, 41, 64, 64, 3, 1, 1),            # 1-column remainder only (5 rows stay ragged)
 ]
 
 
