@@ -43,16 +43,17 @@ def main():
             gb = 4.0 * (x.numel() + n * oh * oh * c) / 1e9
             print("%-46s %9.3f %9.0f" % ("%s [%d,%d,%d,%d]" % (name, n, h, h, c), ms, gb / ms * 1e3))
         b = torch.randn(c, device=dev)
+        y = torch.randn_like(x)
         ms = timeit(lambda: k.bias_act(x, b, None, 3, 0, 0.2, 1.414), flush)
         print("%-46s %9.3f %9.0f" % ("bias_act fwd [%d,%d,%d,%d]" % (n, h, h, c), ms, 8.0 * x.numel() / 1e9 / ms * 1e3))
-        ms = timeit(lambda: k.bias_act_backward(x, x, 0.2, 1.414), flush)
+        ms = timeit(lambda: k.bias_act_backward(x, y, 0.2, 1.414), flush)
         print("%-46s %9.3f %9.0f" % ("bias_act bwd [%d,%d,%d,%d]" % (n, h, h, c), ms, 12.0 * x.numel() / 1e9 / ms * 1e3))
         s = torch.randn(n, c, device=dev)
         ms = timeit(lambda: k.modulate(x, s), flush)
         print("%-46s %9.3f %9.0f" % ("modulate [%d,%d,%d,%d]" % (n, h, h, c), ms, 8.0 * x.numel() / 1e9 / ms * 1e3))
-        ms = timeit(lambda: k.modulate_backward(x, x, s), flush)
+        ms = timeit(lambda: k.modulate_backward(x, y, s), flush)
         print("%-46s %9.3f %9.0f" % ("modulate bwd [%d,%d,%d,%d]" % (n, h, h, c), ms, 12.0 * x.numel() / 1e9 / ms * 1e3))
-        ms = timeit(lambda: k.add_scale(x, x, 0.7), flush)
+        ms = timeit(lambda: k.add_scale(x, y, 0.7), flush)
         print("%-46s %9.3f %9.0f" % ("add_scale [%d,%d,%d,%d]" % (n, h, h, c), ms, 12.0 * x.numel() / 1e9 / ms * 1e3))
         if h <= 128:
             r = torch.randn(n, 2 * h, 2 * h, c, device=dev)
@@ -61,7 +62,7 @@ def main():
             ms = timeit(lambda: k.upsample2x_backward(r, 0.7), flush)
             print("%-46s %9.3f %9.0f" % ("upsample2x_bwd [%d,%d,%d,%d]" % (n, h, h, c), ms, (4.0 * x.numel() + 4.0 * r.numel()) / 1e9 / ms * 1e3))
             del r
-        del x
+        del x, y
 
 
 if __name__ == "__main__":

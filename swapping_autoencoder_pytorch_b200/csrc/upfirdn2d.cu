@@ -8,6 +8,7 @@
 // shared memory, already flipped, so the inner loop is a plain correlation.  A column-strip variant
 // keeps a rolling kh x kw register window so each input element is loaded kw (not kh*kw) times.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sae {
 
@@ -236,6 +237,95 @@ fir_sep_strip_kernel(const float* __restrict__ x, float* __restrict__ out, FirPa
     }
 }
 
+// TMA-staged separable FIR (up = down = 1, 32-channel blocks): one CTA per 16 x 16 output pixels x 32 channels.  A single
+// 4-D bulk tensor load brings the (16+KW-1) x (16+KH-1) pixel window into shared memory — out-of-range rows / columns
+// arrive as zeros, which is exactly upfirdn2d's zero padding — so the whole window is in flight with one instruction and
+// the threads only read shared memory (each input byte leaves HBM once; the halo is served by L2).  Four CTAs share an SM
+// (46 KB each), so loads of three tiles overlap the arithmetic of a fourth.
+constexpr int FT_W = 16, FT_H = 16;
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(256)
+fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ out, FirParams p, SepTaps taps, int tiles_x, int tiles_y) {
+    constexpr int WW = FT_W + KW - 1, WH = FT_H + KH - 1;
+    extern __shared__ uint8_t fir_smem[];
+    __shared__ __align__(8) uint64_t bar_storage;
+    const uint32_t base = (smem_u32(fir_smem) + 127u) & ~127u;
+    const float4* win = reinterpret_cast<const float4*>(fir_smem + (base - smem_u32(fir_smem)));
+    const uint32_t bar = smem_u32(&bar_storage);
+
+    uint32_t t = blockIdx.x;
+    const int tx = (int)(t % tiles_x); t /= tiles_x;
+    const int ty = (int)(t % tiles_y);
+    const int n = (int)(t / tiles_y);
+    const int cb = blockIdx.y;
+    const int ox0 = tx * FT_W, oy0 = ty * FT_H;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)(WW * WH * 128));
+        tma_load_4d(base, &map_x, bar, cb * 32, ox0 - p.pad_x0, oy0 - p.pad_y0, n);
+    }
+    mbar_wait(bar, 0);
+
+    const int cvec = threadIdx.x & 7, x = (threadIdx.x >> 3) & 15, r0 = (threadIdx.x >> 7) * (FT_H / 2);
+    auto hrow = [&](int wy) -> float4 {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < KW; ++b) {
+            const float4 v = win[(wy * WW + x + b) * 8 + cvec];
+            a.x = fmaf(v.x, taps.x[b], a.x); a.y = fmaf(v.y, taps.x[b], a.y);
+            a.z = fmaf(v.z, taps.x[b], a.z); a.w = fmaf(v.w, taps.x[b], a.w);
+        }
+        return a;
+    };
+    float4 w[KH];
+#pragma unroll
+    for (int a = 0; a < KH - 1; ++a) w[a] = hrow(r0 + a);
+    const int ox = ox0 + x;
+    float* dst = out + (((int64_t)n * p.out_h + oy0 + r0) * p.out_w + ox) * p.minor + cb * 32 + cvec * 4;
+#pragma unroll
+    for (int r = 0; r < FT_H / 2; ++r) {
+        w[KH - 1] = hrow(r0 + r + KH - 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < KH; ++a) {
+            acc.x = fmaf(w[a].x, taps.y[a], acc.x); acc.y = fmaf(w[a].y, taps.y[a], acc.y);
+            acc.z = fmaf(w[a].z, taps.y[a], acc.z); acc.w = fmaf(w[a].w, taps.y[a], acc.w);
+        }
+        if (p.round_tf32) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
+        if (ox < p.out_w && oy0 + r0 + r < p.out_h) *reinterpret_cast<float4*>(dst + (int64_t)r * p.out_w * p.minor) = acc;
+#pragma unroll
+        for (int a = 0; a < KH - 1; ++a) w[a] = w[a + 1];
+    }
+}
+
+template <int KH, int KW>
+static int launch_tma(const float* x, float* out, const FirParams& p, const SepTaps& taps, cudaStream_t st) {
+    constexpr int WW = FT_W + KW - 1, WH = FT_H + KH - 1;
+    CUtensorMap mx;
+    cuuint64_t dims[4] = {(cuuint64_t)p.minor, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.major};
+    cuuint64_t strides[3] = {(cuuint64_t)p.minor * 4, (cuuint64_t)p.in_w * p.minor * 4, (cuuint64_t)p.in_h * p.in_w * p.minor * 4};
+    cuuint32_t box[4] = {32, WW, WH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode_map(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    constexpr int smem = WW * WH * 128 + 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(fir_tma_kernel<KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    const int tiles_x = (p.out_w + FT_W - 1) / FT_W, tiles_y = (p.out_h + FT_H - 1) / FT_H;
+    dim3 grid((unsigned)((int64_t)tiles_x * tiles_y * p.major), (unsigned)(p.minor / 32));
+    fir_tma_kernel<KH, KW><<<grid, 256, smem, st>>>(mx, out, p, taps, tiles_x, tiles_y);
+    return SAE_OK;
+}
+
 // zero-insert x2 upsampling FIR (the adjoint of the down = 2 filter): output (y, x) only sees the taps whose
 // up-sampled position is even — 2 of 4 per axis — so it is a 2 x 2 gather from the low-resolution input
 template <int KH, int KW>
@@ -374,6 +464,14 @@ extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, 
     for (int i = 0; i < kernel_h; ++i) t.y[i] = taps_y[kernel_h - 1 - i];
     for (int i = 0; i < kernel_w; ++i) t.x[i] = taps_x[kernel_w - 1 - i];
     cudaStream_t st = (cudaStream_t)stream;
+    static int tma_mode = -1;
+    if (tma_mode < 0) { const char* v = getenv("SAE_FIR_TMA"); tma_mode = (v && v[0] == '0') ? 0 : 1; }
+    if (tma_mode && up == 1 && down == 1 && minor % 32 == 0 && (kernel_h == 3 || kernel_h == 4) && p.out_w >= 8 && p.out_h >= 8 &&
+        major * (int64_t)((p.out_w + FT_W - 1) / FT_W) * ((p.out_h + FT_H - 1) / FT_H) < ((int64_t)1 << 31)) {
+        int rc = kernel_h == 3 ? launch_tma<3, 3>(input, out, p, t, st) : launch_tma<4, 4>(input, out, p, t, st);
+        if (rc) return rc;
+        return check_launch("upfirdn2d_separable(tma)");
+    }
     switch (kernel_h) {
         case 1: launch_sep<1, 1>(input, out, p, t, st); break;
         case 2: launch_sep<2, 2>(input, out, p, t, st); break;
