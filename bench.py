@@ -230,8 +230,17 @@ def run_ours(args, rank, world, local):
     dom = 2 if roof.get(2, [0, 0, 0])[2] > 0 else 1
     fl, sec, cnt = roof[dom]
     achieved = fl / sec / 1e12 if sec > 0 else 0.0
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_note = "%s: dram read+write per launch from %s; algorithmic bytes %d" % (tj["kernel"], tj["source"],
+                                                                                         tj["algorithmic_bytes"])
+    tf32_nominal = 1125.0      # dense kind::tf32 rate = half the nominal 2250 TFLOP/s bf16 rate (B200_PROFILING.md)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_tf32_nominal": tf32_nominal, "frac_of_tf32_nominal": achieved / tf32_nominal,
                 "kernel": "conv implicit GEMM (%s)" % ("tcgen05+TMA TF32" if dom == 2 else "mma.sync TF32 generic"),
                 "launches_timed": cnt, "peak_source": peak_src + " bf16 dense sustained; kind::tf32 peaks at half of it",
                 "by_impl": {("tcgen05" if i == 2 else "generic"): {"tflops": (v[0] / v[1] / 1e12 if v[1] > 0 else 0.0),
