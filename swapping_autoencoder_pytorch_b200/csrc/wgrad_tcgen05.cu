@@ -214,6 +214,135 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Narrow-input variant (C == 32, stride 1, 3 horizontal taps): the patch discriminator's and the encoder's first
+// 32-channel layers.  With only 32 dy channels the kernel above fills a quarter of the 128 M-rows and re-reads the x
+// tile once per tap.  Here the operands swap roles:
+//   A (M = 128) = the x window of one filter row: M-atom j (32 channels) is the SAME 40-pixel window shifted by j pixel
+//                 rows — the descriptor's leading-dimension stride is one 128-byte pixel row, so atoms 0..2 ARE the three
+//                 horizontal taps (atom 3 is a fourth, unused shift) and one window load feeds all of them;
+//   B (N = Ko)  = the dy tile, 32 pixels x Ko channels;
+//   one accumulator per filter row (R x Ko TMEM columns).
+// Per 32-pixel chunk: R window loads (5 KB) + Ko/32 dy loads (4 KB) and 4 R MMAs, against 9 x-loads + 4 dy loads and 12
+// full-size MMAs before.  Rows of the accumulator are (tap s, channel c), columns are output channels: a warp's 32 lanes
+// write 32 consecutive c of dW[k, r, s, :] — coalesced 128-byte reductions.
+constexpr int WN_STAGES = 4;
+
+__device__ __forceinline__ uint64_t make_desc_mn_shift(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;          // next M-atom = next pixel row of the same window
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 2)
+wgrad_narrow_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                    float* __restrict__ dw, const WgParams p, const int tmem_cols) {
+    const int nkb = p.Ko / 32;                                  // dy sub-tiles (N = Ko <= 128)
+    const uint32_t stage_bytes = (uint32_t)(p.R * WG_WSUB + nkb * WG_SUB);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Ko >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + WN_STAGES * stage_bytes;
+    const uint32_t bar_empty = bar_full + 8 * WN_STAGES;
+    const uint32_t bar_acc = bar_empty + 8 * WN_STAGES;
+    const uint32_t tmem_slot = bar_acc + 8;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk_begin = blockIdx.x * p.chunks_per_split;
+    const int chunk_end = min(chunk_begin + p.chunks_per_split, p.chunks_total);
+    const int KB = chunk_end - chunk_begin;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < WN_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (KB > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int s = kb % WN_STAGES;
+                    const uint32_t ph = (uint32_t)(kb / WN_STAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    int ch = chunk_begin + kb;
+                    const int tq = ch % p.tiles_w; ch /= p.tiles_w;
+                    const int p0 = ch % p.tiles_h;
+                    const int n0 = ch / p.tiles_h;
+                    const int q0 = tq * 32;
+                    const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                    mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+                    for (int r = 0; r < p.R; ++r)
+                        tma_load_4d(sa + (uint32_t)r * WG_WSUB, &map_x, bar_full + 8 * s, 0, q0 - p.pad_l, p0 - p.pad_t + r, n0);
+                    for (int i = 0; i < nkb; ++i)
+                        tma_load_4d(sa + (uint32_t)(p.R * WG_WSUB + i * WG_SUB), &map_dy, bar_full + 8 * s, 32 * i, q0, p0, n0);
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int s = kb % WN_STAGES;
+                    const uint32_t ph = (uint32_t)(kb / WN_STAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                    const uint64_t db = make_desc_mn_sw128(sa + (uint32_t)(p.R * WG_WSUB));
+                    for (int r = 0; r < p.R; ++r) {
+#pragma unroll
+                        for (int k = 0; k < WG_KPIX / 8; ++k) {
+                            const uint64_t da = make_desc_mn_shift(sa + (uint32_t)r * WG_WSUB + (uint32_t)(8 * k) * 128u);
+                            umma_tf32(tmem_base + (uint32_t)(r * p.Ko), da, db + (uint64_t)(k * 64), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_acc);
+            }
+        } else {
+            const int lg = warp & 3;                 // TMEM lane group = tap s; lane = input channel c
+            mbar_wait(bar_acc, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t ld = (int64_t)p.ntaps * p.C;
+            for (int r = 0; r < p.R; ++r)
+                for (int nb = 0; nb < nkb; ++nb) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(r * p.Ko + nb * 32), v);
+                    if (lg < p.S) {
+                        float* dst = dw + (int64_t)(nb * 32) * ld + (int64_t)(r * p.S + lg) * p.C + lane;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (int64_t)i * ld), "f"(v[i]) : "memory");
+                    }
+                }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
 bool tc_wgrad_eligible(const sae_conv_geom* g) {
     if (g->K % 32 != 0 || g->C % 32 != 0) return false;
     if (g->stride != 1 && g->stride != 2) return false;
@@ -255,6 +384,47 @@ int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
     if (splits < 1) splits = 1;
     p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
     splits = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
+
+    static int narrow_mode = -1;
+    if (narrow_mode < 0) { const char* v = getenv("SAE_WGRAD_NARROW"); narrow_mode = (v && v[0] == '0') ? 0 : 1; }
+    if (narrow_mode && g->C == 32 && g->stride == 1 && g->S == 3 && g->R <= 3 && p.tw == 32 && g->K <= 128) {
+        // C == 32: x window as the A operand with pixel-shifted M-atoms (see wgrad_narrow_kernel)
+        CUtensorMap mdy, mx;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)g->K, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N};
+            cuuint64_t strides[3] = {(cuuint64_t)g->K * 4, (cuuint64_t)g->Q * g->K * 4, (cuuint64_t)g->P * g->Q * g->K * 4};
+            cuuint32_t box[4] = {32, 32, 1, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            int rc = encode_map(&mdy, dy, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+            if (rc) return rc;
+        }
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)g->C, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N};
+            cuuint64_t strides[3] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
+            cuuint32_t box[4] = {32, WG_WIN, 1, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            int rc = encode_map(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+            if (rc) return rc;
+        }
+        const int nkb = g->K / 32;
+        const size_t stage = (size_t)g->R * WG_WSUB + (size_t)nkb * WG_SUB;
+        const size_t smem_n = WN_STAGES * stage + 1024 + 256;
+        int cols = 32;
+        while (cols < g->R * g->K) cols <<= 1;
+        const int per_sm = (cols <= 256 && 2 * smem_n <= 200 * 1024) ? 2 : 1;
+        static size_t attr_bytes = 0;
+        if (smem_n > attr_bytes) {
+            SAE_CUDA_TRY(cudaFuncSetAttribute(wgrad_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n));
+            attr_bytes = smem_n;
+        }
+        int nsplit = sm_count() * per_sm;
+        if (nsplit > p.chunks_total) nsplit = p.chunks_total;
+        p.chunks_per_split = (p.chunks_total + nsplit - 1) / nsplit;
+        nsplit = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
+        p.shared_b = 0;
+        wgrad_narrow_kernel<<<(unsigned)nsplit, WG_THREADS, smem_n, st>>>(mdy, mx, dw, p, cols);
+        return check_launch("wgrad_narrow");
+    }
 
     static int win_mode = -1;
     // shared-window mode on by default (2 = plain start address: the swizzle is a function of the absolute shared-memory

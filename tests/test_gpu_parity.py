@@ -267,6 +267,9 @@ CONV_CASES = [
     (2, 65, 65, 64, 128, 3, 2, 0),           # dgrad parity classes 33 x 33 / 33 x 32: thin remainder strips split off
     (3, 34, 34, 128, 128, 3, 1, 1),          # stride 1 with a 2-row / 2-column remainder beyond the 16 x 8 tiling
     (2, 37, 41, 64, 64, 3, 1, 1),            # 1-column remainder only (5 rows stay ragged)
+    (2, 40, 40, 32, 32, 3, 1, 1),            # Dpatch / encoder 32 -> 32: narrow-input weight-gradient kernel
+    (1, 33, 70, 32, 64, 3, 1, 0),            # same kernel, pad 0, ragged 32-pixel chunks, 64 output channels
+    (2, 32, 32, 32, 128, 3, 1, 1),           # same kernel at its widest (3 x 128 TMEM columns)
 ]
 
 
