@@ -33,7 +33,7 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _need_cuda(*ts):
+def _need_cuda(*ts, strided=False):
     for t in ts:
         if t is None:
             continue
@@ -42,7 +42,7 @@ def _need_cuda(*ts):
                                 % t.device.type)
         if t.dtype != torch.float32:
             raise _lib.SaeError("sae_b200 kernels are fp32-only (got %s)" % t.dtype)
-        if not t.is_contiguous():
+        if not strided and not t.is_contiguous():
             raise _lib.SaeError("sae_b200 kernels need contiguous NHWC storage")
 
 
@@ -164,7 +164,7 @@ class CudaKernels:
     def pad_channels(self, x, c_out):
         """x: logical [N, c_in, H, W] with any (n, c) strides and a flattenable pixel plane -> NHWC [N, H, W, c_out],
         channels c_in.. zero (one kernel instead of F.pad + a layout copy)"""
-        _need_cuda(x)
+        _need_cuda(x, strided=True)          # the kernel addresses x through (n, c, pixel) element strides
         n, c, h, w = x.shape
         if h > 1 and x.stride(2) != w * x.stride(3):
             x = x.contiguous()

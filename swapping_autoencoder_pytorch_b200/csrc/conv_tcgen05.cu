@@ -813,6 +813,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
 // ------------------------------------------------------------------------------------------------ host side
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle) {
+    if (g_encode == nullptr && !tc_available()) return fail(SAE_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available on this device / driver");
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

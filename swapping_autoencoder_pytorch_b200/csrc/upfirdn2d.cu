@@ -466,7 +466,8 @@ extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, 
     cudaStream_t st = (cudaStream_t)stream;
     static int tma_mode = -1;
     if (tma_mode < 0) { const char* v = getenv("SAE_FIR_TMA"); tma_mode = (v && v[0] == '0') ? 0 : 1; }
-    if (tma_mode && up == 1 && down == 1 && minor % 32 == 0 && (kernel_h == 3 || kernel_h == 4) && p.out_w >= 8 && p.out_h >= 8 &&
+    // tc_available() also resolves the driver's cuTensorMapEncodeTiled entry point (a FIR can be the first call into the library)
+    if (tma_mode && tc_available() && up == 1 && down == 1 && minor % 32 == 0 && (kernel_h == 3 || kernel_h == 4) && p.out_w >= 8 && p.out_h >= 8 &&
         major * (int64_t)((p.out_w + FT_W - 1) / FT_W) * ((p.out_h + FT_H - 1) / FT_H) < ((int64_t)1 << 31)) {
         int rc = kernel_h == 3 ? launch_tma<3, 3>(input, out, p, t, st) : launch_tma<4, 4>(input, out, p, t, st);
         if (rc) return rc;

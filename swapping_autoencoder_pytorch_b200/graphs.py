@@ -1,0 +1,122 @@
+"""CUDA-graph execution of the training half-steps (extension; SURVEY.md Appendix B "launch-count pressure").
+
+One half-step of the reference optimizer (``optimizers/swapping_autoencoder_optimizer.py:67-111``) is ~1200 kernel
+launches issued from Python through autograd; on a B200 the kernels of a 256x256 batch finish about as fast as the
+host can issue them, and at the small per-GPU batches of the reference's own multi-GPU configurations the host is the
+bottleneck outright.  The step has static shapes and no host-visible control flow between "images in" and "losses
+out" — the lazy-R1 decision is a host counter, the D / G toggle too — so each body (D, G, R1) is captured ONCE into a
+``torch.cuda.CUDAGraph`` (forward, backward, and at world size 1 the fused Adam step) and replayed afterwards with the
+images copied into a static input buffer.
+
+* The first ``warmup`` calls of every body run eagerly (lazy initialisation inside the kernels library, Adam state).
+* All graphs share one memory pool: bodies never run concurrently.
+* Random draws (NoiseInjection, crop windows) use torch's graph-safe Philox generator: every replay draws fresh numbers.
+* Data parallel (world > 1): the graph holds forward + backward only; the gradient all-reduce (``parallel.py``) and the
+  Adam step run eagerly after the replay on the graph's static gradient buffers — no NCCL call is captured.
+* A body that fails to capture falls back to eager execution for the rest of the run (``self.disabled`` holds why).
+"""
+import warnings
+
+import torch
+
+from . import _lib
+
+
+class HalfStepGraphs:
+    def __init__(self, trainer, warmup=2):
+        self.trainer = trainer
+        self.warmup = warmup
+        self.calls = {}
+        self.captured = {}        # kind -> (graph, static_input, static_outputs, launches)
+        self.pool = None
+        self.disabled = None
+        self.replayed_launches = 0     # kernels of this library executed through graph replays (bench bookkeeping)
+        self.enabled = True            # bench switches to eager for its per-launch instrumentation pass
+
+    # ------------------------------------------------------------------
+    def _wrapper(self):
+        return self.trainer.model
+
+    def _world(self):
+        return getattr(self._wrapper(), "world", 1)
+
+    def _optimizer(self, kind):
+        return self.trainer.optimizer_G if kind == "G" else self.trainer.optimizer_D
+
+    def _finish_eagerly(self, kind):
+        """world > 1: average the static gradient buffers across ranks, then step"""
+        self._wrapper().reduce_gradients_now()
+        self._optimizer(kind).step()
+
+    def run(self, kind, body, images):
+        if self.disabled is not None or not self.enabled:
+            return body(images)
+        n = self.calls.get(kind, 0)
+        self.calls[kind] = n + 1
+        key = (kind, tuple(images.shape))
+        hit = self.captured.get(key)
+        if hit is None:
+            if n < self.warmup:
+                return body(images)
+            try:
+                hit = self._capture(key, body, images)
+            except Exception as e:      # noqa: BLE001 — any capture failure means "run eagerly", never "stop training"
+                self.disabled = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])
+                warnings.warn("CUDA-graph capture of the %s half-step failed (%s); continuing eagerly" % (kind, self.disabled))
+                torch.cuda.synchronize()
+                return body(images)
+        graph, static_in, outputs, launches, grads = hit
+        # host-side state the eager body would have left behind: which group is trainable, and which gradient buffers
+        # the parameters point at (every graph owns its own static set)
+        self._select_group(kind)
+        for p, g in grads:
+            p.grad = g
+        static_in.copy_(images, non_blocking=True)
+        graph.replay()
+        self.replayed_launches += launches
+        if self._world() > 1:
+            self._finish_eagerly(kind)
+        return dict(outputs)
+
+    def _select_group(self, kind):
+        t = self.trainer
+        t.set_requires_grad(t.Dparams, kind != "G")
+        t.set_requires_grad(t.Gparams, kind == "G")
+
+    def _params(self, kind):
+        return self.trainer.Gparams if kind == "G" else self.trainer.Dparams
+
+    def warm_up(self, images):
+        """Run every body often enough that all three graphs exist (benchmarks call this before their timed region;
+        it performs real optimizer steps, including extra R1 steps)."""
+        t = self.trainer
+        for _ in range(self.warmup + 1):
+            for kind, body in (("D", t._discriminator_body), ("R1", t._r1_body), ("G", t._generator_body)):
+                self.run(kind, body, images)
+        torch.cuda.synchronize()
+
+    def _capture(self, key, body, images):
+        kind = key[0]
+        world = self._world()
+        wrapper = self._wrapper()
+        static_in = torch.empty_like(images)
+        static_in.copy_(images)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        n0 = _lib.launch_count()
+        if world > 1:
+            wrapper.suspend_reduce = True
+        try:
+            with torch.cuda.graph(graph, pool=self.pool):
+                outputs = body(static_in, step=(world == 1))
+        finally:
+            if world > 1:
+                wrapper.suspend_reduce = False
+        launches = _lib.launch_count() - n0
+        outputs = {k: v for k, v in outputs.items() if torch.is_tensor(v)}
+        grads = [(p, p.grad) for p in self._params(kind) if p.grad is not None]
+        hit = (graph, static_in, outputs, launches, grads)
+        self.captured[key] = hit
+        return hit

@@ -7,10 +7,18 @@ import torch.nn.functional as F
 
 from .. import util
 from ..stylegan2_layers import ConvLayer, EqualLinear, StyledConv, ToRGB
-from ..stylegan2_op import add_scale, upsample2x_add_scale
+from ..stylegan2_op import add_scale, conv2d_residual, upsample2x_add_scale
 from .base_network import BaseNetwork
 
 _INV_SQRT2 = 1.0 / math.sqrt(2.0)
+
+
+def _is_plain_pointwise(layer):
+    """ConvLayer that is nothing but a bias-free 1x1 stride-1 convolution (the generator's head skip connections)"""
+    mods = layer._modules
+    conv = mods["Conv"]
+    return (set(mods) == {"Conv"} and conv.bias is None and conv.weight.shape[2] == 1 and conv.weight.shape[3] == 1
+            and conv.stride == 1 and conv.padding == 0)
 
 
 class UpsamplingBlock(torch.nn.Module):
@@ -36,8 +44,16 @@ class ResolutionPreservingResnetBlock(torch.nn.Module):
         self.skip = ConvLayer(inch, outch, 1, activate=False, bias=False) if inch != outch else torch.nn.Identity()
 
     def forward(self, x, style):
+        skip = self.skip
+        if isinstance(skip, ConvLayer) and _is_plain_pointwise(skip):
+            # (skip(x) + res) / sqrt(2) with the factor folded into conv2's activation gain and the skip filter's scale:
+            # the merge is a plain add in the 1x1 conv's epilogue and its backward needs no scaling pass
+            res = self.conv2(self.conv1(x, style), style, out_scale=_INV_SQRT2)
+            conv = skip._modules["Conv"]
+            return conv2d_residual(x, conv.weight, res, 1.0, stride=conv.stride, padding=conv.padding,
+                                   wscale=conv.scale * _INV_SQRT2)
         res = self.conv2(self.conv1(x, style), style)
-        return add_scale(self.skip(x), res, _INV_SQRT2)
+        return add_scale(skip(x), res, _INV_SQRT2)
 
 
 class UpsamplingResnetBlock(torch.nn.Module):
@@ -52,6 +68,12 @@ class UpsamplingResnetBlock(torch.nn.Module):
         self.skip = ConvLayer(inch, outch, 1, activate=True, bias=True) if inch != outch else torch.nn.Identity()
 
     def forward(self, x, style):
+        if isinstance(self.skip, ConvLayer) and self.outch % 4 == 0:
+            # both branches arrive pre-scaled by 1/sqrt(2) (folded into their activation gains; bilinear interpolation
+            # is linear), so "bilinear x2 + merge" is one kernel with unit scale and the residual branch's gradient is
+            # the block's output gradient itself
+            res = self.conv2(self.conv1(x, style), style, out_scale=_INV_SQRT2)
+            return upsample2x_add_scale(self.skip(x, out_scale=_INV_SQRT2), res, 1.0)
         res = self.conv2(self.conv1(x, style), style)
         skip = self.skip(x)
         if skip.shape[1] % 4 == 0:

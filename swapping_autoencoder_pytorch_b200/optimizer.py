@@ -27,7 +27,13 @@ class SwappingAutoencoderOptimizer:
         self.discriminator_iter_counter = 0
         self.Gparams = model.get_parameters_for_mode("generator")
         self.Dparams = model.get_parameters_for_mode("discriminator")
-        fused = dict(fused=True) if (self.Gparams and self.Gparams[0].is_cuda) else {}
+        on_cuda = bool(self.Gparams and self.Gparams[0].is_cuda)
+        # CUDA-graph execution of the half-steps (extension, ``opt.cuda_graphs``): see graphs.py
+        self.graphs = None
+        if on_cuda and getattr(opt, "cuda_graphs", False):
+            from .graphs import HalfStepGraphs
+            self.graphs = HalfStepGraphs(self)
+        fused = dict(fused=True, capturable=self.graphs is not None) if on_cuda else {}
         self.optimizer_G = torch.optim.Adam(self.Gparams, lr=opt.lr, betas=(opt.beta1, opt.beta2), **fused)
         # lazy regularisation correction of lr and betas (StyleGAN2 appendix B; reference :38-42)
         c = opt.R1_once_every / (1 + opt.R1_once_every)
@@ -56,37 +62,64 @@ class SwappingAutoencoderOptimizer:
             losses = self.train_generator_one_step(images)
         return util.to_numpy(losses)
 
-    def train_generator_one_step(self, images):
+    # ------------------------------------------------------------------ half-step bodies (eager or captured)
+    def _generator_body(self, images, step=True):
         self.set_requires_grad(self.Dparams, False)
         self.set_requires_grad(self.Gparams, True)
         self.optimizer_G.zero_grad()
         g_losses, g_metrics = self.model(images, None, None, command="compute_generator_losses")
         sum(v.mean() for v in g_losses.values()).backward()
-        self.optimizer_G.step()
+        if step:
+            self.optimizer_G.step()
         g_losses.update(g_metrics)
         return g_losses
+
+    def _discriminator_body(self, images, step=True):
+        self.set_requires_grad(self.Dparams, True)
+        self.set_requires_grad(self.Gparams, False)
+        self.optimizer_D.zero_grad()
+        d_losses, d_metrics, sp, gl = self.model(images, command="compute_discriminator_losses")
+        sum(v.mean() for v in d_losses.values()).backward()
+        # extra outputs travel under "_"-prefixed keys so that eager and captured execution share one flat dict
+        d_losses["_sp"], d_losses["_gl"] = sp.detach(), gl.detach()
+        d_losses.update({"_metric:" + k: v for k, v in d_metrics.items()})
+        if step:
+            self.optimizer_D.step()
+        return d_losses
+
+    def _r1_body(self, images, step=True):
+        self.set_requires_grad(self.Dparams, True)
+        self.set_requires_grad(self.Gparams, False)
+        self.optimizer_D.zero_grad()
+        r1_losses = self.model(images, command="compute_R1_loss")
+        (sum(v.mean() for v in r1_losses.values()) * self.opt.R1_once_every).backward()
+        if step:
+            self.optimizer_D.step()
+        return r1_losses
+
+    def _run(self, kind, images):
+        """Eager execution of one body, or — with ``opt.cuda_graphs`` on a CUDA device — replay of its CUDA graph."""
+        body = {"G": self._generator_body, "D": self._discriminator_body, "R1": self._r1_body}[kind]
+        if self.graphs is not None and images.is_cuda:
+            return self.graphs.run(kind, body, images)
+        return body(images)
+
+    def train_generator_one_step(self, images):
+        return self._run("G", images)
 
     def train_discriminator_one_step(self, images):
         opt = self.opt
         if opt.lambda_GAN == 0.0 and opt.lambda_PatchGAN == 0.0:
             return {}
-        self.set_requires_grad(self.Dparams, True)
-        self.set_requires_grad(self.Gparams, False)
         self.discriminator_iter_counter += 1
-        self.optimizer_D.zero_grad()
-        d_losses, d_metrics, sp, gl = self.model(images, command="compute_discriminator_losses")
-        self.previous_sp, self.previous_gl = sp.detach(), gl.detach()
-        sum(v.mean() for v in d_losses.values()).backward()
-        self.optimizer_D.step()
+        d_losses = dict(self._run("D", images))
+        self.previous_sp, self.previous_gl = d_losses.pop("_sp"), d_losses.pop("_gl")
+        d_metrics = {k[len("_metric:"):]: d_losses.pop(k) for k in list(d_losses) if k.startswith("_metric:")}
 
         needs_r1 = (opt.lambda_R1 > 0.0 or opt.lambda_patch_R1 > 0.0) and \
             self.discriminator_iter_counter % opt.R1_once_every == 0
         if needs_r1:
-            self.optimizer_D.zero_grad()
-            r1_losses = self.model(images, command="compute_R1_loss")
-            d_losses.update(r1_losses)
-            (sum(v.mean() for v in r1_losses.values()) * opt.R1_once_every).backward()
-            self.optimizer_D.step()
+            d_losses.update(self._run("R1", images))
 
         d_losses["D_total"] = sum(v.mean() for v in d_losses.values())
         d_losses.update(d_metrics)

@@ -27,6 +27,8 @@ def default_options(**overrides):
         max_num_tiles=8, patch_random_transformation=False,
         # optimisation
         lr=0.002, beta1=0.0, beta2=0.99, R1_once_every=16,
+        # extension (not a reference option): replay each half-step as a CUDA graph (graphs.py)
+        cuda_graphs=False,
     )
     for k, v in overrides.items():
         setattr(opt, k, v)

@@ -97,6 +97,7 @@ class MultiGPUModelWrapper:
         self.parallelized_model = model          # attribute kept for callers of the reference wrapper
         self.device = next(model.parameters()).device
         self._pending = False
+        self.suspend_reduce = False           # set while a half-step is being captured into a CUDA graph (graphs.py)
         self._bucket = GradientBucket(self.device)
         model(command="per_gpu_initialize")
         if self.world > 1:
@@ -108,6 +109,8 @@ class MultiGPUModelWrapper:
 
     # the hook fires once per parameter per backward; only the first one queues the callback
     def _on_grad(self, param):
+        if self.suspend_reduce:
+            return
         if not self._pending:
             self._pending = True
             torch.autograd.Variable._execution_engine.queue_callback(self._reduce_gradients)
@@ -117,6 +120,11 @@ class MultiGPUModelWrapper:
         grads = [p.grad for p in self.singlegpu_model.parameters()
                  if p.requires_grad and p.grad is not None]
         self._bucket.all_reduce_mean(grads, self.world)
+
+    def reduce_gradients_now(self):
+        """explicit form of the end-of-backward callback (used after a CUDA-graph replay, where autograd does not run)"""
+        if self.world > 1:
+            self._reduce_gradients()
 
     def get_parameters_for_mode(self, mode):
         return self.singlegpu_model.get_parameters_for_mode(mode)

@@ -19,6 +19,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from .stylegan2_op.blocks import FirSpec, ResBlockSpec, fused_blocks_enabled, resblock
 from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv2d_bias_act, conv2d_noise_bias_act, conv2d_residual,
                            conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, memo, modulate, reflect_pad,
                            upfirdn2d)
@@ -300,29 +301,31 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward(self, input, style, noise=None):
+    def forward(self, input, style, noise=None, out_scale=1.0):
+        """``out_scale`` (extension): extra factor on the activated output, folded into the activation gain (the
+        generator's residual blocks pass 1/sqrt(2), see networks/generator.py)."""
         conv, act = self.conv, self.activate
+        gain = act.scale * out_scale
         if not (conv.upsample or conv.downsample):
             # plain 3x3: noise + bias + activation ride in the conv kernel's epilogue
             x = conv.modulated_input(input, style)
             w = conv.filter()
             if not self.use_noise:
-                return conv2d_bias_act(x, w, act.bias, padding=conv.padding, negative_slope=act.negative_slope,
-                                       scale=act.scale)
+                return conv2d_bias_act(x, w, act.bias, padding=conv.padding, negative_slope=act.negative_slope, scale=gain)
             shape = torch.Size((x.shape[0], conv.out_channel, x.shape[2], x.shape[3]))
             z = self.noise.resolve_noise(_ShapeOnly(shape, x), noise)
             if z.shape[0] == x.shape[0] and z.shape[1] == 1 and z.shape[2:] == x.shape[2:]:
                 return conv2d_noise_bias_act(x, w, z, self.noise.weight, act.bias, padding=conv.padding,
-                                             negative_slope=act.negative_slope, scale=act.scale)
+                                             negative_slope=act.negative_slope, scale=gain)
             out = conv2d(x, w, padding=conv.padding)
-            return act(out + self.noise.weight * z)        # broadcast noise: unfused
+            return fused_leaky_relu(out + self.noise.weight * z, act.bias, act.negative_slope, gain)   # broadcast noise: unfused
         out = conv(input, style)
         if not self.use_noise:
-            return act(out)
+            return fused_leaky_relu(out, act.bias, act.negative_slope, gain)
         z = self.noise.resolve_noise(out, noise)
         if z.shape[0] != out.shape[0] or z.shape[1] != 1:
-            return act(out + self.noise.weight * z)        # broadcast noise: unfused
-        return fused_noise_bias_leaky_relu(out, z, self.noise.weight, act.bias, act.negative_slope, act.scale)
+            return fused_leaky_relu(out + self.noise.weight * z, act.bias, act.negative_slope, gain)   # broadcast noise: unfused
+        return fused_noise_bias_leaky_relu(out, z, self.noise.weight, act.bias, act.negative_slope, gain)
 
 
 class ToRGB(nn.Module):
@@ -445,7 +448,9 @@ class ConvLayer(nn.Sequential):
             layers.append(("Act", FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2)))
         super().__init__(OrderedDict(layers))
 
-    def forward(self, x):
+    def forward(self, x, out_scale=1.0):
+        """``out_scale`` (extension): extra factor on the activated output, folded into the activation gain — the
+        residual blocks pass 1/sqrt(2) so that their merge needs no scaling pass in either direction."""
         mods = self._modules
         conv, act = mods["Conv"], mods.get("Act")
         stride = conv.stride
@@ -459,9 +464,10 @@ class ConvLayer(nn.Sequential):
         if isinstance(act, FusedLeakyReLU) and conv.bias is None:
             # bias + leaky-ReLU applied in the conv kernel's epilogue
             return conv2d_bias_act(x, conv.weight, act.bias, stride=stride, padding=conv.padding,
-                                   negative_slope=act.negative_slope, scale=act.scale, wscale=conv.scale)
+                                   negative_slope=act.negative_slope, scale=act.scale * out_scale, wscale=conv.scale)
         x = conv2d(x, conv.weight, bias=conv.bias, stride=stride, padding=conv.padding, wscale=conv.scale)
-        return act(x) if act is not None else x
+        x = act(x) if act is not None else x
+        return x if out_scale == 1.0 else x * out_scale
 
 
 class ResBlock(nn.Module):
@@ -476,18 +482,55 @@ class ResBlock(nn.Module):
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=downsample, blur_kernel=blur_kernel,
                               activate=False, bias=False)
 
+    def _fused_spec(self):
+        """ResBlockSpec when the block has the discriminators' standard shape (3x3 + act, blur + 3x3 stride 2 + act,
+        blur + 1x1 stride 2 skip, zero padding) — then the whole block is ONE autograd node (stylegan2_op/blocks.py);
+        None otherwise (reflection padding, no downsampling, exotic kernels)."""
+        spec = self.__dict__.get("_spec", False)
+        if spec is not False:
+            return spec
+        spec = None
+        c1, c2, sk = self.conv1._modules, self.conv2._modules, self.skip._modules
+
+        def plain_act(m):
+            return isinstance(m.get("Act"), FusedLeakyReLU) and m["Conv"].bias is None and "RefPad" not in m
+
+        if (plain_act(c1) and plain_act(c2) and "Blur" not in c1 and "Blur" in c2 and "Blur" in sk and "Act" not in sk
+                and "RefPad" not in sk and sk["Conv"].bias is None and _is_pointwise_stride2(sk["Conv"])
+                and not c2["Blur"].reflection and not sk["Blur"].reflection
+                and tuple(c1["Conv"].weight.shape[2:]) == (3, 3) and c1["Conv"].stride == 1 and c1["Conv"].padding == 1
+                and tuple(c2["Conv"].weight.shape[2:]) == (3, 3) and c2["Conv"].stride == 2 and c2["Conv"].padding == 0
+                and c1["Act"].negative_slope == c2["Act"].negative_slope):
+            b2, bs = c2["Blur"], sk["Blur"]
+            spec = ResBlockSpec(c1["Conv"].scale, c2["Conv"].scale, sk["Conv"].scale / _SQRT2, c1["Act"].negative_slope,
+                                c1["Act"].scale, c2["Act"].scale / _SQRT2,
+                                FirSpec(b2.kernel, b2.pad, b2.taps, 1), FirSpec(bs.kernel, bs.pad, bs.taps, 2))
+        self.__dict__["_spec"] = spec
+        return spec
+
     def forward(self, input):
-        out = self.conv2(self.conv1(input))
+        spec = self._fused_spec() if (input.shape[1] % 4 == 0 and fused_blocks_enabled()) else None
+        if spec is not None:
+            # buffers may have moved (module.to(device)) since the spec was built
+            spec.blur2.kernel, spec.blur_s.kernel = self.conv2._modules["Blur"].kernel, self.skip._modules["Blur"].kernel
+            c1, c2, sk = self.conv1._modules, self.conv2._modules, self.skip._modules
+            return resblock(input, c1["Conv"].weight, c1["Act"].bias, c2["Conv"].weight, c2["Act"].bias,
+                            sk["Conv"].weight, spec)
         mods = self.skip._modules
         conv = mods["Conv"]
         if conv.bias is None and "Act" not in mods and "RefPad" not in mods:
-            # skip branch: [Blur] -> 1x1 conv whose epilogue performs the residual merge
+            # skip branch: [Blur] -> 1x1 conv whose epilogue performs the residual merge.  The 1/sqrt(2) of the merge is
+            # folded into conv2's activation gain and into the skip filter's scale, so the merge is a plain add: its
+            # backward hands dy to both branches untouched (no scaling pass over the block output or its gradient).
+            out = self.conv2(self.conv1(input), out_scale=1.0 / _SQRT2)
             stride = conv.stride
             if "Blur" in mods and _is_pointwise_stride2(conv):
                 h, stride = mods["Blur"](input, down=2), 1    # blur evaluated only where the 1x1 stride-2 conv samples it
             else:
                 h = mods["Blur"](input) if "Blur" in mods else input
-            return conv2d_residual(h, conv.weight, out, 1.0 / _SQRT2, stride=stride, padding=conv.padding, wscale=conv.scale)
+            return conv2d_residual(h, conv.weight, out, 1.0, stride=stride, padding=conv.padding,
+                                   wscale=conv.scale / _SQRT2)
+        out = self.conv2(self.conv1(input))
         return add_scale(out, self.skip(input), 1.0 / _SQRT2)
 
 

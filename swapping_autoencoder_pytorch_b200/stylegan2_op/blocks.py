@@ -1,0 +1,157 @@
+"""Block-level autograd Functions: one node per residual block instead of one per operator.
+
+Why: autograd sums the gradients of a tensor that feeds two branches with a separate ``add`` pass.  In the
+discriminators' ResBlock (reference models/networks/stylegan2_layers.py:672-693) the block input feeds ``conv1`` and the
+blurred ``skip`` branch, so every backward pays a read-read-write pass over the largest activation of the block
+(1.07 GB at 128 channels x 256 x 256 x 32 images).  A hand-ordered block backward lets the last data-gradient kernel add
+the other branch's gradient in its epilogue (``residual`` of the conv kernels) — the sum never exists as a pass.
+
+Second order (R1, reference swapping_autoencoder_model.py:138-185): when the backward itself is being recorded
+(``create_graph=True``), the Function re-evaluates the block with the per-operator differentiable Functions of
+conv.py / fused_act.py / upfirdn2d.py and differentiates THAT, so the double-backward graph is exactly the unfused one
+(one extra block forward, only in the lazy-R1 step).
+"""
+import os
+
+import torch
+from torch.autograd import Function
+
+from .. import backend
+from ..backend import make_geom
+from . import conv as C
+from .upfirdn2d import _flip_taps, upfirdn2d
+
+
+_enabled = [os.environ.get("SAE_FUSED_BLOCKS", "1") != "0"]
+
+
+def fused_blocks_enabled():
+    return _enabled[0]
+
+
+def set_fused_blocks(flag):
+    """switch between block-level and per-operator autograd nodes (tests compare the two); returns the previous value"""
+    prev, _enabled[0] = _enabled[0], bool(flag)
+    return prev
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+class FirSpec:
+    """a Blur module's parameters as plain host data + the derived adjoint padding (upfirdn2d.py UpFirDn2d.forward)"""
+
+    def __init__(self, kernel, pad, taps, down):
+        self.kernel, self.pad, self.taps, self.down = kernel, (int(pad[0]), int(pad[1])), taps, int(down)
+
+    def out_extent(self, n):
+        return (n + self.pad[0] + self.pad[1] - self.kernel.shape[0]) // self.down + 1
+
+    def forward(self, k, x):
+        p0, p1 = self.pad
+        return k.upfirdn2d(x, self.kernel, 1, 1, self.down, self.down, p0, p1, p0, p1, taps=self.taps)
+
+    def adjoint(self, k, g, in_h, in_w):
+        """gradient w.r.t. the FIR input of extent (in_h, in_w): flipped taps, up <-> down, gradient padding"""
+        p0, p1 = self.pad
+        kh, kw = self.kernel.shape
+        d = self.down
+        out_h, out_w = g.shape[1], g.shape[2]
+        gx0, gx1 = kw - p0 - 1, in_w - out_w * d + p0
+        gy0, gy1 = kh - p0 - 1, in_h - out_h * d + p0
+        out = k.upfirdn2d(g, torch.flip(self.kernel, [0, 1]), d, d, 1, 1, gx0, gx1, gy0, gy1, taps=_flip_taps(self.taps))
+        assert out.shape[1] == in_h and out.shape[2] == in_w, (tuple(out.shape), in_h, in_w)
+        return out
+
+
+class ResBlockSpec:
+    """host-side constants of one ResBlock (scales, activation constants, the two FIRs)"""
+
+    def __init__(self, s1, s2, ss, slope, gain1, gain2, blur2, blur_s):
+        self.s1, self.s2, self.ss, self.slope, self.gain1, self.gain2 = s1, s2, ss, slope, gain1, gain2
+        self.blur2, self.blur_s = blur2, blur_s
+
+
+def resblock_unfused(x, w1, b1, w2, b2, ws, spec):
+    """The block as a composition of the per-operator differentiable Functions (first and second order)."""
+    o1 = C.conv2d_bias_act(x, w1, b1, stride=1, padding=1, negative_slope=spec.slope, scale=spec.gain1, wscale=spec.s1)
+    bl = upfirdn2d(o1, spec.blur2.kernel, pad=spec.blur2.pad, taps=spec.blur2.taps)
+    o2 = C.conv2d_bias_act(bl, w2, b2, stride=2, padding=0, negative_slope=spec.slope, scale=spec.gain2, wscale=spec.s2)
+    h = upfirdn2d(x, spec.blur_s.kernel, down=2, pad=spec.blur_s.pad, taps=spec.blur_s.taps)
+    return C.conv2d_residual(h, ws, o2, 1.0, stride=1, padding=0, wscale=spec.ss)
+
+
+class _ResBlockFused(Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, ws, spec):
+        k = backend.kernels()
+        n, c, hh, ww = x.shape
+        co = w2.shape[0]
+        w1k, w1t = C.prep_filter(w1, spec.s1)
+        w2k, w2t = C.prep_filter(w2, spec.s2)
+        wsk, wst = C.prep_filter(ws, spec.ss)
+        xh = _nhwc(x)
+        g1 = make_geom(n, hh, ww, c, c, 3, 3, 1, 1, 1)
+        o1 = k.conv_fprop(xh, w1k, g1, prepared=True, bias=b1.contiguous(), act=3, alpha=spec.slope, gain=spec.gain1)
+        bl = spec.blur2.forward(k, o1)
+        g2 = make_geom(n, bl.shape[1], bl.shape[2], c, co, 3, 3, 2, 0, 0)
+        o2 = k.conv_fprop(bl, w2k, g2, prepared=True, bias=b2.contiguous(), act=3, alpha=spec.slope, gain=spec.gain2)
+        h = spec.blur_s.forward(k, xh)
+        gs = make_geom(n, h.shape[1], h.shape[2], c, co, 1, 1, 1, 0, 0)
+        assert (gs.P, gs.Q) == (g2.P, g2.Q), ("ResBlock branches disagree", gs.key(), g2.key())
+        y = k.conv_fprop(h, wsk, gs, prepared=True, residual=o2, res_scale=1.0)
+        ctx.spec, ctx.geoms = spec, (g1, g2, gs)
+        ctx.save_for_backward(x, w1, b1, w2, b2, ws, o1, bl, o2, h, w1k, w1t, w2k, w2t, wsk, wst)
+        return _nchw(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, b1, w2, b2, ws, o1, bl, o2, h, w1k, w1t, w2k, w2t, wsk, wst = ctx.saved_tensors
+        spec = ctx.spec
+        need = ctx.needs_input_grad
+        if torch.is_grad_enabled():
+            # the backward is being recorded (R1): differentiate the per-operator composition instead
+            ins = [t for t, nd in zip((x, w1, b1, w2, b2, ws), need) if nd]
+            with torch.enable_grad():
+                y = resblock_unfused(x, w1, b1, w2, b2, ws, spec)
+                got = iter(torch.autograd.grad(y, ins, dy, create_graph=True, allow_unused=True))
+            return tuple(next(got) if nd else None for nd in need[:6]) + (None,)
+        k = backend.kernels()
+        g1, g2, gs = ctx.geoms
+        dyh = _nhwc(dy)
+        need_x, need_w = need[0], (need[1] or need[3] or need[5])
+        gi2, gb2, _ = k.bias_act_backward(dyh, o2, spec.slope, spec.gain2, want_bias=need[4])
+        # skip branch: 1x1 conv <- decimating blur
+        dws = k.conv_wgrad(dyh, h, gs) if need[5] else None
+        dxs = None
+        if need_x:
+            dh = k.conv_dgrad(dyh, wsk, gs, w_crsk=wst)
+            dxs = spec.blur_s.adjoint(k, dh, g1.H, g1.W)
+        # main branch: conv2 (stride 2) <- blur <- conv1
+        dw2 = k.conv_wgrad(gi2, bl, g2) if need[3] else None
+        dx = gi1 = gb1 = dw1 = None
+        if need_x or need[1] or need[2]:
+            dbl = k.conv_dgrad(gi2, w2k, g2, w_crsk=w2t)
+            do1 = spec.blur2.adjoint(k, dbl, g1.H, g1.W)
+            gi1, gb1, _ = k.bias_act_backward(do1, o1, spec.slope, spec.gain1, want_bias=need[2])
+            if need[1]:
+                dw1 = k.conv_wgrad(gi1, _nhwc(x), g1)
+            if need_x:
+                # the other branch's gradient is added in this kernel's epilogue: no separate accumulation pass
+                dx = _nchw(k.conv_dgrad(gi1, w1k, g1, w_crsk=w1t, residual=dxs, res_scale=1.0))
+        unprep = k.filter_unprep
+        return (dx,
+                unprep(dw1, spec.s1) if dw1 is not None else None, gb1 if need[2] else None,
+                unprep(dw2, spec.s2) if dw2 is not None else None, gb2 if need[4] else None,
+                unprep(dws, spec.ss) if dws is not None else None, None)
+
+
+def resblock(x, w1, b1, w2, b2, ws, spec):
+    """conv1 (3x3) -> blur -> conv2 (3x3, stride 2), plus blur-decimate -> 1x1 skip, merged as (out + skip) / sqrt(2)
+    with the factor pre-folded into ``spec.gain2`` / ``spec.ss`` (reference stylegan2_layers.py:672-693)."""
+    return _ResBlockFused.apply(x, w1, b1, w2, b2, ws, spec)

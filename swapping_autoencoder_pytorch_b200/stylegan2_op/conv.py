@@ -224,7 +224,7 @@ class _ConvResidual(Function):
     @staticmethod
     def backward(ctx, dy):
         x, w, wt = ctx.saved_tensors
-        gs = _AddScale.apply(dy, None, ctx.scale)
+        gs = dy if ctx.scale == 1.0 else _AddScale.apply(dy, None, ctx.scale)
         dx = _ConvDgrad.apply(gs, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
         dw = _ConvWgrad.apply(gs, x, ctx.g) if ctx.needs_input_grad[1] else None
         return dx, dw, None, (gs if ctx.needs_input_grad[3] else None), None, None
@@ -430,7 +430,10 @@ class _Upsample2xAddScale(Function):
         k = backend.kernels()
         g = _nhwc(dy)
         d_skip = _nchw(k.upsample2x_backward(g, ctx.scale)) if ctx.needs_input_grad[0] else None
-        d_res = _nchw(k.add_scale(g, None, ctx.scale)) if ctx.needs_input_grad[1] else None
+        if ctx.scale == 1.0:
+            d_res = dy if ctx.needs_input_grad[1] else None
+        else:
+            d_res = _nchw(k.add_scale(g, None, ctx.scale)) if ctx.needs_input_grad[1] else None
         return d_skip, d_res, None
 
 

@@ -582,3 +582,32 @@ def test_shadow_tiny_model_training_steps():
         trainer.train_one_step({"real_A": real}, 0)
     sh = _run_shadow(go)
     assert len(sh.log) > 300
+
+
+def test_resblock_block_level_node_on_gpu():
+    """stylegan2_op/blocks.py on the device: same kernels in a hand-ordered backward whose last data-gradient launch adds
+    the skip branch's gradient in its epilogue.  Against the per-operator path the only difference is that fused add
+    (rounded once instead of twice), so the two must agree far inside the TF32 tolerance — at a discriminator shape
+    (tcgen05 kernels) and at a small one (generic kernels)."""
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import blocks
+    for cin, cout, n, hw in ((128, 256, 2, 64), (32, 64, 3, 33), (8, 12, 2, 12)):
+        torch.manual_seed(cin)
+        m = L.ResBlock(cin, cout).to(DEV)
+        with torch.no_grad():
+            m.conv1.Act.bias.normal_(0, 0.1)
+            m.conv2.Act.bias.normal_(0, 0.1)
+        params = list(m.parameters())
+        x0 = torch.randn(n, cin, hw, hw, device=DEV)
+        w = torch.randn(n, cout, hw // 2, hw // 2, device=DEV)
+        res = {}
+        for fused in (True, False):
+            prev = blocks.set_fused_blocks(fused)
+            try:
+                x = x0.clone().requires_grad_()
+                y = m(x)
+                res[fused] = [y] + list(torch.autograd.grad((y * w).sum(), [x] + params))
+            finally:
+                blocks.set_fused_blocks(prev)
+        for i, (a, b) in enumerate(zip(res[True], res[False])):
+            assert a.shape == b.shape and rel_err(a, b) < 2e-4, (cin, i, rel_err(a, b))

@@ -219,3 +219,40 @@ def test_filter_memo_shares_derived_filters(fp64_default):
     for a, b in zip(got, ref):
         assert rel_err(a, b) < 1e-12
     assert not C._FilterMemo.store
+
+
+def test_resblock_block_level_node_matches_per_operator_nodes():
+    """stylegan2_op/blocks.py: the one-node ResBlock (hand-ordered backward, gradient accumulation folded into the last
+    data-gradient kernel) against the per-operator composition — outputs, every first-order gradient, and the R1-style
+    second-order gradient (which the block node obtains by re-evaluating the composition)."""
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import blocks
+    m = _load(L.ResBlock(8, 12), {"conv1.Conv.weight": rnd(1, 8, 8, 3, 3), "conv1.Act.bias": rnd(2, 8) * 0.1,
+                                  "conv2.Conv.weight": rnd(3, 12, 8, 3, 3), "conv2.Act.bias": rnd(4, 12) * 0.1,
+                                  "skip.Conv.weight": rnd(5, 12, 8, 1, 1)})
+    assert m._fused_spec() is not None
+    params = [m.conv1.Conv.weight, m.conv1.Act.bias, m.conv2.Conv.weight, m.conv2.Act.bias, m.skip.Conv.weight]
+    results = {}
+    for fused in (True, False):
+        prev = blocks.set_fused_blocks(fused)
+        try:
+            x = rnd(6, 2, 8, 12, 10).requires_grad_()
+            y = m(x)
+            w = rnd(7, *y.shape)
+            first = torch.autograd.grad((y * w).sum(), [x] + params)
+            gx, = torch.autograd.grad((m(x) * w).sum(), x, create_graph=True)
+            second = torch.autograd.grad(gx.pow(2).sum(), params[:1] + params[2:3] + params[4:])
+            # frozen parameters (generator half-step): only the data gradient is requested
+            for p in params:
+                p.requires_grad_(False)
+            gx_only, = torch.autograd.grad((m(x) * w).sum(), x)
+            for p in params:
+                p.requires_grad_(True)
+            results[fused] = [y] + list(first) + list(second) + [gx_only]
+        finally:
+            blocks.set_fused_blocks(prev)
+    for a, b in zip(results[True], results[False]):
+        assert rel_err(a, b) < 1e-12
+    # a block the fused node does not cover (reflection padding) keeps using the per-operator path
+    assert L.ResBlock(8, 12, [1, 2, 1], reflection_pad=True)._fused_spec() is None
+    assert L.ResBlock(8, 12, downsample=False)._fused_spec() is None
