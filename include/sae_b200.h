@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 10
+#define SAE_ABI_VERSION 11
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -93,6 +93,19 @@ int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_i
                           int64_t size_x, int size_b, float alpha, float scale,
                           const float* noise, int64_t noise_div, float* grad_noise_weight,
                           int round_tf32, void* stream);
+
+/* sae_upfirdn2d_separable (up = down = 1) followed by sae_bias_act_backward, in ONE pass:
+ *   grad_in = FIR(grad) * (act_out > 0 ? 1 : alpha) * scale,   grad_bias[c] += sum over pixels of grad_in
+ * — the adjoint of the Blur that follows a ConvLayer's FusedLeakyReLU inside ResBlock (stylegan2_layers.py:672-693):
+ * reference upfirdn2d.py:24-60 (UpFirDn2dBackward) + fused_act.py:23-41 (FusedLeakyReLUFunctionBackward) back to back;
+ * the blurred gradient never travels through HBM.  grad: [major, in_h, in_w, minor]; act_out / grad_in:
+ * [major, out_h, out_w, minor] with out = in + pad0 + pad1 - k + 1.  taps are HOST arrays, unflipped, 3 or 4 of them.
+ * grad_bias (may be NULL) is accumulated into.  Returns SAE_E_UNSUPPORTED outside the TMA-tiled configuration
+ * (minor % 32 == 0, outputs >= 8 x 8): issue the two separate calls then. */
+int sae_fir_act_backward(const float* grad, const float* taps_y, const float* taps_x, const float* act_out,
+                         float* grad_in, float* grad_bias, int64_t major, int in_h, int in_w, int minor,
+                         int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                         float alpha, float scale, int round_tf32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * modulate — x_s[n,h,w,c] = x[n,h,w,c] * s[n,c]: the "input * style" step of

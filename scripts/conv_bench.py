@@ -22,6 +22,10 @@ SHAPES = [
     ("D skip 128->256 @255 1x1 s2", 255, 128, 256, 1, 2, 0, 1.0),
     ("G skip 512->256 @64 1x1", 64, 512, 256, 1, 1, 0, 1.0),
     ("G convT 256->128 @128 (as dgrad of s2)", 257, 128, 256, 3, 2, 0, 1.0),
+    ("FromRGB 32->128 @256 1x1", 256, 32, 128, 1, 1, 0, 1.0),
+    ("D skip 128->256 @128 1x1 (decimated)", 128, 128, 256, 1, 1, 0, 1.0),
+    ("D skip 256->512 @64 1x1 (decimated)", 64, 256, 512, 1, 1, 0, 1.0),
+    ("Dpatch skip 32->64 @64 1x1 (decimated)", 64, 32, 64, 1, 1, 0, 8.0),
     ("Dpatch 32->32 @128 s1", 128, 32, 32, 3, 1, 1, 8.0),
     ("Dpatch 64->64 @64 s1", 64, 64, 64, 3, 1, 1, 8.0),
     ("E 32->32 @258 s1 p0", 258, 32, 32, 3, 1, 0, 1.0),
@@ -40,7 +44,7 @@ def main():
     k.conv_impl = args.impl
     dev = torch.device("cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    print("%-42s %-6s %5s %9s %9s" % ("shape", "dir", "impl", "ms", "TFLOP/s"))
+    print("%-42s %-6s %5s %9s %9s %8s" % ("shape", "dir", "impl", "ms", "TFLOP/s", "GB/s"))
     for name, h, c, kk, r, stride, pad, mult in SHAPES:
         if args.only and args.only not in name:
             continue
@@ -50,6 +54,7 @@ def main():
         w = torch.randn(kk, r, r, c, device=dev) / (c * r * r) ** 0.5
         dy = torch.randn(n, g.P, g.Q, kk, device=dev)
         flops = 2.0 * n * g.P * g.Q * kk * r * r * c
+        nbytes = 4.0 * (x.numel() + dy.numel() + w.numel())
         for d in args.dirs.split(","):
             fn = {"fprop": lambda: k.conv_fprop(x, w, g), "dgrad": lambda: k.conv_dgrad(dy, w, g),
                   "wgrad": lambda: k.conv_wgrad(dy, x, g)}[d]
@@ -66,7 +71,7 @@ def main():
                 ts.append(e0.elapsed_time(e1))
             ms = sorted(ts)[len(ts) // 2]
             impl = k.conv_impl_for(g, {"fprop": 0, "dgrad": 1, "wgrad": 2}[d]) if args.impl == 0 else args.impl
-            print("%-42s %-6s %5d %9.3f %9.1f" % (name, d, impl, ms, flops / ms / 1e9), flush=True)
+            print("%-42s %-6s %5d %9.3f %9.1f %8.0f" % (name, d, impl, ms, flops / ms / 1e9, nbytes / ms / 1e6), flush=True)
         del x, w, dy
 
 

@@ -8,6 +8,7 @@ autograd logic can be grad-checked without a GPU; the product never does that â€
 the shared library is missing or a tensor lives on the CPU.
 """
 import ctypes
+import os
 
 import torch
 
@@ -57,6 +58,7 @@ class CudaKernels:
         # as fp32): the tensor cores ignore the low 13 mantissa bits of their operands, so rounding in the producer
         # makes that truncation exact and unbiased.  Set False for bit-exact fp32 results from the pointwise kernels.
         self.round_tf32 = True
+        self.fused_fir_act = os.environ.get("SAE_FUSED_FIR_ACT", "1") != "0"
 
     # ------------------------------------------------------------------ FIR
     def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, taps=None):
@@ -109,6 +111,30 @@ class CudaKernels:
                                                  alpha, scale, _ptr(noise), c, _ptr(gnw), int(self.round_tf32), _stream()),
                   "sae_bias_act_backward")
         return gi, gb, gnw
+
+    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True):
+        """(FIR(grad) masked by the activation saved in ``act_out``, bias gradient) in one pass, or None when the shape is
+        outside the fused kernel's configuration (the caller then runs upfirdn2d + bias_act_backward).
+        grad [N,h,w,C]; act_out [N,oh,ow,C]; taps = (taps_y, taps_x) host factors; pad = (x0, x1, y0, y1)."""
+        _need_cuda(grad, act_out)
+        n, h, w, c = grad.shape
+        kh, kw = len(taps[0]), len(taps[1])
+        px0, px1, py0, py1 = pad
+        oh, ow = h + py0 + py1 - kh + 1, w + px0 + px1 - kw + 1
+        if (c % 32 != 0 or kh != kw or kh not in (3, 4) or oh < 8 or ow < 8 or n == 0 or grad.data_ptr() % 16 != 0
+                or tuple(act_out.shape) != (n, oh, ow, c) or not self.fused_fir_act):
+            return None
+        gi = torch.empty_like(act_out)
+        gb = torch.zeros(c, device=grad.device, dtype=grad.dtype) if want_bias else None
+        ty = (ctypes.c_float * kh)(*taps[0])
+        tx = (ctypes.c_float * kw)(*taps[1])
+        with torch.cuda.device(grad.device):
+            rc = self.lib.sae_fir_act_backward(_ptr(grad), ty, tx, _ptr(act_out), _ptr(gi), _ptr(gb), n, h, w, c, kh, kw,
+                                               px0, px1, py0, py1, alpha, scale, int(self.round_tf32), _stream())
+        if rc == -3:            # SAE_E_UNSUPPORTED: e.g. no TMA on this device
+            return None
+        check(rc, "sae_fir_act_backward")
+        return gi, gb
 
     # ------------------------------------------------------------- modulate
     def modulate(self, x, s):

@@ -1081,7 +1081,13 @@ static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st)
                 // main loop is ~1k cycles per tile, are faster persistent (setup cost amortised).  SAE_TC_PERSISTENT=2
                 // forces the persistent kernel everywhere, 0 disables it.
                 const int mode = tc4_mode();
-                if (pr.Ncol % 128 == 0 && mode != 2)
+                // short main loops (1x1 convs, the 1- and 2-tap parity classes of a stride-2 data gradient): per-tile setup
+                // dominates just as it does for the narrow layers -> persistent kernel when the K loop has at most
+                // SAE_TC_PERSIST_KB 32-channel blocks
+                static int persist_kb = -1;
+                if (persist_kb < 0) { const char* v = getenv("SAE_TC_PERSIST_KB"); persist_kb = v ? atoi(v) : 0; }
+                const bool short_loop = pr.ntaps * (pr.SC / TC_BK) <= persist_kb;
+                if (pr.Ncol % 128 == 0 && mode != 2 && !(mode && short_loop))
                     return pr.Ncol % 256 == 0 ? tc3_launch<256>(pr, e, st) : tc3_launch<128>(pr, e, st);
                 if (mode) {
                     if (pr.Ncol % 256 == 0) return tc4_launch<256>(pr, e, st);

@@ -244,21 +244,38 @@ fir_sep_strip_kernel(const float* __restrict__ x, float* __restrict__ out, FirPa
 // (46 KB each), so loads of three tiles overlap the arithmetic of a fourth.
 constexpr int FT_W = 16, FT_H = 16;
 
-template <int KH, int KW>
+// MASK variant (sae_fir_act_backward): the FIR result is the gradient arriving at a fused bias + leaky-ReLU, so the store
+// applies that activation's backward — times (act_out > 0 ? 1 : alpha) * scale — and the per-channel sums of the masked
+// gradient (the bias gradient) are reduced CTA-wide in shared memory and added to grad_bias with 32 atomics per CTA.
+struct FirMask {
+    const float* act_out;     // saved activation output, same shape as the FIR output
+    float* grad_bias;         // [minor], accumulated; may be null
+    float alpha, scale;
+};
+
+template <int KH, int KW, bool MASK>
 __global__ void __launch_bounds__(256)
-fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ out, FirParams p, SepTaps taps, int tiles_x, int tiles_y) {
+fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ out, FirParams p, SepTaps taps, int tiles_x, int tiles_y,
+               int ncb, FirMask mk) {
     constexpr int WW = FT_W + KW - 1, WH = FT_H + KH - 1;
     extern __shared__ uint8_t fir_smem[];
     __shared__ __align__(8) uint64_t bar_storage;
+    __shared__ float bias_part[32];
+    if (MASK && threadIdx.x < 32) bias_part[threadIdx.x] = 0.f;
     const uint32_t base = (smem_u32(fir_smem) + 127u) & ~127u;
     const float4* win = reinterpret_cast<const float4*>(fir_smem + (base - smem_u32(fir_smem)));
     const uint32_t bar = smem_u32(&bar_storage);
 
+    // 1-D grid, channel block fastest: CTAs that run together cover whole pixel rows (ncb x 128 contiguous bytes per pixel)
+    // instead of the same 128-byte slice of far-apart pixels
+    // (ncb < 0 selects the old order, channel block slowest: kept for A/B measurements, SAE_FIR_ORDER=0)
     uint32_t t = blockIdx.x;
+    int cb;
+    if (ncb > 0) { cb = (int)(t % (uint32_t)ncb); t /= (uint32_t)ncb; }
+    else { const uint32_t per = (uint32_t)(tiles_x * tiles_y) * (uint32_t)p.major; cb = (int)(t / per); t %= per; }
     const int tx = (int)(t % tiles_x); t /= tiles_x;
     const int ty = (int)(t % tiles_y);
     const int n = (int)(t / tiles_y);
-    const int cb = blockIdx.y;
     const int ox0 = tx * FT_W, oy0 = ty * FT_H;
 
     if (threadIdx.x == 0) {
@@ -287,7 +304,9 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ ou
 #pragma unroll
     for (int a = 0; a < KH - 1; ++a) w[a] = hrow(r0 + a);
     const int ox = ox0 + x;
-    float* dst = out + (((int64_t)n * p.out_h + oy0 + r0) * p.out_w + ox) * p.minor + cb * 32 + cvec * 4;
+    const int64_t off0 = (((int64_t)n * p.out_h + oy0 + r0) * p.out_w + ox) * p.minor + cb * 32 + cvec * 4;
+    float* dst = out + off0;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < FT_H / 2; ++r) {
         w[KH - 1] = hrow(r0 + r + KH - 1);
@@ -297,15 +316,39 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ ou
             acc.x = fmaf(w[a].x, taps.y[a], acc.x); acc.y = fmaf(w[a].y, taps.y[a], acc.y);
             acc.z = fmaf(w[a].z, taps.y[a], acc.z); acc.w = fmaf(w[a].w, taps.y[a], acc.w);
         }
+        const bool inside = ox < p.out_w && oy0 + r0 + r < p.out_h;
+        if (MASK) {
+            if (inside) {
+                const float4 o = ldg_stream(reinterpret_cast<const float4*>(mk.act_out + off0 + (int64_t)r * p.out_w * p.minor));
+                acc.x *= (o.x > 0.f ? mk.scale : mk.alpha * mk.scale); acc.y *= (o.y > 0.f ? mk.scale : mk.alpha * mk.scale);
+                acc.z *= (o.z > 0.f ? mk.scale : mk.alpha * mk.scale); acc.w *= (o.w > 0.f ? mk.scale : mk.alpha * mk.scale);
+                bsum.x += acc.x; bsum.y += acc.y; bsum.z += acc.z; bsum.w += acc.w;
+            }
+        }
         if (p.round_tf32) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
-        if (ox < p.out_w && oy0 + r0 + r < p.out_h) *reinterpret_cast<float4*>(dst + (int64_t)r * p.out_w * p.minor) = acc;
+        if (inside) *reinterpret_cast<float4*>(dst + (int64_t)r * p.out_w * p.minor) = acc;
 #pragma unroll
         for (int a = 0; a < KH - 1; ++a) w[a] = w[a + 1];
     }
+    if (MASK && mk.grad_bias != nullptr) {
+        // the 32 threads that share cvec sit in the lanes {cvec, cvec + 8, cvec + 16, cvec + 24} of every warp: fold those
+        // four with shuffles, then one shared-memory atomic per warp and channel, then 32 global atomics per CTA
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+            bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, o); bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, o);
+            bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, o); bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, o);
+        }
+        if ((threadIdx.x & 31) < 8) {
+            atomicAdd(&bias_part[cvec * 4 + 0], bsum.x); atomicAdd(&bias_part[cvec * 4 + 1], bsum.y);
+            atomicAdd(&bias_part[cvec * 4 + 2], bsum.z); atomicAdd(&bias_part[cvec * 4 + 3], bsum.w);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) atomicAdd(mk.grad_bias + cb * 32 + threadIdx.x, bias_part[threadIdx.x]);
+    }
 }
 
-template <int KH, int KW>
-static int launch_tma(const float* x, float* out, const FirParams& p, const SepTaps& taps, cudaStream_t st) {
+template <int KH, int KW, bool MASK = false>
+static int launch_tma(const float* x, float* out, const FirParams& p, const SepTaps& taps, cudaStream_t st, FirMask mk = FirMask()) {
     constexpr int WW = FT_W + KW - 1, WH = FT_H + KH - 1;
     CUtensorMap mx;
     cuuint64_t dims[4] = {(cuuint64_t)p.minor, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.major};
@@ -317,12 +360,15 @@ static int launch_tma(const float* x, float* out, const FirParams& p, const SepT
     constexpr int smem = WW * WH * 128 + 128;
     static bool attr_done = false;
     if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(fir_tma_kernel<KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SAE_CUDA_TRY(cudaFuncSetAttribute(fir_tma_kernel<KH, KW, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
     const int tiles_x = (p.out_w + FT_W - 1) / FT_W, tiles_y = (p.out_h + FT_H - 1) / FT_H;
-    dim3 grid((unsigned)((int64_t)tiles_x * tiles_y * p.major), (unsigned)(p.minor / 32));
-    fir_tma_kernel<KH, KW><<<grid, 256, smem, st>>>(mx, out, p, taps, tiles_x, tiles_y);
+    const int ncb = p.minor / 32;
+    dim3 grid((unsigned)((int64_t)tiles_x * tiles_y * p.major * ncb));
+    static int order = -1;
+    if (order < 0) { const char* v = getenv("SAE_FIR_ORDER"); order = (v && v[0] == '0') ? 0 : 1; }
+    fir_tma_kernel<KH, KW, MASK><<<grid, 256, smem, st>>>(mx, out, p, taps, tiles_x, tiles_y, order ? ncb : -ncb, mk);
     return SAE_OK;
 }
 
@@ -468,7 +514,7 @@ extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, 
     if (tma_mode < 0) { const char* v = getenv("SAE_FIR_TMA"); tma_mode = (v && v[0] == '0') ? 0 : 1; }
     // tc_available() also resolves the driver's cuTensorMapEncodeTiled entry point (a FIR can be the first call into the library)
     if (tma_mode && tc_available() && up == 1 && down == 1 && minor % 32 == 0 && (kernel_h == 3 || kernel_h == 4) && p.out_w >= 8 && p.out_h >= 8 &&
-        major * (int64_t)((p.out_w + FT_W - 1) / FT_W) * ((p.out_h + FT_H - 1) / FT_H) < ((int64_t)1 << 31)) {
+        major * (int64_t)((p.out_w + FT_W - 1) / FT_W) * ((p.out_h + FT_H - 1) / FT_H) * (minor / 32) < ((int64_t)1 << 31)) {
         int rc = kernel_h == 3 ? launch_tma<3, 3>(input, out, p, t, st) : launch_tma<4, 4>(input, out, p, t, st);
         if (rc) return rc;
         return check_launch("upfirdn2d_separable(tma)");
@@ -480,4 +526,42 @@ extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, 
         default: launch_sep<4, 4>(input, out, p, t, st); break;
     }
     return check_launch("upfirdn2d_separable");
+}
+
+// FIR (up = down = 1, separable 3 or 4 taps) whose result is the gradient arriving at a fused bias + leaky-ReLU:
+//   grad_in = FIR(grad) * (act_out > 0 ? 1 : alpha) * scale,   grad_bias[c] += sum over pixels of grad_in
+// i.e. sae_upfirdn2d_separable followed by sae_bias_act_backward in ONE pass (the blur adjoint in front of a
+// discriminator block's first activation, stylegan2_layers.py:672-693): the blurred gradient is never written to HBM.
+// Only the TMA-tiled configuration is implemented (minor % 32 == 0, output >= 8 x 8); anything else returns
+// SAE_E_UNSUPPORTED and the caller issues the two separate calls.
+extern "C" int sae_fir_act_backward(const float* grad, const float* taps_y, const float* taps_x, const float* act_out,
+                                    float* grad_in, float* grad_bias, int64_t major, int in_h, int in_w, int minor,
+                                    int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                                    float alpha, float scale, int round_tf32, void* stream) {
+    using namespace sae;
+    if (major == 0) return SAE_OK;
+    if (!grad || !taps_y || !taps_x || !act_out || !grad_in) return fail(SAE_E_INVALID, "fir_act_backward: null pointer");
+    if ((kernel_h != 3 && kernel_h != 4) || kernel_w != kernel_h) return fail(SAE_E_UNSUPPORTED, "fir_act_backward: taps must be 3 or 4, square");
+    if (minor % 32 != 0 || ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(grad_in) | reinterpret_cast<uintptr_t>(act_out)) & 15) != 0)
+        return fail(SAE_E_UNSUPPORTED, "fir_act_backward: needs minor %% 32 == 0 and 16-byte aligned pointers");
+    FirParams p;
+    p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
+    p.up_x = p.up_y = 1; p.down_x = p.down_y = 1; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.round_tf32 = round_tf32;
+    const int full_h = in_h + pad_y0 + pad_y1 - kernel_h, full_w = in_w + pad_x0 + pad_x1 - kernel_w;
+    if (full_h < 0 || full_w < 0) return fail(SAE_E_INVALID, "fir_act_backward: kernel larger than padded input");
+    p.out_h = full_h + 1;
+    p.out_w = full_w + 1;
+    if (!tc_available() || p.out_w < 8 || p.out_h < 8 ||
+        major * (int64_t)((p.out_w + FT_W - 1) / FT_W) * ((p.out_h + FT_H - 1) / FT_H) * (minor / 32) >= ((int64_t)1 << 31))
+        return fail(SAE_E_UNSUPPORTED, "fir_act_backward: shape outside the TMA-tiled configuration");
+    SepTaps t;
+    for (int i = 0; i < 8; ++i) { t.y[i] = 0.f; t.x[i] = 0.f; }
+    for (int i = 0; i < kernel_h; ++i) t.y[i] = taps_y[kernel_h - 1 - i];
+    for (int i = 0; i < kernel_w; ++i) t.x[i] = taps_x[kernel_w - 1 - i];
+    FirMask mk;
+    mk.act_out = act_out; mk.grad_bias = grad_bias; mk.alpha = alpha; mk.scale = scale;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = kernel_h == 3 ? launch_tma<3, 3, true>(grad, grad_in, p, t, st, mk) : launch_tma<4, 4, true>(grad, grad_in, p, t, st, mk);
+    if (rc) return rc;
+    return check_launch("fir_act_backward");
 }

@@ -15,6 +15,7 @@ images copied into a static input buffer.
   Adam step run eagerly after the replay on the graph's static gradient buffers — no NCCL call is captured.
 * A body that fails to capture falls back to eager execution for the rest of the run (``self.disabled`` holds why).
 """
+import traceback
 import warnings
 
 import torch
@@ -29,7 +30,9 @@ class HalfStepGraphs:
         self.calls = {}
         self.captured = {}        # kind -> (graph, static_input, static_outputs, launches)
         self.pool = None
+        self.stream = None             # side stream shared by the eager warm-up calls and every capture (see _side)
         self.disabled = None
+        self.last_traceback = None
         self.replayed_launches = 0     # kernels of this library executed through graph replays (bench bookkeeping)
         self.enabled = True            # bench switches to eager for its per-launch instrumentation pass
 
@@ -48,6 +51,36 @@ class HalfStepGraphs:
         self._wrapper().reduce_gradients_now()
         self._optimizer(kind).step()
 
+    def _side(self, fn):
+        """Run ``fn`` on the capture stream.  The warm-up calls must run where the capture will: autograd remembers
+        the stream a parameter's gradient-accumulation node was created on, and a capture that has to synchronise
+        with the (non-capturing) default stream for such a node is invalid."""
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = fn()
+        cur.wait_stream(self.stream)
+        return out
+
+    def _give_up(self, kind, err):
+        self.disabled = "%s: %s" % (type(err).__name__, (str(err).splitlines() or ["?"])[0][:200])
+        self.last_traceback = traceback.format_exc()
+        warnings.warn("CUDA-graph capture of the %s half-step failed (%s); continuing eagerly\n%s"
+                      % (kind, self.disabled, self.last_traceback))
+        torch.cuda.synchronize()
+        try:
+            # a capture that died half-way can leave torch's CUDA generator in "capturing" state; one empty, successful
+            # capture cycle resets it so that eager random draws work again
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                torch.zeros(1, device="cuda")
+            del g
+        except Exception:      # noqa: BLE001
+            pass
+        torch.cuda.synchronize()
+
     def run(self, kind, body, images):
         if self.disabled is not None or not self.enabled:
             return body(images)
@@ -57,13 +90,11 @@ class HalfStepGraphs:
         hit = self.captured.get(key)
         if hit is None:
             if n < self.warmup:
-                return body(images)
+                return self._side(lambda: body(images))
             try:
                 hit = self._capture(key, body, images)
             except Exception as e:      # noqa: BLE001 — any capture failure means "run eagerly", never "stop training"
-                self.disabled = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])
-                warnings.warn("CUDA-graph capture of the %s half-step failed (%s); continuing eagerly" % (kind, self.disabled))
-                torch.cuda.synchronize()
+                self._give_up(kind, e)
                 return body(images)
         graph, static_in, outputs, launches, grads = hit
         # host-side state the eager body would have left behind: which group is trainable, and which gradient buffers
@@ -71,7 +102,8 @@ class HalfStepGraphs:
         self._select_group(kind)
         for p, g in grads:
             p.grad = g
-        static_in.copy_(images, non_blocking=True)
+        with torch.no_grad():            # the R1 body marks its input as requiring grad
+            static_in.copy_(images, non_blocking=True)
         graph.replay()
         self.replayed_launches += launches
         if self._world() > 1:
@@ -99,17 +131,22 @@ class HalfStepGraphs:
         kind = key[0]
         world = self._world()
         wrapper = self._wrapper()
-        static_in = torch.empty_like(images)
-        static_in.copy_(images)
+        static_in = torch.empty_like(images).requires_grad_(False)
+        with torch.no_grad():
+            static_in.copy_(images)
+        for p in self._params(kind):
+            p.grad = None                    # gradients of the eager calls: the capture allocates its own static set
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
         n0 = _lib.launch_count()
         if world > 1:
             wrapper.suspend_reduce = True
         try:
-            with torch.cuda.graph(graph, pool=self.pool):
+            with torch.cuda.graph(graph, pool=self.pool, stream=self.stream):
                 outputs = body(static_in, step=(world == 1))
         finally:
             if world > 1:

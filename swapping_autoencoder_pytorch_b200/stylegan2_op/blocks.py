@@ -56,17 +56,32 @@ class FirSpec:
         p0, p1 = self.pad
         return k.upfirdn2d(x, self.kernel, 1, 1, self.down, self.down, p0, p1, p0, p1, taps=self.taps)
 
-    def adjoint(self, k, g, in_h, in_w):
-        """gradient w.r.t. the FIR input of extent (in_h, in_w): flipped taps, up <-> down, gradient padding"""
-        p0, p1 = self.pad
+    def _adjoint_pad(self, g, in_h, in_w):
+        p0 = self.pad[0]
         kh, kw = self.kernel.shape
         d = self.down
         out_h, out_w = g.shape[1], g.shape[2]
-        gx0, gx1 = kw - p0 - 1, in_w - out_w * d + p0
-        gy0, gy1 = kh - p0 - 1, in_h - out_h * d + p0
-        out = k.upfirdn2d(g, torch.flip(self.kernel, [0, 1]), d, d, 1, 1, gx0, gx1, gy0, gy1, taps=_flip_taps(self.taps))
+        return kw - p0 - 1, in_w - out_w * d + p0, kh - p0 - 1, in_h - out_h * d + p0
+
+    def adjoint(self, k, g, in_h, in_w):
+        """gradient w.r.t. the FIR input of extent (in_h, in_w): flipped taps, up <-> down, gradient padding"""
+        d = self.down
+        out = k.upfirdn2d(g, torch.flip(self.kernel, [0, 1]), d, d, 1, 1, *self._adjoint_pad(g, in_h, in_w),
+                          taps=_flip_taps(self.taps))
         assert out.shape[1] == in_h and out.shape[2] == in_w, (tuple(out.shape), in_h, in_w)
         return out
+
+    def adjoint_into_activation(self, k, g, act_out, slope, gain, want_bias):
+        """``bias_act_backward(adjoint(g), act_out)`` — in one kernel when the fused FIR + activation-backward kernel
+        takes the shape (the blurred gradient then never exists in HBM), as two launches otherwise"""
+        in_h, in_w = act_out.shape[1], act_out.shape[2]
+        if self.down == 1 and self.taps is not None:
+            hit = k.fir_act_backward(g, _flip_taps(self.taps), act_out, self._adjoint_pad(g, in_h, in_w), slope, gain,
+                                     want_bias=want_bias)
+            if hit is not None:
+                return hit
+        gi, gb, _ = k.bias_act_backward(self.adjoint(k, g, in_h, in_w), act_out, slope, gain, want_bias=want_bias)
+        return gi, gb
 
 
 class ResBlockSpec:
@@ -137,8 +152,7 @@ class _ResBlockFused(Function):
         dx = gi1 = gb1 = dw1 = None
         if need_x or need[1] or need[2]:
             dbl = k.conv_dgrad(gi2, w2k, g2, w_crsk=w2t)
-            do1 = spec.blur2.adjoint(k, dbl, g1.H, g1.W)
-            gi1, gb1, _ = k.bias_act_backward(do1, o1, spec.slope, spec.gain1, want_bias=need[2])
+            gi1, gb1 = spec.blur2.adjoint_into_activation(k, dbl, o1, spec.slope, spec.gain1, need[2])
             if need[1]:
                 dw1 = k.conv_wgrad(gi1, _nhwc(x), g1)
             if need_x:

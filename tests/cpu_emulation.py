@@ -69,6 +69,12 @@ class EmulatedKernels:
             gnw = (gi.reshape(-1, c).sum(1) * noise.reshape(-1)).sum().reshape(1)
         return gi, gb, gnw
 
+    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True):
+        kernel = torch.outer(torch.tensor(taps[0]), torch.tensor(taps[1])).to(grad.dtype)
+        d = self.upfirdn2d(grad, kernel, 1, 1, 1, 1, *pad)
+        gi, gb, _ = self.bias_act_backward(d, act_out, alpha, scale, want_bias=want_bias)
+        return gi, gb
+
     def modulate(self, x, s):
         return x * s[:, None, None, :]
 

@@ -67,6 +67,16 @@ class ShadowKernels:
         return self._both("bias_act_backward", "x%s noise%s" % (tuple(out.shape), noise is not None),
                           (grad_out, out, alpha, scale), dict(want_bias=want_bias, noise=noise))
 
+    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True):
+        out = self.real.fir_act_backward(grad, taps, act_out, pad, alpha, scale, want_bias=want_bias)
+        if out is None:           # shape outside the fused kernel: the caller issues the two separate (shadowed) calls
+            return None
+        ref = self.emu.fir_act_backward(_cpu(grad), taps, _cpu(act_out), pad, alpha, scale, want_bias=want_bias)
+        for i, (o, r) in enumerate(zip(out, ref)):
+            if o is not None:
+                self.log.append(("fir_act_backward", "g%s pad%s out%d" % (tuple(grad.shape), pad, i), _err(o, r)))
+        return out
+
     def modulate(self, x, s):
         return self._both("modulate", "x%s" % (tuple(x.shape),), (x, s), {})
 

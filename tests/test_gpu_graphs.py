@@ -19,10 +19,25 @@ def _trainer(**over):
     return S.create_optimizer(opt, model)
 
 
-def test_graph_replay_matches_eager_on_a_deterministic_step(monkeypatch):
-    """Without crops (no patch discriminator) and with the noise maps zeroed the half-steps draw no random numbers, so
-    eager and captured execution must follow the same loss trajectory (Adam at beta1 = 0 is sign-like on tiny
-    gradients, so the comparison is on losses, not on individual parameters)."""
+def _sync_state(src, dst):
+    """parameters, buffers and Adam state of trainer ``src`` copied into trainer ``dst`` (same architecture)"""
+    with torch.no_grad():
+        ms, md = src.model.singlegpu_model, dst.model.singlegpu_model
+        for a, b in zip(list(ms.parameters()) + list(ms.buffers()), list(md.parameters()) + list(md.buffers())):
+            b.copy_(a)
+        for os_, od in ((src.optimizer_G, dst.optimizer_G), (src.optimizer_D, dst.optimizer_D)):
+            for ps, pd in zip(os_.param_groups[0]["params"], od.param_groups[0]["params"]):
+                if ps in os_.state and pd in od.state:
+                    for key, val in os_.state[ps].items():
+                        od.state[pd][key].copy_(val)
+
+
+def test_graph_replay_matches_eager_step_by_step(monkeypatch):
+    """Teacher-forced comparison: before every half-step the graph trainer receives the eager trainer's parameters and
+    Adam state, then both run the step on the same images.  Without crops (no patch discriminator) and with the noise
+    maps zeroed the step draws no random numbers, so losses and gradients must agree to kernel-level noise (fp32 atomics
+    in the weight-gradient reductions).  Trajectories are NOT compared: Adam at beta1 = 0 is sign-like on tiny gradients
+    and two eager runs drift apart just the same."""
     from swapping_autoencoder_pytorch_b200.stylegan2_layers import NoiseInjection
 
     def zero_noise(self, image, noise=None):
@@ -33,23 +48,26 @@ def test_graph_replay_matches_eager_on_a_deterministic_step(monkeypatch):
     monkeypatch.setattr(NoiseInjection, "resolve_noise", zero_noise)
     det = dict(lambda_PatchGAN=0.0, lambda_patch_R1=0.0, R1_once_every=2)
     real = torch.randn(2, 3, 64, 64, device=DEV, generator=torch.Generator(DEV).manual_seed(5)).clamp(-1, 1)
-    runs = {}
-    for mode in (False, True):
-        tr = _trainer(cuda_graphs=mode, **det)
-        hist = []
-        for _ in range(14):
-            hist.append(tr.train_one_step({"real_A": real.clone()}, 0))
-        runs[mode] = (tr, hist)
-    tr, hist = runs[True]
-    assert tr.graphs is not None and tr.graphs.disabled is None, tr.graphs and tr.graphs.disabled
-    assert {k[0] for k in tr.graphs.captured} == {"D", "G", "R1"}, list(tr.graphs.captured)
-    assert tr.graphs.replayed_launches > 0
-    for step, (a, b) in enumerate(zip(runs[False][1], hist)):
+    te, tg = _trainer(cuda_graphs=False, **det), _trainer(cuda_graphs=True, **det)
+    worst_loss, worst_grad = 0.0, 0.0
+    for step in range(16):
+        _sync_state(te, tg)
+        a = te.train_one_step({"real_A": real.clone()}, 0)
+        b = tg.train_one_step({"real_A": real.clone()}, 0)
         assert a.keys() == b.keys(), (step, a.keys(), b.keys())
         for k in a:
             fa, fb = float(a[k]), float(b[k])
             assert math.isfinite(fb), (step, k, fb)
-            assert abs(fa - fb) <= 2e-2 * max(abs(fa), 1e-2), (step, k, fa, fb)
+            worst_loss = max(worst_loss, abs(fa - fb) / max(abs(fa), 1e-2))
+        group = "Dparams" if step % 2 == 0 else "Gparams"
+        ga = torch.cat([p.grad.reshape(-1) for p in getattr(te, group) if p.grad is not None])
+        gb = torch.cat([p.grad.reshape(-1) for p in getattr(tg, group) if p.grad is not None])
+        assert ga.shape == gb.shape, (step, ga.shape, gb.shape)
+        worst_grad = max(worst_grad, float((ga - gb).norm() / ga.norm().clamp_min(1e-20)))
+    assert tg.graphs is not None and tg.graphs.disabled is None, tg.graphs and tg.graphs.disabled
+    assert {k[0] for k in tg.graphs.captured} == {"D", "G", "R1"}, list(tg.graphs.captured)
+    assert tg.graphs.replayed_launches > 0
+    assert worst_loss < 1e-3 and worst_grad < 1e-2, (worst_loss, worst_grad)
 
 
 def test_graph_replay_full_model_with_crops_and_noise():

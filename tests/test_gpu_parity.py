@@ -584,6 +584,32 @@ def test_shadow_tiny_model_training_steps():
     assert len(sh.log) > 300
 
 
+@pytest.mark.parametrize("kh,c,h,pad", [(4, 128, 65, (1, 1)), (4, 32, 33, (1, 1)), (3, 64, 40, (1, 1)), (4, 64, 17, (2, 2))])
+def test_fir_act_backward_fused(kh, c, h, pad, exact_fp32):
+    """sae_fir_act_backward == sae_upfirdn2d_separable followed by sae_bias_act_backward (incl. the bias gradient)."""
+    kern = backend.kernels()
+    taps1 = [1.0, 3.0, 3.0, 1.0] if kh == 4 else [1.0, 2.0, 1.0]
+    t = tuple(v / sum(taps1) for v in taps1)
+    taps = (t, t)
+    kernel = torch.outer(torch.tensor(t), torch.tensor(t)).to(DEV)
+    n = 3
+    g = torch.randn(n, h, h, c, device=DEV)
+    oh = h + pad[0] + pad[1] - kh + 1
+    act_out = torch.randn(n, oh, oh, c, device=DEV)
+    fused = kern.fir_act_backward(g, taps, act_out, (pad[0], pad[1], pad[0], pad[1]), 0.2, 2 ** 0.5, want_bias=True)
+    assert fused is not None
+    d = kern.upfirdn2d(g, kernel, 1, 1, 1, 1, pad[0], pad[1], pad[0], pad[1], taps=taps)
+    gi, gb, _ = kern.bias_act_backward(d, act_out, 0.2, 2 ** 0.5, want_bias=True)
+    assert rel_err(fused[0], gi) < TOL_FP32, rel_err(fused[0], gi)
+    assert rel_err(fused[1], gb) < 2e-5, rel_err(fused[1], gb)            # atomics: summation order differs
+    # and against the fp64 emulation
+    from tests.cpu_emulation import EmulatedKernels
+    ref = EmulatedKernels().fir_act_backward(g.double().cpu(), taps, act_out.double().cpu(), (pad[0], pad[1], pad[0], pad[1]),
+                                             0.2, 2 ** 0.5)
+    assert rel_err(fused[0], ref[0]) < TOL_FP32 and rel_err(fused[1], ref[1]) < 2e-5
+    assert kern.fir_act_backward(g[..., :8].contiguous(), taps, act_out[..., :8].contiguous(), (pad[0],) * 4, 0.2, 1.0) is None
+
+
 def test_resblock_block_level_node_on_gpu():
     """stylegan2_op/blocks.py on the device: same kernels in a hand-ordered backward whose last data-gradient launch adds
     the skip branch's gradient in its epilogue.  Against the per-operator path the only difference is that fused add
@@ -610,4 +636,6 @@ def test_resblock_block_level_node_on_gpu():
             finally:
                 blocks.set_fused_blocks(prev)
         for i, (a, b) in enumerate(zip(res[True], res[False])):
-            assert a.shape == b.shape and rel_err(a, b) < 2e-4, (cin, i, rel_err(a, b))
+            # i == 1 is the input gradient: the fused path rounds (dgrad + skip gradient) to TF32 once, the per-operator
+            # path rounds both terms and adds them exactly — up to one TF32 ulp (2^-11) apart
+            assert a.shape == b.shape and rel_err(a, b) < (1e-3 if i == 1 else 2e-4), (cin, i, rel_err(a, b))
