@@ -810,6 +810,219 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent kernel, overlapped epilogue
+// conv_tc4_kernel serialises each CTA's tiles: the producer may not refill the rings while the previous tile's output is
+// staged in them, and the MMA warp waits for the epilogue to drain the single accumulator.  This variant (BLOCK_N <= 128)
+// gives the epilogue its own two 16 KB staging buffers and double-buffers the accumulators in TMEM (2 x BLOCK_N columns,
+// still two CTAs per SM), so a CTA loads and multiplies tile i+1 while tile i streams out — the shape the memory-bound
+// layers need (1x1 convs, 32/64-channel layers, the 1- and 2-tap parity classes of a stride-2 data gradient), where the
+// epilogue's stores ARE the critical path and nothing else may wait for them.
+template <int BLOCK_N> constexpr int tc5_nb() { return BLOCK_N >= 128 ? 4 : 8; }     // B ring: 32 KB at N = 128 / 64, 16 KB at 32
+constexpr int TC5_NSTG = 2;                          // dedicated 16 KB output staging buffers
+template <int BLOCK_N>
+constexpr size_t tc5_smem_bytes() {
+    return (size_t)tc5_nb<BLOCK_N>() * (BLOCK_N / 2) * 128 + (size_t)TC3_NA * TC3_ASLOT + (size_t)TC5_NSTG * TC_A_BYTES + 1024 + 256;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks, const int total_work) {
+    constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
+    constexpr int TC3_NB = tc5_nb<BLOCK_N>();
+    constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
+    constexpr uint32_t RING0 = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
+    constexpr uint32_t STG_OFF = RING0;                                  // staging follows the rings (1024-byte aligned)
+    constexpr uint32_t RING = RING0 + (uint32_t)TC5_NSTG * TC_A_BYTES;
+    constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                         // two accumulator buffers
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
+    constexpr int NCHUNK = BLOCK_N / 32;
+    static_assert(BLOCK_N <= 128 && (B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc5: layout");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_ring = base + B_RING;
+    const uint32_t bar_fullA = base + RING;
+    const uint32_t bar_emptyA = bar_fullA + 8 * TC3_NA;
+    const uint32_t bar_fullB = bar_emptyA + 8 * TC3_NA;
+    const uint32_t bar_emptyB = bar_fullB + 8 * TC3_NB;
+    const uint32_t bar_acc = bar_emptyB + 8 * TC3_NB;              // [2]: accumulator buffer b is complete
+    const uint32_t bar_tmem_empty = bar_acc + 16;                  // [2]: leader's copy in use, both CTAs' epilogues arrive on it
+    const uint32_t tmem_slot = bar_tmem_empty + 16;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const uint32_t a_bytes = (uint32_t)(p.ww * p.wh) * 128u;
+    // work item -> (pixel tile of this CTA, channel block); the channel block is the fast index
+    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0) {
+        const int nblk = work % n_blocks;
+        int tile = (work / n_blocks) * 2 + (int)rank;
+        const int tq = tile % p.tiles_w; tile /= p.tiles_w;
+        const int tp = tile % p.tiles_h; tile /= p.tiles_h;
+        q0 = tq * p.tw; p0 = tp * p.th; n0 = tile; col0 = nblk * BLOCK_N;
+    };
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        for (int s = 0; s < TC3_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
+        for (int s = 0; s < TC3_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
+        mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
+        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        if (elect_one()) {
+            int ia = 0, ib = 0, it = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+                int q0, p0, n0, col0;
+                decode(work, q0, p0, n0, col0);
+                // (the output staging has its own shared memory: the loads of the next tile never wait for the epilogue)
+                for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
+                    const int sa = ia % TC3_NA;
+                    mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC3_NA)) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
+                    tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
+                    for (int t = 0; t < p.ntaps; ++t, ++ib) {
+                        const int sb = ib % TC3_NB;
+                        mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
+                        if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
+                        tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, p.wk[t] + cb * TC_BK,
+                                     col0 + (int)rank * (BLOCK_N / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (leader && elect_one()) {
+            const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;        // 8-row atoms are one window row apart
+            int ia = 0, ib = 0, it = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+            // accumulator buffer (it & 1): both CTAs' epilogues must have drained its previous tile (it - 2)
+            const uint32_t buf = (uint32_t)it & 1u;
+            if (it > 1) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
+            int tstep = 0;
+            for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
+                const int sa = ia % TC3_NA;
+                mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC3_NA)) & 1u);
+                const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
+                for (int t = 0; t < p.ntaps; ++t, ++ib, ++tstep) {
+                    const int sb = ib % TC3_NB;
+                    mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // A descriptor: start = window row arow[t]; same 128B-swizzle K-major layout, SBO = ww * 128 B
+                    const uint32_t aaddr = a0 + (uint32_t)p.arow[t] * 128u;
+                    uint64_t da = (uint64_t)((aaddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | sbo | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                    const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (tstep > 0 || k > 0) ? 1u : 0u);
+                    umma2_commit(bar_emptyB + 8 * sb);
+                }
+                umma2_commit(bar_emptyA + 8 * sa);
+            }
+            umma2_commit(bar_acc + 8 * buf);
+            }
+        }
+    } else {
+        // ===================================================== epilogue (identical to the pair kernel)
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const int iw = row % p.tw, ih = row / p.tw;
+        int it = 0, gch = 0;         // gch: running chunk count -> staging buffer and bulk-group bookkeeping across tiles
+        for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+        int q0, p0, n0, col0;
+        decode(work, q0, p0, n0, col0);
+        const uint32_t buf = (uint32_t)it & 1u;
+        const int n = n0, pp = p0 + ih, qq = q0 + iw;
+        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
+        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
+        mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float nz = 0.f;
+        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
+#pragma unroll 1
+        for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
+            if (gch >= TC5_NSTG) {
+                // the bulk store that last read this staging buffer (TC5_NSTG chunks ago) must have finished reading it
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            float v[32];
+            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+            const int colb = col0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float t = v[j];
+                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
+                t += nz;
+                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
+                t *= p.epi.gain;
+                v[j] = t;
+            }
+            if (p.epi.residual && valid) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 r = __ldg(r4 + j);
+                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
+                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
+                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
+                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
+                }
+            }
+            if (p.epi.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+            }
+            const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
+            uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                tma_store_4d(&map_out, base + stg_off, colb, q0, p0, n0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (ch == NCHUNK - 1) {
+                    // all 128 epilogue threads have finished reading TMEM: tell the leader's MMA warp (remote for rank 1)
+                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
+                }
+            }
+        }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // before the CTA retires
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle) {
@@ -1042,6 +1255,60 @@ static int tc4_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
     return check_launch("conv_tc4");
 }
 
+// persistent launch with overlapped epilogue (conv_tc5_kernel): same grid as tc4_launch
+template <int BLOCK_N>
+static int tc5_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    TcParams p;
+    tc_fill_params(pr, e, p);
+    p.tw = 8; p.th = 16; p.tn = 1;
+    p.tiles_w = (pr.OW + p.tw - 1) / p.tw;
+    p.tiles_h = (pr.OH + p.th - 1) / p.th;
+    p.tiles_n = pr.SN;
+    int oy_min = pr.oy[0], oy_max = pr.oy[0], ox_min = pr.ox[0], ox_max = pr.ox[0];
+    for (int t = 1; t < pr.ntaps; ++t) {
+        oy_min = pr.oy[t] < oy_min ? pr.oy[t] : oy_min; oy_max = pr.oy[t] > oy_max ? pr.oy[t] : oy_max;
+        ox_min = pr.ox[t] < ox_min ? pr.ox[t] : ox_min; ox_max = pr.ox[t] > ox_max ? pr.ox[t] : ox_max;
+    }
+    p.oy_min = oy_min; p.ox_min = ox_min;
+    p.ww = p.tw + (ox_max - ox_min);
+    p.wh = p.th + (oy_max - oy_min);
+    for (int t = 0; t < pr.ntaps; ++t) p.arow[t] = (unsigned short)((pr.oy[t] - oy_min) * p.ww + (pr.ox[t] - ox_min));
+    CUtensorMap msrc, mw, mout;
+    int rc = tc_encode_maps(pr, p, BLOCK_N / 2, &msrc, &mw, &mout);
+    if (rc) return rc;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)pr.SC, (cuuint64_t)pr.SW, (cuuint64_t)pr.SH, (cuuint64_t)pr.SN};
+        cuuint64_t strides[3] = {(cuuint64_t)pr.SC * 4, (cuuint64_t)pr.SW * pr.SC * 4, (cuuint64_t)pr.SH * pr.SW * pr.SC * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.ww, (cuuint32_t)p.wh, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        rc = encode_map(&msrc, pr.src, 4, dims, strides, box, es);
+        if (rc) return rc;
+    }
+    constexpr size_t smem = tc5_smem_bytes<BLOCK_N>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int n_blocks = pr.Ncol / BLOCK_N;
+    const int total_work = ((tiles + 1) / 2) * n_blocks;
+    int clusters = sm_count();                       // 2 CTAs per SM, 2 CTAs per cluster
+    if (clusters > total_work) clusters = total_work;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks, total_work));
+    return check_launch("conv_tc5");
+}
+
 static int tc4_mode() {
     static int mode = -1;
     if (mode < 0) { const char* v = getenv("SAE_TC_PERSISTENT"); mode = v ? atoi(v) : 1; }
@@ -1081,6 +1348,17 @@ static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st)
                 // main loop is ~1k cycles per tile, are faster persistent (setup cost amortised).  SAE_TC_PERSISTENT=2
                 // forces the persistent kernel everywhere, 0 disables it.
                 const int mode = tc4_mode();
+                // SAE_TC5: 0 = off; 1 = the overlapped-epilogue persistent kernel replaces conv_tc4 on the narrow layers;
+                // 2 (default) = and also takes wide layers whose K loop has at most SAE_TC5_KB (default 16) 32-channel blocks
+                // (1x1 convs, the 1- and 2-tap parity classes of stride-2 data gradients): those are HBM-bound, and their
+                // stores may not stall the next tile's loads
+                static int tc5 = -1, tc5_kb = -1;
+                if (tc5 < 0) { const char* v = getenv("SAE_TC5"); tc5 = v ? atoi(v) : 2; }
+                if (tc5_kb < 0) { const char* v = getenv("SAE_TC5_KB"); tc5_kb = v ? atoi(v) : 16; }
+                if (tc5 && mode) {
+                    if (pr.Ncol % 128 != 0) return pr.Ncol % 64 == 0 ? tc5_launch<64>(pr, e, st) : tc5_launch<32>(pr, e, st);
+                    if (tc5 >= 2 && pr.ntaps * (pr.SC / TC_BK) <= tc5_kb) return tc5_launch<128>(pr, e, st);
+                }
                 // short main loops (1x1 convs, the 1- and 2-tap parity classes of a stride-2 data gradient): per-tile setup
                 // dominates just as it does for the narrow layers -> persistent kernel when the K loop has at most
                 // SAE_TC_PERSIST_KB 32-channel blocks

@@ -153,7 +153,7 @@ class HalfStepGraphs:
                 wrapper.suspend_reduce = False
         launches = _lib.launch_count() - n0
         outputs = {k: v for k, v in outputs.items() if torch.is_tensor(v)}
-        grads = [(p, p.grad) for p in self._params(kind) if p.grad is not None]
+        grads = [(p, p.grad) for p in self._params(kind)]      # None where the body produces no gradient (R1: final bias)
         hit = (graph, static_in, outputs, launches, grads)
         self.captured[key] = hit
         return hit

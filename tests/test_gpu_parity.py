@@ -270,6 +270,11 @@ CONV_CASES = [
     (2, 40, 40, 32, 32, 3, 1, 1),            # Dpatch / encoder 32 -> 32: narrow-input weight-gradient kernel
     (1, 33, 70, 32, 64, 3, 1, 0),            # same kernel, pad 0, ragged 32-pixel chunks, 64 output channels
     (2, 32, 32, 32, 128, 3, 1, 1),           # same kernel at its widest (3 x 128 TMEM columns)
+    # persistent overlapped-epilogue kernel (conv_tc5): enough tiles that every CTA pair loops several times, so both
+    # TMEM accumulator buffers, both staging buffers and every barrier phase are exercised
+    (8, 128, 128, 32, 32, 3, 1, 1),          # narrow 3x3: 512 work items over <= 148 pairs
+    (4, 128, 128, 128, 256, 1, 1, 0),        # wide 1x1 (two 128-column blocks per pixel tile)
+    (16, 129, 129, 128, 256, 3, 2, 0),       # stride-2 data gradient: its 1- and 2-tap parity classes
 ]
 
 
@@ -636,6 +641,6 @@ def test_resblock_block_level_node_on_gpu():
             finally:
                 blocks.set_fused_blocks(prev)
         for i, (a, b) in enumerate(zip(res[True], res[False])):
-            # i == 1 is the input gradient: the fused path rounds (dgrad + skip gradient) to TF32 once, the per-operator
-            # path rounds both terms and adds them exactly — up to one TF32 ulp (2^-11) apart
-            assert a.shape == b.shape and rel_err(a, b) < (1e-3 if i == 1 else 2e-4), (cin, i, rel_err(a, b))
+            # the two paths round different intermediates to TF32 (fused: dgrad + skip gradient rounded once, blurred
+            # gradient never rounded; per-operator: every stored tensor rounded) — a TF32 ulp (2^-11) apart at most
+            assert a.shape == b.shape and rel_err(a, b) < (2e-5 if i == 0 else 1e-3), (cin, i, rel_err(a, b))
