@@ -1,24 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "==== conv tests (SAE_TC5 default)"
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 200 -k "conv" 2>&1 | grep -v "^E   *+\|^E  *where" | tail -15 | tee gpurun_out/tests_conv.log
-if grep -q "failed\|Timeout\|error" gpurun_out/tests_conv.log; then echo "CONV TESTS FAILED"; export SAE_TC5=0; fi
-for m in 0 1 2; do
-echo "==== conv bench SAE_TC5=$m"
-SAE_TC5=$m timeout 300 python scripts/conv_bench.py --dirs fprop,dgrad --only "1x1" 2>&1 | tail -12
-SAE_TC5=$m timeout 300 python scripts/conv_bench.py --dirs dgrad --only "s2" 2>&1 | tail -4
-SAE_TC5=$m timeout 300 python scripts/conv_bench.py --dirs fprop,dgrad --only "Dpatch" 2>&1 | tail -5
-SAE_TC5=$m timeout 300 python scripts/conv_bench.py --dirs fprop,dgrad --only "E 32" 2>&1 | tail -2
-done
-echo "==== conv bench SAE_TC5=2 KB=36"
-SAE_TC5_KB=36 timeout 300 python scripts/conv_bench.py --dirs fprop,dgrad --only "s2" 2>&1 | tail -8
 echo "==== graph tests"
-timeout 600 python -m pytest tests/test_gpu_graphs.py -m gpu -q --timeout 300 2>&1 | grep -v "^E   *+\|^E  *where" | tail -25 | tee gpurun_out/tests_graphs.log
+timeout 600 python -m pytest tests/test_gpu_graphs.py -m gpu -q --timeout 300 2>&1 | grep -v "^E   *+\|^E  *where" > gpurun_out/tests_graphs_full.log; tail -5 gpurun_out/tests_graphs_full.log; grep -n "Error\|error" gpurun_out/tests_graphs_full.log | head -20
 echo "==== all parity tests"
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 2>&1 | grep -v "^E   *+\|^E  *where" | tail -8 | tee gpurun_out/tests.log
-echo "==== bench (tc5 default)"
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_graphs.log 2>&1; grep -B2 -A25 "capture of the" gpurun_out/bench_graphs.log | head -40; tail -1 gpurun_out/bench_graphs.log | tee gpurun_out/bench_graphs.json | cut -c1-300
-echo "==== bench tc5 off"
-SAE_TC5=0 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs_tc5off.json | cut -c1-250
-echo "==== bench tc5=1"
-SAE_TC5=1 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs_tc5_1.json | cut -c1-250
+echo "==== bench default"
+timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs.json | cut -c1-200
+echo "==== bench per-operator blocks"
+SAE_FUSED_BLOCKS=0 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs_unfused.json | cut -c1-200
+echo "==== bench no fused fir+act"
+SAE_FUSED_FIR_ACT=0 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs_nofiract.json | cut -c1-200
+echo "==== op profile (eager, kernel table only)"
+timeout 300 python scripts/op_profile.py > gpurun_out/op_profile.txt 2>&1; grep "sae::\|at::native\|Self C" gpurun_out/op_profile.txt | cut -c1-50,130-215 | head -45

@@ -1348,13 +1348,14 @@ static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st)
                 // main loop is ~1k cycles per tile, are faster persistent (setup cost amortised).  SAE_TC_PERSISTENT=2
                 // forces the persistent kernel everywhere, 0 disables it.
                 const int mode = tc4_mode();
-                // SAE_TC5: 0 = off; 1 = the overlapped-epilogue persistent kernel replaces conv_tc4 on the narrow layers;
-                // 2 (default) = and also takes wide layers whose K loop has at most SAE_TC5_KB (default 16) 32-channel blocks
-                // (1x1 convs, the 1- and 2-tap parity classes of stride-2 data gradients): those are HBM-bound, and their
-                // stores may not stall the next tile's loads
+                // SAE_TC5: 0 = off; 1 = the overlapped-epilogue persistent kernel replaces conv_tc4 on the narrow layers only;
+                // 2 (default) = it also takes every wide layer whose K loop has at most SAE_TC5_KB 32-channel blocks, as
+                // 128-column blocks.  Measured (profiles/r1_conv_bench_tc5.txt): it wins at EVERY depth — +18 % on 128 -> 128 at
+                // 256^2 (epilogue-bound before), +7 % on 256 -> 256, +3 % on 512 -> 512 against the 256-column one-tile kernel,
+                // 1.2-1.6x on the HBM-bound 1x1 / narrow / short-loop stride-2 dgrad shapes — so the default threshold is "all".
                 static int tc5 = -1, tc5_kb = -1;
                 if (tc5 < 0) { const char* v = getenv("SAE_TC5"); tc5 = v ? atoi(v) : 2; }
-                if (tc5_kb < 0) { const char* v = getenv("SAE_TC5_KB"); tc5_kb = v ? atoi(v) : 16; }
+                if (tc5_kb < 0) { const char* v = getenv("SAE_TC5_KB"); tc5_kb = v ? atoi(v) : (1 << 20); }
                 if (tc5 && mode) {
                     if (pr.Ncol % 128 != 0) return pr.Ncol % 64 == 0 ? tc5_launch<64>(pr, e, st) : tc5_launch<32>(pr, e, st);
                     if (tc5 >= 2 && pr.ntaps * (pr.SC / TC_BK) <= tc5_kb) return tc5_launch<128>(pr, e, st);

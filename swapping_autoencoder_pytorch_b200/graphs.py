@@ -15,6 +15,7 @@ images copied into a static input buffer.
   Adam step run eagerly after the replay on the graph's static gradient buffers — no NCCL call is captured.
 * A body that fails to capture falls back to eager execution for the rest of the run (``self.disabled`` holds why).
 """
+import gc
 import traceback
 import warnings
 
@@ -145,10 +146,17 @@ class HalfStepGraphs:
         n0 = _lib.launch_count()
         if world > 1:
             wrapper.suspend_reduce = True
+        # no cyclic garbage collection while the stream is capturing: a collected object that owns device memory or an
+        # older CUDA graph would issue cudaFree / cudaGraphExecDestroy in the middle of the capture and invalidate it
+        gc.collect()
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
         try:
             with torch.cuda.graph(graph, pool=self.pool, stream=self.stream):
                 outputs = body(static_in, step=(world == 1))
         finally:
+            if gc_was_enabled:
+                gc.enable()
             if world > 1:
                 wrapper.suspend_reduce = False
         launches = _lib.launch_count() - n0

@@ -76,7 +76,7 @@ def test_graph_replay_full_model_with_crops_and_noise():
     tr = _trainer(cuda_graphs=True, R1_once_every=2)
     real = torch.randn(2, 3, 64, 64, device=DEV).clamp(-1, 1)
     tr.graphs.warm_up(real)
-    assert tr.graphs.disabled is None, tr.graphs.disabled
+    assert tr.graphs.disabled is None, (tr.graphs.disabled, tr.graphs.last_traceback)
     assert len(tr.graphs.captured) == 3
     w = tr.Dparams[0].detach().clone()
     seen = []
