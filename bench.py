@@ -226,12 +226,12 @@ def run_ours(args, rank, world, local):
 
     # at least 4 untimed half-steps: D, G, D, G — both step kinds twice, so the caching allocator and every kernel
     # variant have reached steady state before the timed region
-    n_warm = max(args.warmup, 4)
+    n_warm = max(args.warmup, int(os.environ.get("SAE_BENCH_MIN_WARM", "4")))      # (profiling runs under ncu lower it)
     for _ in range(n_warm):
         trainer.train_one_step({"real_A": resident}, 0)
     if trainer.graphs is not None:
         trainer.graphs.warm_up(resident)          # capture the D, G and R1 graphs before the timed region
-    if trainer.graphs is None or trainer.graphs.disabled:
+    if (trainer.graphs is None or trainer.graphs.disabled) and os.environ.get("SAE_BENCH_SKIP_R1_WARM") != "1":
         # eager execution: the lazy-R1 evaluation (every 16th discriminator step) must not meet the caching allocator's
         # cold start inside the timed region — keep stepping until one R1 has run in its natural place (<= 32 half-steps)
         for _ in range(2 * opt.R1_once_every):

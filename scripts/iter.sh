@@ -1,14 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "==== graph tests"
-timeout 600 python -m pytest tests/test_gpu_graphs.py -m gpu -q --timeout 300 2>&1 | grep -v "^E   *+\|^E  *where" > gpurun_out/tests_graphs_full.log; tail -5 gpurun_out/tests_graphs_full.log; grep -n "Error\|error" gpurun_out/tests_graphs_full.log | head -20
-echo "==== all parity tests"
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 2>&1 | grep -v "^E   *+\|^E  *where" | tail -8 | tee gpurun_out/tests.log
-echo "==== bench default"
+echo "==== fir tests"
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 -k "fir or resblock or shadow or layers or networks" 2>&1 | grep -v "^E   *+\|^E  *where" | tail -6
+echo "==== mem bench fir"
+timeout 300 python scripts/mem_bench.py 2>&1 | grep "fir4 down2\|fir4 up2\|fused" | head -20
+echo "==== bench N=2 (graphs on)"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 32 --warmup 4 > gpurun_out/bench_n2.log 2>&1; grep -i "capture of the\|Error" gpurun_out/bench_n2.log | head -10; tail -1 gpurun_out/bench_n2.log | tee gpurun_out/bench_n2.json | cut -c1-700
+echo "==== bench N=1"
 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs.json | cut -c1-200
-echo "==== bench per-operator blocks"
-SAE_FUSED_BLOCKS=0 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs_unfused.json | cut -c1-200
-echo "==== bench no fused fir+act"
-SAE_FUSED_FIR_ACT=0 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_graphs_nofiract.json | cut -c1-200
-echo "==== op profile (eager, kernel table only)"
-timeout 300 python scripts/op_profile.py > gpurun_out/op_profile.txt 2>&1; grep "sae::\|at::native\|Self C" gpurun_out/op_profile.txt | cut -c1-50,130-215 | head -45

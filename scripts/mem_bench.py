@@ -42,6 +42,19 @@ def main():
             oh = h + pad[0] + pad[1] - kern.shape[0] + 1
             gb = 4.0 * (x.numel() + n * oh * oh * c) / 1e9
             print("%-46s %9.3f %9.0f" % ("%s [%d,%d,%d,%d]" % (name, n, h, h, c), ms, gb / ms * 1e3))
+        # decimating blur of the skip branches (down 2, pad (1,1)) and its adjoint (zero-insert x2)
+        ms = timeit(lambda: k.upfirdn2d(x, k4, 1, 1, 2, 2, 1, 1, 1, 1, taps=(t4, t4)), flush)
+        oh = (h + 2 - 4) // 2 + 1
+        print("%-46s %9.3f %9.0f" % ("fir4 down2 [%d,%d,%d,%d]" % (n, h, h, c), ms, 4.0 * (x.numel() + n * oh * oh * c) / 1e9 / ms * 1e3))
+        xs = torch.randn(n, oh, oh, c, device=dev)
+        ms = timeit(lambda: k.upfirdn2d(xs, k4, 2, 2, 1, 1, 2, h - oh * 2 + 1, 2, h - oh * 2 + 1, taps=(t4, t4)), flush)
+        print("%-46s %9.3f %9.0f" % ("fir4 up2 (adjoint) -> [%d,%d,%d,%d]" % (n, h, h, c), ms, 4.0 * (x.numel() + xs.numel()) / 1e9 / ms * 1e3))
+        # blur adjoint fused with the activation backward
+        act = torch.randn(n, h, h, c, device=dev)
+        gsrc = torch.randn(n, h + 1, h + 1, c, device=dev)
+        ms = timeit(lambda: k.fir_act_backward(gsrc, (t4, t4), act, (1, 1, 1, 1), 0.2, 1.414), flush)
+        print("%-46s %9.3f %9.0f" % ("fir4 + act bwd fused -> [%d,%d,%d,%d]" % (n, h, h, c), ms, 4.0 * (gsrc.numel() + 2 * act.numel()) / 1e9 / ms * 1e3))
+        del xs, act, gsrc
         b = torch.randn(c, device=dev)
         y = torch.randn_like(x)
         ms = timeit(lambda: k.bias_act(x, b, None, 3, 0, 0.2, 1.414), flush)

@@ -387,19 +387,21 @@ fir_sep_up2_kernel(const float* __restrict__ x, float* __restrict__ out, FirPara
         const int64_t n = t / p.out_h;
         const float* xn = x + n * (int64_t)p.in_h * p.in_w * p.minor + (int64_t)c * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // only taps whose zero-upsampled position (o + tap - pad) is even land on an input sample: per axis that is tap
+        // a0 = (pad - o) & 1 and tap a0 + 2 — a 2 x 2 gather, selected without divergent branches or indexed parameters
+        const int ay = (p.pad_y0 - oy) & 1, ax = (p.pad_x0 - ox) & 1;
+        const float ty[2] = {ay ? taps.y[1] : taps.y[0], ay ? (KH > 3 ? taps.y[3] : 0.f) : (KH > 2 ? taps.y[2] : 0.f)};
+        const float tx[2] = {ax ? taps.x[1] : taps.x[0], ax ? (KW > 3 ? taps.x[3] : 0.f) : (KW > 2 ? taps.x[2] : 0.f)};
+        const int uy0 = oy + ay - p.pad_y0, ux0 = ox + ax - p.pad_x0;          // both even (possibly negative)
 #pragma unroll
-        for (int a = 0; a < KH; ++a) {
-            const int uy = oy + a - p.pad_y0;
-            if (uy < 0 || (uy & 1)) continue;
-            const int iy = uy >> 1;
-            if (iy >= p.in_h) continue;
+        for (int dy = 0; dy < 2; ++dy) {
+            const int iy = (uy0 >> 1) + dy;
+            if (ay + 2 * dy >= KH || iy < 0 || iy >= p.in_h) continue;
 #pragma unroll
-            for (int b = 0; b < KW; ++b) {
-                const int ux = ox + b - p.pad_x0;
-                if (ux < 0 || (ux & 1)) continue;
-                const int ix = ux >> 1;
-                if (ix >= p.in_w) continue;
-                const float w = taps.y[a] * taps.x[b];
+            for (int dx = 0; dx < 2; ++dx) {
+                const int ix = (ux0 >> 1) + dx;
+                if (ax + 2 * dx >= KW || ix < 0 || ix >= p.in_w) continue;
+                const float w = ty[dy] * tx[dx];
                 const float4 v = __ldg(reinterpret_cast<const float4*>(xn + ((int64_t)iy * p.in_w + ix) * p.minor));
                 acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
             }

@@ -12,6 +12,7 @@ import torch
 
 from . import networks, util
 from .stylegan2_op import filter_reuse
+from .stylegan2_op.blocks import per_operator_blocks
 
 
 class BaseModel(torch.nn.Module):
@@ -174,6 +175,10 @@ class SwappingAutoencoderModel(BaseModel):
     def compute_R1_loss(self, real):
         """R1 gradient penalty on D (w.r.t. the image) and on Dpatch (w.r.t. both crop sets); needs the
         second-order autograd of every op in D / Dpatch (reference :138-185)."""
+        with per_operator_blocks():      # the backward is differentiated again: block-level nodes would only recompute
+            return self._compute_R1_loss(real)
+
+    def _compute_R1_loss(self, real):
         opt = self.opt
         penalty = 0.0
         if opt.lambda_R1 > 0.0:

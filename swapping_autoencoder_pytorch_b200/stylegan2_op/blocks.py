@@ -35,6 +35,19 @@ def set_fused_blocks(flag):
     return prev
 
 
+class per_operator_blocks:
+    """``with per_operator_blocks():`` — build per-operator autograd nodes inside the scope.  A caller that knows it
+    will differentiate the backward (compute_R1_loss) uses it to skip the block node's forward, which the node would
+    have to repeat in per-operator form anyway once the backward is recorded."""
+
+    def __enter__(self):
+        self.prev = set_fused_blocks(False)
+
+    def __exit__(self, *exc):
+        set_fused_blocks(self.prev)
+        return False
+
+
 def _nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
