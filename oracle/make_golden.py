@@ -203,12 +203,71 @@ def gen_networks(R):
     save("losses_tiny", dict(opt=TINY, param_seed=7, bias_seed=11, real_seed=900, seeds=dict(D=21, G=22, R1=23)), **losses)
 
 
+def gen_surface_branches(R):
+    """Branches of the operator surface that training does not exercise but evaluation / the original StyleGAN2 classes
+    do: Upsample / Downsample modules, ToRGB with an upsampled skip, ModulatedConv2d with a spatially
+    varying style and with downsample=True, the original Generator class, encoder feature extraction."""
+    L = R.layers
+    out = {}
+    x = rnd(1000, 2, 4, 7, 6).requires_grad_()
+    for name, mod in (("upsample", L.Upsample([1, 3, 3, 1])), ("downsample", L.Downsample([1, 3, 3, 1]))):
+        mod = mod.double()
+        y = mod(x)
+        w = rnd(1001, *y.shape)
+        gx, = torch.autograd.grad((y * w).sum(), x)
+        out[name + "_y"], out[name + "_gx"] = y, gx
+    m = L.ToRGB(8, 16, upsample=True)
+    load_module(m, {"conv.weight": rnd(1010, 1, 3, 8, 1, 1), "conv.modulation.weight": rnd(1011, 8, 16),
+                    "conv.modulation.bias": rnd(1012, 8) * 0.1 + 1, "bias": rnd(1013, 1, 3, 1, 1) * 0.1})
+    out["torgb_skip_y"] = m(rnd(1014, 2, 8, 10, 10), rnd(1015, 2, 16), skip=rnd(1016, 2, 3, 5, 5))
+    m = L.ModulatedConv2d(8, 12, 3, 16)
+    P = {"weight": rnd(1020, 1, 12, 8, 3, 3), "modulation.weight": rnd(1021, 8, 16), "modulation.bias": rnd(1022, 8) * 0.1 + 1}
+    load_module(m, P)
+    # spatially varying style, interpolated to the input size.  Batch 1: the reference's branch broadcasts
+    # [B,C,H,W] * [B,1,C,H,W] into a 5-D tensor and only survives its own .view() when B == 1 (stylegan2_layers.py:269-276)
+    xs = rnd(1023, 1, 8, 6, 7).requires_grad_()
+    ss = rnd(1024, 1, 16, 3, 4).requires_grad_()
+    y = m(xs, ss)
+    w = rnd(1025, *y.shape)
+    gx, gs = torch.autograd.grad((y * w).sum(), [xs, ss])
+    out.update({"modconv_spatial_y": y, "modconv_spatial_gx": gx, "modconv_spatial_gs": gs})
+    m = L.ModulatedConv2d(8, 12, 3, 16, downsample=True)
+    load_module(m, P)
+    out["modconv_down_y"] = m(rnd(1026, 2, 8, 8, 8), rnd(1027, 2, 16))
+    # the original StyleGAN2 synthesis network at its smallest size, fixed noise buffers
+    torch.manual_seed(31)
+    g = L.Generator(8, 16, 2, channel_multiplier=1).double()
+    sd = g.state_dict()
+    rs = np.random.RandomState(1030)
+    for k in sorted(sd):
+        if sd[k].dtype.is_floating_point and not k.endswith(".kernel"):
+            sd[k] = torch.from_numpy(rs.standard_normal(tuple(sd[k].shape))).to(DT) * (0.1 if k.endswith("bias") or "noise" in k else 1.0)
+    g.load_state_dict(sd)
+    img, _ = g([rnd(1031, 2, 16)], randomize_noise=False)
+    out["generator8_img"] = img
+    save("surface_branches", dict(state_seed=1030, keys=sorted(k for k in sd if sd[k].dtype.is_floating_point and not k.endswith(".kernel"))),
+         **out)
+
+    # encoder feature extraction (evaluation path, encoder.py:93-107) on the tiny networks of the other fixtures
+    opt = default_options(**TINY)
+    model, sd = build_ref_model(R, opt)
+    real = rnd(900, 2, 3, 64, 64).clamp(-1, 1)
+    sp, gl, feat = model.E(real, extract_features=True)
+    save("encoder_features_tiny", dict(opt=TINY, param_seed=7, bias_seed=11, real_seed=900), sp=sp, gl=gl, feature=feat)
+
+
 def main():
     torch.set_default_dtype(torch.float32)
     R = ref_import.import_reference()
-    gen_ops(R)
-    gen_layers(R)
-    gen_networks(R)
+    which = sys.argv[1:] or ["ops", "layers", "networks", "surface"]
+    if "ops" in which:
+        gen_ops(R)
+    if "layers" in which:
+        gen_layers(R)
+    if "networks" in which:
+        gen_networks(R)
+    if "surface" in which:
+        gen_surface_branches(R)
 
 
 if __name__ == "__main__":

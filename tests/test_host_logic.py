@@ -256,3 +256,60 @@ def test_resblock_block_level_node_matches_per_operator_nodes():
     # a block the fused node does not cover (reflection padding) keeps using the per-operator path
     assert L.ResBlock(8, 12, [1, 2, 1], reflection_pad=True)._fused_spec() is None
     assert L.ResBlock(8, 12, downsample=False)._fused_spec() is None
+
+
+def test_surface_branches_against_reference():
+    """the operator-surface branches training does not exercise — Upsample / Downsample modules, ToRGB
+    with an upsampled skip, ModulatedConv2d with a spatially varying style and with downsample=True, the original
+    StyleGAN2 Generator class — against numbers produced by the reference (oracle/make_golden.py::gen_surface_branches)."""
+    import numpy as np
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    meta, G = load_golden("surface_branches")
+    x = rnd(1000, 2, 4, 7, 6).requires_grad_()
+    for name, mod in (("upsample", L.Upsample([1, 3, 3, 1])), ("downsample", L.Downsample([1, 3, 3, 1]))):
+        mod = mod.double()
+        y = mod(x)
+        gx, = torch.autograd.grad((y * rnd(1001, *y.shape)).sum(), x)
+        assert rel_err(y, G[name + "_y"]) < TOL and rel_err(gx, G[name + "_gx"]) < TOL, name
+    m = _load(L.ToRGB(8, 16, upsample=True), {"conv.weight": rnd(1010, 1, 3, 8, 1, 1), "conv.modulation.weight": rnd(1011, 8, 16),
+                                              "conv.modulation.bias": rnd(1012, 8) * 0.1 + 1, "bias": rnd(1013, 1, 3, 1, 1) * 0.1})
+    assert rel_err(m(rnd(1014, 2, 8, 10, 10), rnd(1015, 2, 16), skip=rnd(1016, 2, 3, 5, 5)), G["torgb_skip_y"]) < TOL
+    P = {"weight": rnd(1020, 1, 12, 8, 3, 3), "modulation.weight": rnd(1021, 8, 16), "modulation.bias": rnd(1022, 8) * 0.1 + 1}
+    m = _load(L.ModulatedConv2d(8, 12, 3, 16), P)
+    xs = rnd(1023, 1, 8, 6, 7).requires_grad_()
+    ss = rnd(1024, 1, 16, 3, 4).requires_grad_()
+    y = m(xs, ss)
+    gx, gs = torch.autograd.grad((y * rnd(1025, *y.shape)).sum(), [xs, ss])
+    assert rel_err(y, G["modconv_spatial_y"]) < TOL
+    assert rel_err(gx, G["modconv_spatial_gx"]) < TOL and rel_err(gs, G["modconv_spatial_gs"]) < TOL
+    # batch > 1 with a spatial style: the reference's branch cannot run (it broadcasts to 5-D); here it is per-sample
+    y2 = m(torch.cat([xs, xs]), torch.cat([ss, ss]))
+    assert rel_err(y2[1], y[0]) < TOL
+    m = _load(L.ModulatedConv2d(8, 12, 3, 16, downsample=True), P)
+    assert rel_err(m(rnd(1026, 2, 8, 8, 8), rnd(1027, 2, 16)), G["modconv_down_y"]) < TOL
+    g = L.Generator(8, 16, 2, channel_multiplier=1).double()
+    sd = g.state_dict()
+    keys = sorted(k for k in sd if sd[k].dtype.is_floating_point and not k.endswith(".kernel"))
+    assert keys == meta["keys"], set(keys) ^ set(meta["keys"])          # same state_dict contract as the reference class
+    rs = np.random.RandomState(meta["state_seed"])
+    for k in keys:
+        sd[k] = torch.from_numpy(rs.standard_normal(tuple(sd[k].shape))).double() * (0.1 if k.endswith("bias") or "noise" in k else 1.0)
+    g.load_state_dict(sd)
+    img, _ = g([rnd(1031, 2, 16)], randomize_noise=False)
+    assert rel_err(img, G["generator8_img"]) < TOL
+
+
+def test_encoder_feature_extraction_against_reference():
+    """evaluation path of the encoder (reference encoder.py:93-107): reflection-padded stride-2 conv features, 7x7"""
+    import swapping_autoencoder_pytorch_b200 as S
+    from oracle import sae_oracle as O
+    meta, G = load_golden("encoder_features_tiny")
+    opt = default_options(**meta["opt"])
+    model = S.create_model(opt).singlegpu_model.double()
+    sd = perturbed_state_dict(opt, dtype=torch.float64, param_seed=meta["param_seed"], bias_seed=meta["bias_seed"])
+    own = model.state_dict()
+    own.update({k: v for k, v in sd.items() if k in own})
+    model.load_state_dict(own)
+    real = rnd(meta["real_seed"], 2, 3, 64, 64).clamp(-1, 1)
+    sp, gl, feat = model.encode(real, extract_features=True)
+    assert rel_err(sp, G["sp"]) < TOL and rel_err(gl, G["gl"]) < TOL and rel_err(feat, G["feature"]) < TOL
