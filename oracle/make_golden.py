@@ -256,10 +256,26 @@ def gen_surface_branches(R):
     save("encoder_features_tiny", dict(opt=TINY, param_seed=7, bias_seed=11, real_seed=900), sp=sp, gl=gl, feature=feat)
 
 
+def gen_state_dict_contract(R):
+    """names, shapes and dtypes of the reference model's state_dict (what its checkpoints contain) for the default 256x256
+    option set and for the reduced one — the contract reference checkpoints are loaded by"""
+    contract = {}
+    for label, over in (("default256", dict(num_gpus=0)), ("tiny", TINY)):
+        opt = default_options(**over)
+        model = R.sae_model.SwappingAutoencoderModel(opt)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.initialize()
+        contract[label] = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in model.state_dict().items()}
+        print("state_dict contract", label, len(contract[label]), "tensors")
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "state_dict_contract.json"), "w") as f:
+        json.dump(contract, f, indent=0, sort_keys=True)
+
+
 def main():
     torch.set_default_dtype(torch.float32)
     R = ref_import.import_reference()
-    which = sys.argv[1:] or ["ops", "layers", "networks", "surface"]
+    which = sys.argv[1:] or ["ops", "layers", "networks", "surface", "contract"]
     if "ops" in which:
         gen_ops(R)
     if "layers" in which:
@@ -268,6 +284,8 @@ def main():
         gen_networks(R)
     if "surface" in which:
         gen_surface_branches(R)
+    if "contract" in which:
+        gen_state_dict_contract(R)
 
 
 if __name__ == "__main__":
