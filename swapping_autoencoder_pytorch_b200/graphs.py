@@ -160,8 +160,7 @@ class HalfStepGraphs:
             if world > 1:
                 wrapper.suspend_reduce = False
         launches = _lib.launch_count() - n0
-        # detached views of the static result buffers: the captured step's autograd graph is not needed after the capture
-        outputs = {k: v.detach() for k, v in outputs.items() if torch.is_tensor(v)}
+        outputs = {k: v for k, v in outputs.items() if torch.is_tensor(v)}
         grads = [(p, p.grad) for p in self._params(kind)]      # None where the body produces no gradient (R1: final bias)
         hit = (graph, static_in, outputs, launches, grads)
         self.captured[key] = hit
