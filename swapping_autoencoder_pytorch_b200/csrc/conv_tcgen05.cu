@@ -1023,6 +1023,205 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent per-tap pair kernel (experimental)
+// conv_tc2_kernel (stride-2 fprop, maps too small for the shared window) with the two changes that made conv_tc5_kernel:
+// a persistent loop over (tile pair, 128-column block) work items, two accumulator buffers in TMEM and dedicated output
+// staging, so loads and MMAs of tile i+1 overlap the epilogue of tile i.  NOT YET VALIDATED ON HARDWARE: written at the
+// end of round 1 after the GPU budget was spent; off unless SAE_TC6=1 (the conv parity tests cover its shapes).
+template <int BLOCK_N>
+constexpr int tc6_stages() { return 3; }      // 3 x (16 KB A + 8 KB half-B) + 2 x 16 KB staging = 104 KB: two CTAs per SM
+
+template <int BLOCK_N>
+constexpr size_t tc6_smem_bytes() {
+    return (size_t)tc6_stages<BLOCK_N>() * (TC_A_BYTES + (BLOCK_N / 2) * 128) + (size_t)TC5_NSTG * TC_A_BYTES + 1024 + 256;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks, const int total_work) {
+    constexpr int STAGES = tc6_stages<BLOCK_N>();
+    constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_HALF_BYTES;                 // per CTA
+    constexpr uint32_t ACC_COLS = BLOCK_N;
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                           // two accumulator buffers
+    static_assert(BLOCK_N == 128, "tc6: 128-column blocks only (2 x 128 TMEM columns per CTA, two CTAs per SM)");
+    // D fp32, A/B tf32 K-major, N = BLOCK_N, M = 256 (128 rows from each CTA)
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t RING = (uint32_t)STAGES * STAGE_BYTES;
+    constexpr uint32_t STG_OFF = RING;                                     // dedicated staging behind the ring
+    constexpr uint32_t BAR_OFF = RING + (uint32_t)TC5_NSTG * TC_A_BYTES;
+    static_assert(RING % 1024u == 0, "tc6: staging must stay 1024-byte aligned");
+    constexpr int NCHUNK = BLOCK_N / 32;
+    const uint32_t bar_full = base + BAR_OFF;
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_acc = bar_empty + 8 * STAGES;              // [2]
+    const uint32_t bar_tmem_empty = bar_acc + 16;                 // [2], leader's copy in use
+    const uint32_t tmem_slot = bar_tmem_empty + 16;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    // persistent: one wave of CTA pairs loops over work items = (pair of consecutive pixel tiles, output-channel block),
+    // the channel block being the fast index so that the pairs re-reading one activation tile run together (L2 hits)
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0) {
+        const int nblk = work % n_blocks;
+        int tile = (work / n_blocks) * 2 + (int)rank;
+        const int tq = tile % p.tiles_w; tile /= p.tiles_w;
+        const int tp = tile % p.tiles_h; tile /= p.tiles_h;
+        q0 = tq * p.tw; p0 = tp * p.th; n0 = tile * p.tn; col0 = nblk * BLOCK_N;      // beyond the batch for a padding tile: all OOB
+    };
+    const int KB = p.ntaps * p.num_cblk;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
+        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                      // both CTAs' barriers exist before any remote complete_tx / commit arrives
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        if (elect_one()) {
+            int kg = 0;                                       // ring position runs on across tiles
+            for (int work = cluster_id; work < total_work; work += num_clusters) {
+            int q0, p0, n0, col0;
+            decode(work, q0, p0, n0, col0);
+            for (int kb = 0; kb < KB; ++kb, ++kg) {
+                const int s = kg % STAGES;
+                const uint32_t ph = (uint32_t)(kg / STAGES) & 1u;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                const int t = kb / p.num_cblk, cb = kb - t * p.num_cblk;
+                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+                if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
+                tma2_load_4d(sa, &map_src, bar_full + 8 * s, cb * TC_BK, q0 * p.stride + p.ox[t], p0 * p.stride + p.oy[t], n0);
+                tma2_load_2d(sb, &map_w, bar_full + 8 * s, p.wk[t] + cb * TC_BK, col0 + (int)rank * (BLOCK_N / 2));
+            }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (leader && elect_one()) {
+            int kg = 0, it = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+            // accumulator buffer (it & 1): both CTAs' epilogues must have drained its previous tile (it - 2)
+            const uint32_t buf = (uint32_t)it & 1u;
+            if (it > 1) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
+            for (int kb = 0; kb < KB; ++kb, ++kg) {
+                const int s = kg % STAGES;
+                const uint32_t ph = (uint32_t)(kg / STAGES) & 1u;
+                mbar_wait(bar_full + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)
+                    umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                umma2_commit(bar_empty + 8 * s);          // frees stage s in both CTAs
+            }
+            umma2_commit(bar_acc + 8 * buf);              // this buffer's accumulators complete in both CTAs
+            }
+        }
+    } else {
+        // ===================================================== epilogue: identical to the 1-CTA kernel (own 128 rows)
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const int iw = row % p.tw, ih = (row / p.tw) % p.th, in_ = row / (p.tw * p.th);
+        int it = 0, gch = 0;
+        for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+        int q0, p0, n0, col0;
+        decode(work, q0, p0, n0, col0);
+        const uint32_t buf = (uint32_t)it & 1u;
+        const int n = n0 + in_, pp = p0 + ih, qq = q0 + iw;
+        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
+        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
+        mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float nz = 0.f;
+        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
+#pragma unroll 1
+        for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
+            if (gch >= TC5_NSTG) {
+                // the bulk store that last read this staging buffer (TC5_NSTG chunks ago) must have finished reading it
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            float v[32];
+            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+            const int colb = col0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float t = v[j];
+                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
+                t += nz;
+                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
+                t *= p.epi.gain;
+                v[j] = t;
+            }
+            if (p.epi.residual && valid) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 r = __ldg(r4 + j);
+                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
+                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
+                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
+                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
+                }
+            }
+            if (p.epi.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+            }
+            const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
+            uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                tma_store_4d(&map_out, base + stg_off, colb, q0, p0, n0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (ch == NCHUNK - 1)      // all 128 epilogue threads are done with this accumulator buffer
+                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
+            }
+        }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                      // nobody leaves (or frees TMEM) while the peer may still touch this CTA
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle) {
@@ -1146,6 +1345,40 @@ static int tc2_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
     cfg.numAttrs = 1;
     SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks));
     return check_launch("conv_tc2");
+}
+
+// experimental persistent variant of tc2_launch (conv_tc6_kernel): SAE_TC6=1
+template <int BLOCK_N>
+static int tc6_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    TcParams p;
+    tc_fill_params(pr, e, p);
+    CUtensorMap msrc, mw, mout;
+    int rc = tc_encode_maps(pr, p, BLOCK_N / 2, &msrc, &mw, &mout);
+    if (rc) return rc;
+    constexpr size_t smem = tc6_smem_bytes<BLOCK_N>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc6_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int pairs = (tiles + 1) / 2;
+    const int n_blocks = pr.Ncol / BLOCK_N;
+    cudaLaunchConfig_t cfg = {};
+    const int total_work = pairs * n_blocks;
+    int clusters = sm_count();                       // persistent: one wave, 2 CTAs per SM, 2 CTAs per cluster
+    if (clusters > total_work) clusters = total_work;
+    cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc6_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks, total_work));
+    return check_launch("conv_tc6");
 }
 
 // shared-window pair launch: tile = 16 rows x 8 columns of one image; window = tile + tap offset range
@@ -1375,6 +1608,9 @@ static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st)
                     return tc4_launch<32>(pr, e, st);
                 }
             }
+            static int tc6 = -1;
+            if (tc6 < 0) { const char* v = getenv("SAE_TC6"); tc6 = v ? atoi(v) : 0; }     // not validated on hardware yet: opt-in
+            if (tc6 && pr.Ncol % 128 == 0) return tc6_launch<128>(pr, e, st);
             if (pr.Ncol % 256 == 0) return tc2_launch<256>(pr, e, st);
             if (pr.Ncol % 128 == 0) return tc2_launch<128>(pr, e, st);
         }
