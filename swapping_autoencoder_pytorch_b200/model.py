@@ -141,7 +141,12 @@ class SwappingAutoencoderModel(BaseModel):
         lam = self.opt.lambda_GAN
         if lam == 0.0:
             return {}
-        pred_real, pred_rec, pred_mix = self.D(real), self.D(rec), self.D(mix)
+        if getattr(self.opt, "batch_discriminator_passes", False):
+            # extension: D has no cross-sample operation, so one pass over the concatenated batch gives the same
+            # per-sample predictions with a third of the launches and fuller tiles on the small late layers
+            pred_real, pred_rec, pred_mix = self.D(torch.cat([real, rec, mix])).split([real.size(0), rec.size(0), mix.size(0)])
+        else:
+            pred_real, pred_rec, pred_mix = self.D(real), self.D(rec), self.D(mix)
         return {
             "D_real": util.gan_loss(pred_real, should_be_classified_as_real=True) * lam,
             "D_rec": util.gan_loss(pred_rec, should_be_classified_as_real=False) * (0.5 * lam),
@@ -150,9 +155,17 @@ class SwappingAutoencoderModel(BaseModel):
 
     def compute_patch_discriminator_losses(self, real, mix):
         opt = self.opt
-        real_feat = self.Dpatch.extract_features(self.get_random_crops(real), aggregate=opt.patch_use_aggregation)
-        target_feat = self.Dpatch.extract_features(self.get_random_crops(real))
-        mix_feat = self.Dpatch.extract_features(self.get_random_crops(mix))
+        if getattr(opt, "batch_discriminator_passes", False):
+            # same three crop draws in the same order (the feature extractor draws nothing), one pass over all of them
+            crops = [self.get_random_crops(real), self.get_random_crops(real), self.get_random_crops(mix)]
+            feats = self.Dpatch.extract_features(torch.cat(crops)).split([c.size(0) * c.size(1) for c in crops])
+            real_feat, target_feat, mix_feat = feats
+            if opt.patch_use_aggregation:
+                real_feat = self.Dpatch.aggregate_features(real_feat, crops[0].size(0), crops[0].size(1))
+        else:
+            real_feat = self.Dpatch.extract_features(self.get_random_crops(real), aggregate=opt.patch_use_aggregation)
+            target_feat = self.Dpatch.extract_features(self.get_random_crops(real))
+            mix_feat = self.Dpatch.extract_features(self.get_random_crops(mix))
         return {
             "PatchD_real": util.gan_loss(self.Dpatch.discriminate_features(real_feat, target_feat),
                                          should_be_classified_as_real=True) * opt.lambda_PatchGAN,
@@ -215,8 +228,12 @@ class SwappingAutoencoderModel(BaseModel):
             real, gl, sp_mix = real[b // 2:], gl[b // 2:], sp_mix[b // 2:]
         mix = self.G(sp_mix, gl)
         if opt.lambda_GAN > 0.0:
-            losses["G_GAN_rec"] = util.gan_loss(self.D(rec), should_be_classified_as_real=True) * (opt.lambda_GAN * 0.5)
-            losses["G_GAN_mix"] = util.gan_loss(self.D(mix), should_be_classified_as_real=True) * (opt.lambda_GAN * 1.0)
+            if getattr(opt, "batch_discriminator_passes", False):
+                pred_rec, pred_mix = self.D(torch.cat([rec, mix])).split([rec.size(0), mix.size(0)])
+            else:
+                pred_rec, pred_mix = self.D(rec), self.D(mix)
+            losses["G_GAN_rec"] = util.gan_loss(pred_rec, should_be_classified_as_real=True) * (opt.lambda_GAN * 0.5)
+            losses["G_GAN_mix"] = util.gan_loss(pred_mix, should_be_classified_as_real=True) * (opt.lambda_GAN * 1.0)
         if opt.lambda_PatchGAN > 0.0:
             real_feat = self.Dpatch.extract_features(self.get_random_crops(real),
                                                      aggregate=opt.patch_use_aggregation).detach()

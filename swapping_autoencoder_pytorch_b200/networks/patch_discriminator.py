@@ -65,10 +65,15 @@ class StyleGAN2PatchDiscriminator(BasePatchDiscriminator):
             b, t = patches.size(0), patches.size(1)
             flat = patches
         feat = self.convs(flat)
-        feat = feat.reshape(b, t, *feat.shape[1:])
         if aggregate:
-            feat = feat.mean(1, keepdim=True).expand(-1, t, -1, -1, -1)
-        return feat.flatten(0, 1)
+            return self.aggregate_features(feat, b, t)
+        return feat
+
+    @staticmethod
+    def aggregate_features(feat, b, t):
+        """[b*t, ...] crop features -> the mean over the t crops of each image, repeated t times (reference :156-157)"""
+        feat = feat.reshape(b, t, *feat.shape[1:])
+        return feat.mean(1, keepdim=True).expand(-1, t, -1, -1, -1).flatten(0, 1)
 
     def extract_layerwise_features(self, image):
         feats = [image]

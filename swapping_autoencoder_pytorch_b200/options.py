@@ -29,6 +29,8 @@ def default_options(**overrides):
         lr=0.002, beta1=0.0, beta2=0.99, R1_once_every=16,
         # extension (not a reference option): replay each half-step as a CUDA graph (graphs.py)
         cuda_graphs=False,
+        # extension: run D (and Dpatch in the discriminator step) once over the concatenated real / rec / mix batch
+        batch_discriminator_passes=False,
     )
     for k, v in overrides.items():
         setattr(opt, k, v)

@@ -313,3 +313,27 @@ def test_encoder_feature_extraction_against_reference():
     real = rnd(meta["real_seed"], 2, 3, 64, 64).clamp(-1, 1)
     sp, gl, feat = model.encode(real, extract_features=True)
     assert rel_err(sp, G["sp"]) < TOL and rel_err(gl, G["gl"]) < TOL and rel_err(feat, G["feature"]) < TOL
+
+
+def test_batched_discriminator_passes_give_the_same_losses_and_gradients(fp64_default):
+    """extension ``opt.batch_discriminator_passes``: D over cat(real, rec, mix) and Dpatch over the three crop sets at once
+    are per-sample identical to the reference's separate passes — same losses (same RNG draw order) and same gradients"""
+    import swapping_autoencoder_pytorch_b200 as S
+    real = rnd(900, 2, 3, 64, 64).clamp(-1, 1)
+    res = {}
+    for flag in (False, True):
+        opt = default_options(**dict(TINY, batch_discriminator_passes=flag))
+        torch.manual_seed(0)
+        model = S.create_model(opt).singlegpu_model.double()
+        for p in model.parameters():
+            p.requires_grad_(True)
+        torch.manual_seed(21)
+        dl, _, _, _ = model(real, command="compute_discriminator_losses")
+        gd = torch.autograd.grad(sum(v.mean() for v in dl.values()), [model.D.stylegan2_D.convs[1].conv1.Conv.weight,
+                                                                       model.Dpatch.convs[1].conv2.Conv.weight])
+        torch.manual_seed(22)
+        gl, _ = model(real, None, None, command="compute_generator_losses")
+        gg = torch.autograd.grad(sum(v.mean() for v in gl.values()), [model.G.ToRGB.conv.weight, model.E.FromRGB.Conv.weight])
+        res[flag] = list(dl.values()) + list(gl.values()) + list(gd) + list(gg)
+    for a, b in zip(res[False], res[True]):
+        assert rel_err(a, b) < 1e-10
