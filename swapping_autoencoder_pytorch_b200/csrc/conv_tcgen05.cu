@@ -1023,6 +1023,228 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------ conv_tc5 over several parity classes (experimental)
+// The stride-2 data gradient (and the generator's transposed convolution) is four dense stride-1 problems — the parity classes
+// of the output — over the SAME input.  conv_tc5m_kernel is conv_tc5_kernel whose work items carry a class index: each class
+// has its own tap list, output sub-grid offset and output tensor map; the input window is the union window of all taps.
+// One launch instead of four (plus strips), and the input tile of a pixel block travels from HBM once instead of four times.
+// NOT YET VALIDATED ON HARDWARE (written after round 1's GPU budget was spent): opt-in via SAE_DGRAD_MERGED=1.
+constexpr int TC_MAX_CLS = 4;
+struct TcOutMaps { CUtensorMap m[TC_MAX_CLS]; };
+struct TcClasses {
+    int ncls;
+    int ntaps[TC_MAX_CLS];
+    int wk[TC_MAX_CLS][4];
+    int o_offy[TC_MAX_CLS], o_offx[TC_MAX_CLS];
+    unsigned short arow[TC_MAX_CLS][4];
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ TcOutMaps outs, const TcParams p, const __grid_constant__ TcClasses cls, const int n_blocks,
+                 const int total_work) {
+    constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
+    constexpr int TC3_NB = tc5_nb<BLOCK_N>();
+    constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
+    constexpr uint32_t RING0 = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
+    constexpr uint32_t STG_OFF = RING0;                                  // staging follows the rings (1024-byte aligned)
+    constexpr uint32_t RING = RING0 + (uint32_t)TC5_NSTG * TC_A_BYTES;
+    constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                         // two accumulator buffers
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
+    constexpr int NCHUNK = BLOCK_N / 32;
+    static_assert(BLOCK_N <= 128 && (B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc5: layout");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_ring = base + B_RING;
+    const uint32_t bar_fullA = base + RING;
+    const uint32_t bar_emptyA = bar_fullA + 8 * TC3_NA;
+    const uint32_t bar_fullB = bar_emptyA + 8 * TC3_NA;
+    const uint32_t bar_emptyB = bar_fullB + 8 * TC3_NB;
+    const uint32_t bar_acc = bar_emptyB + 8 * TC3_NB;              // [2]: accumulator buffer b is complete
+    const uint32_t bar_tmem_empty = bar_acc + 16;                  // [2]: leader's copy in use, both CTAs' epilogues arrive on it
+    const uint32_t tmem_slot = bar_tmem_empty + 16;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const uint32_t a_bytes = (uint32_t)(p.ww * p.wh) * 128u;
+    // work item -> (pixel tile of this CTA, parity class, channel block); channel block fastest, then the class: the
+    // classes of one pixel tile run on neighbouring clusters at the same time, so only the first of them reads the tile's
+    // input window from HBM — the others find it in L2
+    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0, int& c) {
+        const int nblk = work % n_blocks;
+        const int rest = work / n_blocks;
+        c = rest % cls.ncls;
+        int tile = (rest / cls.ncls) * 2 + (int)rank;
+        const int tq = tile % p.tiles_w; tile /= p.tiles_w;
+        const int tp = tile % p.tiles_h; tile /= p.tiles_h;
+        q0 = tq * p.tw; p0 = tp * p.th; n0 = tile; col0 = nblk * BLOCK_N;
+    };
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int c = 0; c < cls.ncls; ++c) asm volatile("prefetch.tensormap [%0];" ::"l"(&outs.m[c]) : "memory");
+        for (int s = 0; s < TC3_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
+        for (int s = 0; s < TC3_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
+        mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
+        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        if (elect_one()) {
+            int ia = 0, ib = 0, it = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+                int q0, p0, n0, col0, c;
+                decode(work, q0, p0, n0, col0, c);
+                const int ntaps = cls.ntaps[c];
+                for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
+                    const int sa = ia % TC3_NA;
+                    mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC3_NA)) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
+                    tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
+                    for (int t = 0; t < ntaps; ++t, ++ib) {
+                        const int sb = ib % TC3_NB;
+                        mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
+                        if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
+                        tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, cls.wk[c][t] + cb * TC_BK,
+                                     col0 + (int)rank * (BLOCK_N / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (leader && elect_one()) {
+            const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;        // 8-row atoms are one window row apart
+            int ia = 0, ib = 0, it = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+            // accumulator buffer (it & 1): both CTAs' epilogues must have drained its previous tile (it - 2)
+            const uint32_t buf = (uint32_t)it & 1u;
+            if (it > 1) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
+            const int c = (work / n_blocks) % cls.ncls;
+            const int ntaps = cls.ntaps[c];
+            int tstep = 0;
+            for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
+                const int sa = ia % TC3_NA;
+                mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC3_NA)) & 1u);
+                const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
+                for (int t = 0; t < ntaps; ++t, ++ib, ++tstep) {
+                    const int sb = ib % TC3_NB;
+                    mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // A descriptor: start = window row arow[t]; same 128B-swizzle K-major layout, SBO = ww * 128 B
+                    const uint32_t aaddr = a0 + (uint32_t)cls.arow[c][t] * 128u;
+                    uint64_t da = (uint64_t)((aaddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | sbo | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                    const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (tstep > 0 || k > 0) ? 1u : 0u);
+                    umma2_commit(bar_emptyB + 8 * sb);
+                }
+                umma2_commit(bar_emptyA + 8 * sa);
+            }
+            umma2_commit(bar_acc + 8 * buf);
+            }
+        }
+    } else {
+        // ===================================================== epilogue (identical to the pair kernel)
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const int iw = row % p.tw, ih = row / p.tw;
+        int it = 0, gch = 0;         // gch: running chunk count -> staging buffer and bulk-group bookkeeping across tiles
+        for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+        int q0, p0, n0, col0, c;
+        decode(work, q0, p0, n0, col0, c);
+        const uint32_t buf = (uint32_t)it & 1u;
+        const int n = n0, pp = p0 + ih, qq = q0 + iw;
+        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
+        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + cls.o_offy[c]) * p.FW + qq * p.o_mul + cls.o_offx[c];
+        mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float nz = 0.f;
+        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
+#pragma unroll 1
+        for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
+            if (gch >= TC5_NSTG) {
+                // the bulk store that last read this staging buffer (TC5_NSTG chunks ago) must have finished reading it
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            float v[32];
+            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+            const int colb = col0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float t = v[j];
+                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
+                t += nz;
+                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
+                t *= p.epi.gain;
+                v[j] = t;
+            }
+            if (p.epi.residual && valid) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 r = __ldg(r4 + j);
+                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
+                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
+                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
+                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
+                }
+            }
+            if (p.epi.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+            }
+            const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
+            uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                tma_store_4d(&outs.m[c], base + stg_off, colb, q0, p0, n0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (ch == NCHUNK - 1) {
+                    // all 128 epilogue threads have finished reading TMEM: tell the leader's MMA warp (remote for rank 1)
+                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
+                }
+            }
+        }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // before the CTA retires
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ persistent per-tap pair kernel (experimental)
 // conv_tc2_kernel (stride-2 fprop, maps too small for the shared window) with the two changes that made conv_tc5_kernel:
 // a persistent loop over (tile pair, 128-column block) work items, two accumulator buffers in TMEM and dedicated output
@@ -1685,6 +1907,100 @@ int tc_fprop(const float* x, const float* w, float* y, const sae_conv_geom* g, c
     return tc_dispatch_split(pr, e, st);
 }
 
+// One conv_tc5m launch over the rectangle all four parity classes share, then each class's thin remainder strips through
+// the ordinary per-class path.  Returns SAE_E_UNSUPPORTED (quietly) when the shape is outside the merged kernel's reach.
+static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t st) {
+    const TcProblem& p0 = cp[0];
+    if (!pair_enabled() || p0.Ncol % 128 != 0 || p0.SC % 32 != 0) return SAE_E_UNSUPPORTED;
+    int MH = cp[0].OH, MW = cp[0].OW;
+    int oy_min = cp[0].oy[0], oy_max = oy_min, ox_min = cp[0].ox[0], ox_max = ox_min;
+    for (int c = 0; c < TC_MAX_CLS; ++c) {
+        if (cp[c].ntaps < 1 || cp[c].ntaps > 4) return SAE_E_UNSUPPORTED;
+        MH = cp[c].OH < MH ? cp[c].OH : MH; MW = cp[c].OW < MW ? cp[c].OW : MW;
+        for (int t = 0; t < cp[c].ntaps; ++t) {
+            oy_min = cp[c].oy[t] < oy_min ? cp[c].oy[t] : oy_min; oy_max = cp[c].oy[t] > oy_max ? cp[c].oy[t] : oy_max;
+            ox_min = cp[c].ox[t] < ox_min ? cp[c].ox[t] : ox_min; ox_max = cp[c].ox[t] > ox_max ? cp[c].ox[t] : ox_max;
+        }
+    }
+    if (MH < 16 || MW < 8 || oy_max - oy_min > 2 || ox_max - ox_min > 2) return SAE_E_UNSUPPORTED;
+    if ((int64_t)p0.SN * MH * MW < 2 * 128) return SAE_E_UNSUPPORTED;
+
+    TcProblem main = p0;                       // geometry of the shared rectangle (taps / offsets come from the class tables)
+    main.OH = MH; main.OW = MW;
+    TcParams p;
+    tc_fill_params(main, e, p);
+    p.tw = 8; p.th = 16; p.tn = 1;
+    p.tiles_w = (MW + p.tw - 1) / p.tw;
+    p.tiles_h = (MH + p.th - 1) / p.th;
+    p.tiles_n = main.SN;
+    p.oy_min = oy_min; p.ox_min = ox_min;
+    p.ww = p.tw + (ox_max - ox_min);
+    p.wh = p.th + (oy_max - oy_min);
+    TcClasses cls;
+    TcOutMaps outs;
+    cls.ncls = TC_MAX_CLS;
+    CUtensorMap msrc, mw, mdummy;
+    int rc = tc_encode_maps(main, p, 128 / 2, &msrc, &mw, &mdummy);      // weight map (the others are rebuilt below)
+    if (rc) return rc;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)main.SC, (cuuint64_t)main.SW, (cuuint64_t)main.SH, (cuuint64_t)main.SN};
+        cuuint64_t strides[3] = {(cuuint64_t)main.SC * 4, (cuuint64_t)main.SW * main.SC * 4, (cuuint64_t)main.SH * main.SW * main.SC * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.ww, (cuuint32_t)p.wh, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        rc = encode_map(&msrc, main.src, 4, dims, strides, box, es);
+        if (rc) return rc;
+    }
+    for (int c = 0; c < TC_MAX_CLS; ++c) {
+        const TcProblem& q = cp[c];
+        cls.ntaps[c] = q.ntaps;
+        cls.o_offy[c] = q.o_offy; cls.o_offx[c] = q.o_offx;
+        for (int t = 0; t < 4; ++t) { cls.wk[c][t] = 0; cls.arow[c][t] = 0; }
+        for (int t = 0; t < q.ntaps; ++t) {
+            cls.wk[c][t] = q.wk[t];
+            cls.arow[c][t] = (unsigned short)((q.oy[t] - oy_min) * p.ww + (q.ox[t] - ox_min));
+        }
+        // output sub-grid of class c restricted to the shared MH x MW rectangle (the tensor map's extent clips the stores)
+        cuuint64_t dims[4] = {(cuuint64_t)q.Ncol, (cuuint64_t)MW, (cuuint64_t)MH, (cuuint64_t)q.SN};
+        cuuint64_t strides[3] = {(cuuint64_t)q.o_mul * q.Ncol * 4, (cuuint64_t)q.o_mul * q.FW * q.Ncol * 4,
+                                 (cuuint64_t)q.FH * q.FW * q.Ncol * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        rc = encode_map(&outs.m[c], q.out + ((int64_t)q.o_offy * q.FW + q.o_offx) * q.Ncol, 4, dims, strides, box, es);
+        if (rc) return rc;
+    }
+    constexpr size_t smem = tc5_smem_bytes<128>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5m_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int n_blocks = main.Ncol / 128;
+    const int total_work = ((tiles + 1) / 2) * TC_MAX_CLS * n_blocks;
+    int clusters = sm_count();
+    if (clusters > total_work) clusters = total_work;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<128>, msrc, mw, outs, p, cls, n_blocks, total_work));
+    rc = check_launch("conv_tc5m");
+    if (rc) return rc;
+    // remainders of each class beyond the shared rectangle: right strip (full height, takes the corner), bottom strip
+    for (int c = 0; c < TC_MAX_CLS; ++c) {
+        const TcProblem& q = cp[c];
+        if (MW < q.OW) { rc = tc_dispatch(tc_subproblem(q, 0, q.OH, MW, q.OW), e, st); if (rc) return rc; }
+        if (MH < q.OH) { rc = tc_dispatch(tc_subproblem(q, MH, q.OH, 0, MW), e, st); if (rc) return rc; }
+    }
+    return SAE_OK;
+}
+
 int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g, const EpiParams& e, cudaStream_t st) {
     if (!ptr_ok(dy, wt, dx)) return fail(SAE_E_INVALID, "conv2d_dgrad(tcgen05): pointers must be 16-byte aligned");
     TcProblem pr;
@@ -1713,6 +2029,8 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
             if (rp >= g->R || sp >= g->S) need_zero = true;
         }
     if (need_zero) SAE_CUDA_TRY(cudaMemsetAsync(dx, 0, (size_t)g->N * g->H * g->W * g->C * sizeof(float), st));
+    TcProblem cls_pr[TC_MAX_CLS];
+    int ncls = 0;
     for (int ho = 0; ho < 2; ++ho)
         for (int wo = 0; wo < 2; ++wo) {
             const int rp = (ho + g->pad_t) & 1, sp = (wo + g->pad_l) & 1;
@@ -1731,9 +2049,18 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
                     ++nt;
                 }
             pr.ntaps = nt;
-            int rc = tc_dispatch_split(pr, e, st);
-            if (rc) return rc;
+            cls_pr[ncls++] = pr;
         }
+    static int merged = -1;
+    if (merged < 0) { const char* v = getenv("SAE_DGRAD_MERGED"); merged = v ? atoi(v) : 0; }     // not validated on hardware yet
+    if (merged && ncls == TC_MAX_CLS && !need_zero) {
+        int rc = tc_dgrad_merged(cls_pr, e, st);
+        if (rc != SAE_E_UNSUPPORTED) return rc;
+    }
+    for (int c = 0; c < ncls; ++c) {
+        int rc = tc_dispatch_split(cls_pr[c], e, st);
+        if (rc) return rc;
+    }
     return SAE_OK;
 }
 
