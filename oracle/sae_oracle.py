@@ -62,7 +62,7 @@ def upfirdn2d(x, k, up=1, down=1, pad=(0, 0)):
     u = u.reshape(b * c, 1, h * up, w * up)
     u = F.pad(u, [max(p0, 0), max(p1, 0), max(p0, 0), max(p1, 0)])
     u = u[:, :, max(-p0, 0):u.shape[2] - max(-p1, 0), max(-p0, 0):u.shape[3] - max(-p1, 0)]
-    out = F.conv2d(u, torch.flip(k, [0, 1]).to(x.dtype).view(1, 1, kh, kw))
+    out = F.conv2d(u, torch.flip(k, [0, 1]).to(x).view(1, 1, kh, kw))
     out = out[:, :, ::down, ::down]
     return out.reshape(b, c, out.shape[2], out.shape[3])
 
@@ -127,7 +127,7 @@ def conv_layer(P, name, x, kernel_size, downsample=False, blur_taps=(1, 3, 3, 1)
         if reflection_pad:
             x = F.pad(x, (p0, p1, p0, p1), mode="reflect")
             p0 = p1 = 0
-        x = upfirdn2d(x, k.to(x.dtype), pad=(p0, p1))
+        x = upfirdn2d(x, k.to(x), pad=(p0, p1))
         stride, padding = 2, 0
     else:
         stride = 1
@@ -172,7 +172,7 @@ def modulated_conv2d(P, name, x, style, kernel_size, demodulate=True, upsample=F
         k = P.get(name + ".blur.kernel")
         if k is None:
             k = make_kernel(list(blur_taps), x.dtype) * 4
-        return upfirdn2d(out, k.to(x.dtype), pad=((p + 1) // 2 + 1, p // 2 + 1))
+        return upfirdn2d(out, k.to(x), pad=((p + 1) // 2 + 1, p // 2 + 1))
     return F.conv2d(x, w, padding=kernel_size // 2)
 
 
@@ -181,7 +181,7 @@ def styled_conv(P, name, x, style, upsample=False, use_noise=True, noise=None, b
     out = modulated_conv2d(P, name + ".conv", x, style, 3, upsample=upsample, blur_taps=blur_taps)
     if use_noise:
         if noise is None:
-            noise = torch.randn(out.shape[0], 1, out.shape[2], out.shape[3], dtype=out.dtype)
+            noise = torch.randn(out.shape[0], 1, out.shape[2], out.shape[3], dtype=out.dtype).to(out.device)
         out = out + P[name + ".noise.weight"] * noise
     return fused_leaky_relu(out, P[name + ".activate.bias"])
 
@@ -326,8 +326,8 @@ def random_crops(x, opt):
     n = opt.patch_num_crops
     size = opt.patch_size
     B = x.size(0) * n
-    flip, scale, offset = (t.to(x.dtype) for t in draw_crop_parameters(B, opt))
-    lin = torch.linspace(-1.0, 1.0, size, dtype=x.dtype)
+    flip, scale, offset = (t.to(x) for t in draw_crop_parameters(B, opt))      # drawn on the host: one RNG stream
+    lin = torch.linspace(-1.0, 1.0, size, dtype=x.dtype).to(x.device)
     gx = lin.view(1, 1, size, 1).expand(B, size, size, 1)
     gy = lin.view(1, size, 1, 1).expand(B, size, size, 1)
     unit = torch.cat([gx * flip, gy], dim=3)

@@ -111,6 +111,10 @@ class HalfStepGraphs:
             self._finish_eagerly(kind)
         return dict(outputs)
 
+    def describe(self, world):
+        """one-line account of what a replay contains (bench.py reports it)"""
+        return "forward+backward+Adam per replay" if world == 1 else "forward+backward per replay; all-reduce and Adam eager"
+
     def _select_group(self, kind):
         t = self.trainer
         t.set_requires_grad(t.Dparams, kind != "G")

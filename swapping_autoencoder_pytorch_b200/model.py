@@ -12,7 +12,7 @@ import torch
 
 from . import networks, util
 from .stylegan2_op import filter_reuse
-from .stylegan2_op.blocks import per_operator_blocks
+from .stylegan2_op.blocks import data_gradients_only
 
 
 class BaseModel(torch.nn.Module):
@@ -188,7 +188,9 @@ class SwappingAutoencoderModel(BaseModel):
     def compute_R1_loss(self, real):
         """R1 gradient penalty on D (w.r.t. the image) and on Dpatch (w.r.t. both crop sets); needs the
         second-order autograd of every op in D / Dpatch (reference :138-185)."""
-        with per_operator_blocks():      # the backward is differentiated again: block-level nodes would only recompute
+        # both autograd.grad calls below ask for gradients with respect to images / crops only: the recorded backward skips
+        # weight gradients and the fused blocks take their closed-form double backward (stylegan2_op/blocks.py)
+        with data_gradients_only():
             return self._compute_R1_loss(real)
 
     def _compute_R1_loss(self, real):

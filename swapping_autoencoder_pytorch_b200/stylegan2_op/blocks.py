@@ -6,15 +6,27 @@ blurred ``skip`` branch, so every backward pays a read-read-write pass over the 
 (1.07 GB at 128 channels x 256 x 256 x 32 images).  A hand-ordered block backward lets the last data-gradient kernel add
 the other branch's gradient in its epilogue (``residual`` of the conv kernels) — the sum never exists as a pass.
 
-Second order (R1, reference swapping_autoencoder_model.py:138-185): when the backward itself is being recorded
-(``create_graph=True``), the Function re-evaluates the block with the per-operator differentiable Functions of
-conv.py / fused_act.py / upfirdn2d.py and differentiates THAT, so the double-backward graph is exactly the unfused one
-(one extra block forward, only in the lazy-R1 step).
+Second order (R1, reference swapping_autoencoder_model.py:138-185).  The R1 penalty differentiates the gradient of the
+prediction with respect to the IMAGE (or the crops): ``autograd.grad(pred, [real], create_graph=True)`` then
+``penalty.backward()``.  A discriminator is piecewise linear in its input — bilinear convolutions, linear FIRs, and leaky-ReLU
+masks that are constant almost everywhere — so for a block  y = M2 C2 B2 M1 C1 x + Cs Bs x  (C: conv, B: blur, M: mask x gain)
+
+    first backward      dx = C1' M1 B2' C2' M2 dy + Bs' Cs' dy                         (the fused data-gradient chain)
+    second backward     given the cotangent v of dx:
+                          d(dy) = M2 C2 B2 M1 C1 v + Cs Bs v                           (the block's forward on v, saved masks)
+                          dW1 = wgrad(M1 B2' C2' M2 dy, v)    dW2 = wgrad(M2 dy, B2 M1 C1 v)    dWs = wgrad(dy, Bs v)
+
+i.e. forward + data-gradient chain + tangent forward + one weight gradient per conv = 4 forward-equivalents, all on the
+block's fused kernels (``_ResBlockDataGrad``).  That path is taken inside ``data_gradients_only()`` — the scope
+``compute_R1_loss`` opens to say that recorded backward passes are asked for data gradients only.  Outside that scope a
+recorded backward re-evaluates the block with the per-operator differentiable Functions of conv.py / fused_act.py /
+upfirdn2d.py and differentiates THAT (general, slower; what the reference's own unchanged model file gets).
 """
 import os
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from .. import backend
 from ..backend import make_geom
@@ -45,6 +57,20 @@ class per_operator_blocks:
 
     def __exit__(self, *exc):
         set_fused_blocks(self.prev)
+        return False
+
+
+class data_gradients_only:
+    """``with data_gradients_only():`` — promise of the caller (compute_R1_loss) that every backward pass recorded inside the
+    scope (``create_graph=True``) is asked for gradients with respect to activations only (the image, the crops).  The
+    recorded backward then skips the weight / bias gradients it would otherwise compute, record and throw away, and the
+    fused blocks use their closed-form double backward."""
+
+    def __enter__(self):
+        self.prev = C.set_data_gradients_only(True)
+
+    def __exit__(self, *exc):
+        C.set_data_gradients_only(self.prev)
         return False
 
 
@@ -114,6 +140,53 @@ def resblock_unfused(x, w1, b1, w2, b2, ws, spec):
     return C.conv2d_residual(h, ws, o2, 1.0, stride=1, padding=0, wscale=spec.ss)
 
 
+class _ResBlockDataGrad(Function):
+    """dx of the fused block as a differentiable function of (dy, w1, w2, ws): the recorded form of the block's data
+    gradient inside ``data_gradients_only()``.  Its backward is the closed form in the module docstring."""
+
+    @staticmethod
+    def forward(ctx, dy, w1, w2, ws, o1, o2, w1k, w1t, w2k, w2t, wsk, wst, spec, geoms):
+        k = backend.kernels()
+        g1, g2, gs = geoms
+        dyh = _nhwc(dy)
+        gi2, _, _ = k.bias_act_backward(dyh, o2, spec.slope, spec.gain2, want_bias=False)
+        dh = k.conv_dgrad(dyh, wsk, gs, w_crsk=wst)
+        dxs = spec.blur_s.adjoint(k, dh, g1.H, g1.W)
+        dbl = k.conv_dgrad(gi2, w2k, g2, w_crsk=w2t)
+        gi1, _ = spec.blur2.adjoint_into_activation(k, dbl, o1, spec.slope, spec.gain1, False)
+        dx = k.conv_dgrad(gi1, w1k, g1, w_crsk=w1t, residual=dxs, res_scale=1.0)
+        ctx.spec, ctx.geoms = spec, geoms
+        ctx.save_for_backward(dyh, gi2, gi1, o1, o2, w1k, w2k, wsk)
+        return _nchw(dx)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, v):
+        dyh, gi2, gi1, o1, o2, w1k, w2k, wsk = ctx.saved_tensors
+        spec = ctx.spec
+        g1, g2, gs = ctx.geoms
+        k = backend.kernels()
+        need = ctx.needs_input_grad
+        vh = _nhwc(v)
+        # tangent forward through the linearised block: no biases, the saved leaky-ReLU masks
+        r = None
+        if need[0] or need[2]:
+            p1 = k.conv_fprop(vh, w1k, g1, prepared=True)
+            q1, _, _ = k.bias_act_backward(p1, o1, spec.slope, spec.gain1, want_bias=False)
+            r = spec.blur2.forward(k, q1)
+        hv = spec.blur_s.forward(k, vh) if (need[0] or need[3]) else None
+        d_dy = None
+        if need[0]:
+            p2 = k.conv_fprop(r, w2k, g2, prepared=True)
+            m2, _, _ = k.bias_act_backward(p2, o2, spec.slope, spec.gain2, want_bias=False)
+            d_dy = _nchw(k.conv_fprop(hv, wsk, gs, prepared=True, residual=m2, res_scale=1.0))
+        unprep = k.filter_unprep
+        dw1 = unprep(k.conv_wgrad(gi1, vh, g1), spec.s1) if need[1] else None
+        dw2 = unprep(k.conv_wgrad(gi2, r, g2), spec.s2) if need[2] else None
+        dws = unprep(k.conv_wgrad(dyh, hv, gs), spec.ss) if need[3] else None
+        return (d_dy, dw1, dw2, dws) + (None,) * 10
+
+
 class _ResBlockFused(Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, ws, spec):
@@ -142,8 +215,14 @@ class _ResBlockFused(Function):
         x, w1, b1, w2, b2, ws, o1, bl, o2, h, w1k, w1t, w2k, w2t, wsk, wst = ctx.saved_tensors
         spec = ctx.spec
         need = ctx.needs_input_grad
+        if torch.is_grad_enabled() and C.data_gradients_only_active():
+            # R1: the recorded backward is asked for dx only; closed-form double backward (module docstring)
+            dx = None
+            if need[0]:
+                dx = _ResBlockDataGrad.apply(dy, w1, w2, ws, o1, o2, w1k, w1t, w2k, w2t, wsk, wst, spec, ctx.geoms)
+            return (dx, None, None, None, None, None, None)
         if torch.is_grad_enabled():
-            # the backward is being recorded (R1): differentiate the per-operator composition instead
+            # the backward is being recorded by a general caller: differentiate the per-operator composition instead
             ins = [t for t, nd in zip((x, w1, b1, w2, b2, ws), need) if nd]
             with torch.enable_grad():
                 y = resblock_unfused(x, w1, b1, w2, b2, ws, spec)

@@ -21,6 +21,26 @@ from .. import backend
 from ..backend import make_geom
 
 
+_data_only = [False]
+
+
+def set_data_gradients_only(flag):
+    """see blocks.data_gradients_only; returns the previous value"""
+    prev, _data_only[0] = _data_only[0], bool(flag)
+    return prev
+
+
+def data_gradients_only_active():
+    return _data_only[0]
+
+
+def _want_wgrad(ctx, idx):
+    """weight gradient of a conv Function's backward: skipped when the backward is being recorded inside
+    ``data_gradients_only()`` (R1's first backward needs the data gradient only; the weight gradient would be computed,
+    recorded and thrown away — one forward-equivalent of tensor work per convolution)"""
+    return ctx.needs_input_grad[idx] and not (_data_only[0] and torch.is_grad_enabled())
+
+
 def _nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
@@ -118,7 +138,7 @@ class _ConvFprop(Function):
     def backward(ctx, dy):
         x, w, wt = ctx.saved_tensors
         dx = _ConvDgrad.apply(dy, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
-        dw = _ConvWgrad.apply(dy, x, ctx.g) if ctx.needs_input_grad[1] else None
+        dw = _ConvWgrad.apply(dy, x, ctx.g) if _want_wgrad(ctx, 1) else None
         return dx, dw, None, None
 
 
@@ -174,9 +194,12 @@ class _ConvBiasAct(Function):
     def backward(ctx, dy):
         from .fused_act import FusedLeakyReLUFunctionBackward
         x, w, wt, out = ctx.saved_tensors
-        gi, gb = FusedLeakyReLUFunctionBackward.apply(dy, out, *ctx.cfg)
+        # out.detach(): the mask is piecewise constant (the masked-gradient Function returns no gradient for it), but an
+        # attached ``out`` would keep this node's own forward graph reachable from a recorded backward, and the engine
+        # would then run a complete extra backward of the network on materialised zeros during R1's second backward
+        gi, gb = FusedLeakyReLUFunctionBackward.apply(dy, out.detach(), *ctx.cfg)
         dx = _ConvDgrad.apply(gi, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
-        dw = _ConvWgrad.apply(gi, x, ctx.g) if ctx.needs_input_grad[1] else None
+        dw = _ConvWgrad.apply(gi, x, ctx.g) if _want_wgrad(ctx, 1) else None
         return dx, dw, None, gb, None, None, None
 
 
@@ -226,7 +249,7 @@ class _ConvResidual(Function):
         x, w, wt = ctx.saved_tensors
         gs = dy if ctx.scale == 1.0 else _AddScale.apply(dy, None, ctx.scale)
         dx = _ConvDgrad.apply(gs, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
-        dw = _ConvWgrad.apply(gs, x, ctx.g) if ctx.needs_input_grad[1] else None
+        dw = _ConvWgrad.apply(gs, x, ctx.g) if _want_wgrad(ctx, 1) else None
         return dx, dw, None, (gs if ctx.needs_input_grad[3] else None), None, None
 
 

@@ -55,7 +55,8 @@ class FusedLeakyReLUFunction(Function):
     def backward(ctx, grad_output):
         out, = ctx.saved_tensors
         negative_slope, scale = ctx.cfg
-        grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(grad_output, out, negative_slope, scale)
+        # detached mask: see _ConvBiasAct.backward (stylegan2_op/conv.py)
+        grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(grad_output, out.detach(), negative_slope, scale)
         return grad_input, grad_bias, None, None
 
 

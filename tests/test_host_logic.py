@@ -1,10 +1,12 @@
 """CPU: the product's host-side logic (autograd Functions incl. double backward, layer wiring, state_dict contract,
 loss graph) on an oracle-backed emulation of the kernel interface, against the reference's golden numbers (fp64)."""
+import contextlib
+
 import pytest
 import torch
 
 from oracle.fixtures import TINY, load_golden, perturbed_state_dict, rel_err, rnd
-from swapping_autoencoder_pytorch_b200 import default_options
+from swapping_autoencoder_pytorch_b200 import backend, default_options
 
 TOL = 1e-9
 pytestmark = pytest.mark.usefixtures("emulated_kernels")
@@ -337,3 +339,52 @@ def test_batched_discriminator_passes_give_the_same_losses_and_gradients(fp64_de
         res[flag] = list(dl.values()) + list(gl.values()) + list(gd) + list(gg)
     for a, b in zip(res[False], res[True]):
         assert rel_err(a, b) < 1e-10
+
+
+def test_resblock_closed_form_double_backward_matches_autograd():
+    """stylegan2_op/blocks.py ``_ResBlockDataGrad``: inside ``data_gradients_only()`` (what compute_R1_loss opens) the block's
+    recorded backward is the fused data-gradient chain and its backward the closed form (tangent forward + one weight
+    gradient per conv).  Against ordinary autograd through the per-operator nodes: dx, the R1-style second-order gradients
+    with respect to all three filters AND with respect to the upstream gradient (what the next block receives); biases get
+    no gradient on either path."""
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import blocks
+    m = _load(L.ResBlock(8, 12), {"conv1.Conv.weight": rnd(1, 8, 8, 3, 3), "conv1.Act.bias": rnd(2, 8) * 0.1,
+                                  "conv2.Conv.weight": rnd(3, 12, 8, 3, 3), "conv2.Act.bias": rnd(4, 12) * 0.1,
+                                  "skip.Conv.weight": rnd(5, 12, 8, 1, 1)})
+    weights = [m.conv1.Conv.weight, m.conv2.Conv.weight, m.skip.Conv.weight]
+    biases = [m.conv1.Act.bias, m.conv2.Act.bias]
+    res = {}
+    for mode in ("closed_form", "per_operator"):
+        prev = blocks.set_fused_blocks(mode == "closed_form")
+        try:
+            x = rnd(6, 2, 8, 12, 10).requires_grad_()
+            w = rnd(7, 2, 12, 6, 5).requires_grad_()
+            scope = blocks.data_gradients_only() if mode == "closed_form" else contextlib.nullcontext()
+            with scope:
+                gx, = torch.autograd.grad((m(x) * w).sum(), x, create_graph=True)
+                second = torch.autograd.grad(gx.pow(2).sum(), weights + [w] + biases, allow_unused=True)
+            assert all(g is None or float(g.abs().max()) == 0.0 for g in second[4:])      # masks are constant a.e.
+            res[mode] = [gx.detach()] + list(second[:4])
+        finally:
+            blocks.set_fused_blocks(prev)
+    for a, b in zip(res["closed_form"], res["per_operator"]):
+        assert rel_err(a, b) < 1e-12
+    # the scope also stops the per-operator conv nodes from computing weight gradients in a recorded backward
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import conv as C
+    calls = []
+    k = backend.kernels()
+    orig = k.conv_wgrad
+    k.conv_wgrad = lambda *a, **kw: (calls.append(1), orig(*a, **kw))[1]
+    try:
+        prev = blocks.set_fused_blocks(False)
+        x = rnd(6, 2, 8, 12, 10).requires_grad_()
+        with blocks.data_gradients_only():
+            gx, = torch.autograd.grad(m(x).sum(), x, create_graph=True)
+            assert not calls
+            gx.pow(2).sum().backward()
+        assert len(calls) == 3
+    finally:
+        blocks.set_fused_blocks(prev)
+        k.conv_wgrad = orig
+    assert not C.data_gradients_only_active()
