@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 11
+#define SAE_ABI_VERSION 12
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -106,6 +106,18 @@ int sae_fir_act_backward(const float* grad, const float* taps_y, const float* ta
                          float* grad_in, float* grad_bias, int64_t major, int in_h, int in_w, int minor,
                          int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                          float alpha, float scale, int round_tf32, void* stream);
+
+/* sae_upfirdn2d_separable (up = down = 1) followed by NoiseInjection + bias + leaky-ReLU, in ONE pass:
+ *   out = lrelu(FIR(x) + noise_weight * noise[pixel] + bias[c], alpha) * scale
+ * — the Blur behind the generator's transposed modulated convolution and the StyledConv tail after it
+ * (stylegan2_layers.py:306-309 self.blur(out), then :398-405 noise -> FusedLeakyReLU; fused_act.py:89-96):
+ * the blurred activation never travels through HBM.  x: [major, in_h, in_w, minor]; out: [major, out_h, out_w, minor];
+ * noise: one value per OUTPUT pixel ([major, out_h, out_w]) or NULL; bias: [minor] or NULL.  taps are HOST arrays,
+ * unflipped.  Returns SAE_E_UNSUPPORTED outside the TMA-tiled configuration (minor % 32 == 0, outputs >= 8 x 8). */
+int sae_fir_bias_act(const float* x, const float* taps_y, const float* taps_x, const float* bias, const float* noise,
+                     const float* noise_weight, float* out, int64_t major, int in_h, int in_w, int minor,
+                     int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                     float alpha, float scale, int round_tf32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * modulate — x_s[n,h,w,c] = x[n,h,w,c] * s[n,c]: the "input * style" step of
@@ -225,6 +237,58 @@ int sae_bucket_pack(const float* const* ptrs, const int64_t* offsets, const int6
                     float* bucket, int64_t total, void* stream);
 int sae_bucket_unpack(float* const* ptrs, const int64_t* offsets, const int64_t* sizes, int n,
                       const float* bucket, int64_t total, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-tensor Adam.  Replaces the two torch.optim.Adam instances of
+ * optimizers/swapping_autoencoder_optimizer.py:34-42 with one launch per parameter group.
+ * torch.optim.Adam semantics (amsgrad off, no weight decay):  for every tensor t with g_ptrs[t] != NULL
+ *   steps[t] += 1;  m += (1 - beta1)(g - m);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^steps[t]) * m / (sqrt(v) / sqrt(1 - beta2^steps[t]) + eps),        g = grad_scale * *g_ptrs[t]
+ * a NULL gradient pointer skips the tensor and leaves its step count alone (a parameter whose .grad is None).
+ * p_ptrs / g_ptrs: device arrays of n pointers; offsets / sizes: device arrays of n int64 (elements) locating each
+ * tensor's moments inside the flat exp_avg / exp_avg_sq buffers; steps: device array of n floats.
+ * g_ptrs may point into the flat all-reduce bucket (sae_bucket_pack) with grad_scale = 1 / world: the gradient
+ * average is then never written back to the per-parameter gradient tensors.
+ * ------------------------------------------------------------------------------------------ */
+int sae_adam_step(float* const* p_ptrs, const float* const* g_ptrs, const int64_t* offsets, const int64_t* sizes, int n,
+                  float* exp_avg, float* exp_avg_sq, float* steps, float lr, float beta1, float beta2, float eps,
+                  float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Random-crop resampler of the patch discriminator.  Replaces
+ *   apply_random_crop: affine sampling grid + F.grid_sample(bilinear, zeros padding, align_corners=False)
+ *   (util/util.py:323-343, called from models/swapping_autoencoder_model.py:100-103)
+ * and the channel pad / layout copy in front of the first Dpatch convolution (patch_discriminator.py:146-158).
+ * x: source images, logical [B, C, H, W] addressed through element strides (any layout), C <= 4.
+ * Crop q (Q = B * num_crops of them, q / num_crops = source image) samples
+ *   gx = (lin_j * flip[q]) * scale[q][0] + offset[q][0],  gy = lin_i * scale[q][1] + offset[q][1],  lin = linspace(-1, 1, S)
+ * out: NHWC [Q, S, S, CP] with channels C..CP-1 written as zeros (CP % 4 == 0), optionally TF32-rounded.
+ * sae_crop_gather_backward: the adjoint in gather form (no atomics, deterministic): dx [B, C, H, W] contiguous is
+ * OVERWRITTEN with the sum over each image's crops; dy is addressed through element strides (n, c, h, w).
+ * ------------------------------------------------------------------------------------------ */
+int sae_crop_gather(const float* x, const float* flip, const float* scale, const float* offset, float* out,
+                    int Q, int num_crops, int C, int H, int W, int S, int CP,
+                    int64_t xs_n, int64_t xs_c, int64_t xs_h, int64_t xs_w, int round_tf32, void* stream);
+int sae_crop_gather_backward(const float* dy, const float* flip, const float* scale, const float* offset, float* dx,
+                             int Q, int num_crops, int C, int H, int W, int S,
+                             int64_t ds_n, int64_t ds_c, int64_t ds_h, int64_t ds_w, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ToRGB — the generator's final 1x1 style-modulated convolution without demodulation, as a bandwidth kernel.
+ * Replaces ToRGB.forward -> ModulatedConv2d(in_channel, 3, 1, demodulate=False) + bias
+ *   (models/networks/stylegan2_layers.py:408-427, :266-325: input * style, grouped F.conv2d, + bias).
+ * forward:  y[n,p,o] = bias[o] + sum_c x[n,p,c] * (wscale * s[n,c] * w[o,c]),  o < 3;  y is NHWC with 4 channels (4th = 0).
+ *   x [N,H,W,C] NHWC, s [N,C], w [3,C], bias [3] or NULL; C % 4 == 0, C <= 1024.  x is read once; nothing else is large.
+ * backward (one pass over x): dx[n,p,c] = sum_o dy[n,p,o] * wscale * s[n,c] * w[o,c]   (NHWC, optional)
+ *                             gw[n,o,c] += sum_p dy[n,p,o] * x[n,p,c]                   ([N,3,C], zero-initialised, optional)
+ *   dy is addressed through element strides (n, c, h, w).  The caller forms d s = wscale * sum_o gw * w and
+ *   d w = wscale * sum_n gw * s from the [N,3,C] values.
+ * ------------------------------------------------------------------------------------------ */
+int sae_torgb_forward(const float* x, const float* s, const float* w, const float* bias, float* y,
+                      int N, int H, int W, int C, float wscale, int round_tf32, void* stream);
+int sae_torgb_backward(const float* dy, const float* x, const float* s, const float* w, float* dx, float* gw,
+                       int N, int H, int W, int C, float wscale,
+                       int64_t ds_n, int64_t ds_c, int64_t ds_h, int64_t ds_w, int round_tf32, void* stream);
 
 #ifdef __cplusplus
 }

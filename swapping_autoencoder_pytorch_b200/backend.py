@@ -47,6 +47,58 @@ def _need_cuda(*ts, strided=False):
             raise _lib.SaeError("sae_b200 kernels need contiguous NHWC storage")
 
 
+class PointerTables:
+    """Device copies of host address lists (tuples of ``data_ptr()``), cached by content.  The pinned staging rows are
+    allocated up front — a miss costs a device allocation and an async copy, so a miss inside a CUDA-graph capture is legal:
+    the copy becomes a memcpy node that re-reads its pinned row on every replay.  Rows filled during a capture are therefore
+    permanent; rows filled in eager execution (where the caching allocator may hand the gradients new addresses now and
+    then) are recycled round-robin, each guarded by an event so a row is never rewritten before its copy has run."""
+
+    def __init__(self, n, device, eager_rows=24, capture_rows=24):
+        self.n, self.device = n, device
+        self.eager_rows, self.capture_rows = eager_rows, capture_rows
+        cuda = device.type == "cuda"
+        self.pinned = torch.zeros(eager_rows + capture_rows, max(n, 1), dtype=torch.int64).pin_memory() if cuda else None
+        self.eager, self.captured = {}, {}
+        self.row_key, self.row_event = [None] * eager_rows, [None] * eager_rows
+        self.next_row, self.next_capture = 0, 0
+
+    def _upload(self, row, key):
+        row[:len(key)].copy_(torch.tensor(key, dtype=torch.int64))
+        dev = torch.empty(len(key), dtype=torch.int64, device=self.device)
+        dev.copy_(row[:len(key)], non_blocking=True)
+        return dev
+
+    def get(self, key):
+        hit = self.captured.get(key)
+        if hit is None:
+            hit = self.eager.get(key)
+        if hit is not None:
+            return hit
+        if self.pinned is None:
+            hit = torch.tensor(key, dtype=torch.int64)
+            self.eager[key] = hit
+            return hit
+        if torch.cuda.is_current_stream_capturing():
+            if self.next_capture >= self.capture_rows:
+                raise _lib.SaeError("PointerTables: more than %d address lists captured into CUDA graphs" % self.capture_rows)
+            hit = self._upload(self.pinned[self.eager_rows + self.next_capture], key)
+            self.next_capture += 1
+            self.captured[key] = hit
+            return hit
+        r = self.next_row
+        self.next_row = (r + 1) % self.eager_rows
+        if self.row_key[r] is not None:
+            self.eager.pop(self.row_key[r], None)
+            self.row_event[r].synchronize()
+        hit = self._upload(self.pinned[r], key)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.row_key[r], self.row_event[r] = key, ev
+        self.eager[key] = hit
+        return hit
+
+
 class CudaKernels:
     """The product path: every method is one (or two) launches of hand-written sm_100a kernels."""
     name = "cuda"
@@ -135,6 +187,28 @@ class CudaKernels:
             return None
         check(rc, "sae_fir_act_backward")
         return gi, gb
+
+    def fir_bias_act(self, x, taps, pad, bias, noise, noise_weight, alpha, scale):
+        """lrelu(FIR(x) + noise_weight * noise + bias) * scale in one pass, or None when the shape is outside the fused kernel's
+        configuration (the caller then runs upfirdn2d + bias_act).  x [N,h,w,C]; taps = (taps_y, taps_x) host factors;
+        pad = (x0, x1, y0, y1); noise: one value per output pixel or None."""
+        _need_cuda(x, bias, noise, noise_weight)
+        n, h, w, c = x.shape
+        kh, kw = len(taps[0]), len(taps[1])
+        px0, px1, py0, py1 = pad
+        oh, ow = h + py0 + py1 - kh + 1, w + px0 + px1 - kw + 1
+        if c % 32 != 0 or kh != kw or kh not in (3, 4) or oh < 8 or ow < 8 or n == 0 or x.data_ptr() % 16 != 0:
+            return None
+        out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
+        ty = (ctypes.c_float * kh)(*taps[0])
+        tx = (ctypes.c_float * kw)(*taps[1])
+        with torch.cuda.device(x.device):
+            rc = self.lib.sae_fir_bias_act(_ptr(x), ty, tx, _ptr(bias), _ptr(noise), _ptr(noise_weight), _ptr(out), n, h, w, c,
+                                           kh, kw, px0, px1, py0, py1, alpha, scale, int(self.round_tf32), _stream())
+        if rc == -3:
+            return None
+        check(rc, "sae_fir_bias_act")
+        return out
 
     # ------------------------------------------------------------- modulate
     def modulate(self, x, s):
@@ -315,6 +389,76 @@ class CudaKernels:
         with torch.cuda.device(bucket.device):
             check(self.lib.sae_bucket_unpack(_ptr(ptrs), _ptr(offsets), _ptr(sizes), n, _ptr(bucket), bucket.numel(),
                                              scale, _stream()), "sae_bucket_unpack")
+
+
+    # ----------------------------------------------------------------- Adam
+    def adam_step(self, params, grads, offsets, sizes, exp_avg, exp_avg_sq, steps, lr, beta1, beta2, eps, grad_scale, cache):
+        """One multi-tensor Adam update (torch.optim.Adam semantics) of ``params`` (list of tensors).  grads: list aligned with
+        params — a tensor (the parameter's own gradient, or a view into the flat all-reduce bucket) or None (parameter
+        skipped, its step count untouched).  offsets / sizes: device int64 tensors locating each parameter's moments in
+        the flat ``exp_avg`` / ``exp_avg_sq``; steps: device float tensor, one count per parameter.  cache: the caller's
+        ``PointerTables`` (device copies of the address lists)."""
+        dev = exp_avg.device
+        p_tab = cache.get(tuple(p.data_ptr() for p in params))
+        g_tab = cache.get(tuple(0 if g is None else g.data_ptr() for g in grads))
+        for g in grads:
+            if g is not None and (not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous()):
+                raise _lib.SaeError("adam_step: gradients must be contiguous fp32 CUDA tensors")
+        with torch.cuda.device(dev):
+            check(self.lib.sae_adam_step(_ptr(p_tab), _ptr(g_tab), _ptr(offsets), _ptr(sizes), len(params), _ptr(exp_avg),
+                                         _ptr(exp_avg_sq), _ptr(steps), lr, beta1, beta2, eps, grad_scale, _stream()),
+                  "sae_adam_step")
+
+    # ----------------------------------------------------------------- ToRGB
+    def torgb_forward(self, x, s, w, bias, wscale):
+        """x [N,H,W,C], s [N,C], w [3,C], bias [3] or None -> y [N,H,W,4] (channel 3 zero)"""
+        _need_cuda(x, s, w, bias)
+        n, h, wd, c = x.shape
+        y = torch.empty((n, h, wd, 4), device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_torgb_forward(_ptr(x), _ptr(s), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, c, wscale,
+                                             int(self.round_tf32), _stream()), "sae_torgb_forward")
+        return y
+
+    def torgb_backward(self, dy, x, s, w, wscale, want_dx=True, want_gw=True):
+        """dy: logical [N,3,H,W] (any strides) -> (dx [N,H,W,C] or None, gw [N,3,C] = sum_p dy (x) x or None)"""
+        _need_cuda(x, s, w)
+        _need_cuda(dy, strided=True)
+        n, h, wd, c = x.shape
+        dx = torch.empty_like(x) if want_dx else None
+        gw = torch.zeros((n, 3, c), device=x.device, dtype=x.dtype) if want_gw else None
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_torgb_backward(_ptr(dy), _ptr(x), _ptr(s), _ptr(w), _ptr(dx), _ptr(gw), n, h, wd, c, wscale,
+                                              dy.stride(0), dy.stride(1), dy.stride(2), dy.stride(3), int(self.round_tf32),
+                                              _stream()), "sae_torgb_backward")
+        return dx, gw
+
+    # ----------------------------------------------------------------- crops
+    def crop_gather(self, x, flip, scale, offset, num_crops, size, c_pad, out=None):
+        """x: logical [B, C, H, W] (any strides); flip [Q], scale / offset [Q, 2] -> NHWC [Q, size, size, c_pad], channels
+        C.. zero.  out: optional destination (a [Q, size, size, c_pad] slice of a larger batch buffer)"""
+        _need_cuda(x, flip, scale, offset, strided=True)
+        b, c, h, w = x.shape
+        q = flip.numel()
+        if out is None:
+            out = torch.empty((q, size, size, c_pad), device=x.device, dtype=x.dtype)
+        assert tuple(out.shape) == (q, size, size, c_pad) and out.is_contiguous()
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_crop_gather(_ptr(x), _ptr(flip), _ptr(scale), _ptr(offset), _ptr(out), q, num_crops, c, h, w, size,
+                                           c_pad, x.stride(0), x.stride(1), x.stride(2), x.stride(3), int(self.round_tf32),
+                                           _stream()), "sae_crop_gather")
+        return out
+
+    def crop_gather_backward(self, dy, flip, scale, offset, num_crops, c, h, w):
+        """dy: logical [Q, C', S, S] (any strides, C' >= c) -> dx [Q / num_crops, c, h, w] contiguous"""
+        _need_cuda(dy, flip, scale, offset, strided=True)
+        q, s = dy.shape[0], dy.shape[2]
+        dx = torch.empty((q // num_crops, c, h, w), device=dy.device, dtype=dy.dtype)
+        with torch.cuda.device(dy.device):
+            check(self.lib.sae_crop_gather_backward(_ptr(dy), _ptr(flip), _ptr(scale), _ptr(offset), _ptr(dx), q, num_crops, c, h, w,
+                                                    s, dy.stride(0), dy.stride(1), dy.stride(2), dy.stride(3), _stream()),
+                  "sae_crop_gather_backward")
+        return dx
 
 
 _kernels = None

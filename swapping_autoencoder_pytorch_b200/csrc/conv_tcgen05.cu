@@ -1245,13 +1245,227 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------ stride-2 data gradient, all four parity classes per window
+// conv_tc5m_kernel still loads the input window of a pixel tile once PER CLASS, and a class's K loop is only 1, 2 or 4 taps
+// per channel block: the window ring (two slots) then covers a few hundred cycles of latency and the tensor pipe idles (ncu,
+// profiles/r2_prof_s2_dgrad_tc5m.txt: tensor 40 %, L2 32 %, DRAM 47 % — nothing saturated).  Here ONE CTA pair per SM pair
+// keeps all four class accumulators in TMEM at once — 4 classes x 64 columns, double-buffered = 512 columns — so per
+// 32-channel block the window is loaded once and all nine taps run against it (the same 72-step K loop as a stride-1 3x3
+// layer); loads of the next window are four slots ahead.  Work item = (pixel tile pair, 64-column block); the epilogue of
+// item i (eight 32-column chunk stores into the four interleaved output sub-grids) overlaps the main loop of item i + 1.
+constexpr int TC7_NA = 4;                           // window ring slots
+constexpr int TC7_NB = 8;                           // B ring slots of 4 KB (32 filter rows per CTA)
+constexpr int TC7_N = 64;                           // columns per class accumulator
+constexpr size_t tc7_smem_bytes() {
+    return (size_t)TC7_NB * (TC7_N / 2) * 128 + (size_t)TC7_NA * TC3_ASLOT + (size_t)TC5_NSTG * TC_A_BYTES + 1024 + 256;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc7_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ TcOutMaps outs, const TcParams p, const __grid_constant__ TcClasses cls, const int n_blocks,
+                const int total_work) {
+    constexpr int B_HALF_BYTES = (TC7_N / 2) * 128;
+    constexpr uint32_t B_RING = (uint32_t)TC7_NB * B_HALF_BYTES;
+    constexpr uint32_t RING0 = B_RING + (uint32_t)TC7_NA * TC3_ASLOT;
+    constexpr uint32_t STG_OFF = RING0;
+    constexpr uint32_t RING = RING0 + (uint32_t)TC5_NSTG * TC_A_BYTES;
+    constexpr uint32_t BUF_COLS = TC_MAX_CLS * TC7_N;                    // 256 columns per accumulator set
+    constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;                         // two sets: the whole TMEM of the SM
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC7_N >> 3) << 17) | ((256u >> 4) << 24);
+    constexpr int NCHUNK = TC7_N / 32;
+    static_assert((B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc7: layout");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_ring = base + B_RING;
+    const uint32_t bar_fullA = base + RING;
+    const uint32_t bar_emptyA = bar_fullA + 8 * TC7_NA;
+    const uint32_t bar_fullB = bar_emptyA + 8 * TC7_NA;
+    const uint32_t bar_emptyB = bar_fullB + 8 * TC7_NB;
+    const uint32_t bar_acc = bar_emptyB + 8 * TC7_NB;              // [2]
+    const uint32_t bar_tmem_empty = bar_acc + 16;                  // [2], leader's copy in use
+    const uint32_t tmem_slot = bar_tmem_empty + 16;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const uint32_t a_bytes = (uint32_t)(p.ww * p.wh) * 128u;
+    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0) {
+        const int nblk = work % n_blocks;
+        int tile = (work / n_blocks) * 2 + (int)rank;
+        const int tq = tile % p.tiles_w; tile /= p.tiles_w;
+        const int tp = tile % p.tiles_h; tile /= p.tiles_h;
+        q0 = tq * p.tw; p0 = tp * p.th; n0 = tile; col0 = nblk * TC7_N;
+    };
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int c = 0; c < cls.ncls; ++c) asm volatile("prefetch.tensormap [%0];" ::"l"(&outs.m[c]) : "memory");
+        for (int s = 0; s < TC7_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
+        for (int s = 0; s < TC7_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
+        mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
+        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        if (elect_one()) {
+            int ia = 0, ib = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters) {
+                int q0, p0, n0, col0;
+                decode(work, q0, p0, n0, col0);
+                for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
+                    const int sa = ia % TC7_NA;
+                    mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC7_NA)) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
+                    tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
+                    for (int c = 0; c < cls.ncls; ++c)
+                        for (int t = 0; t < cls.ntaps[c]; ++t, ++ib) {
+                            const int sb = ib % TC7_NB;
+                            mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC7_NB)) & 1u) ^ 1u);
+                            if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
+                            tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, cls.wk[c][t] + cb * TC_BK,
+                                         col0 + (int)rank * (TC7_N / 2));
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (leader && elect_one()) {
+            const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;
+            int ia = 0, ib = 0, it = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+                const uint32_t buf = (uint32_t)it & 1u;
+                if (it > 1) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
+                    const int sa = ia % TC7_NA;
+                    mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC7_NA)) & 1u);
+                    const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
+                    for (int c = 0; c < cls.ncls; ++c) {
+                        const uint32_t tmem_acc = tmem_base + buf * BUF_COLS + (uint32_t)c * TC7_N;
+                        for (int t = 0; t < cls.ntaps[c]; ++t, ++ib) {
+                            const int sb = ib % TC7_NB;
+                            mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC7_NB)) & 1u);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint32_t aaddr = a0 + (uint32_t)cls.arow[c][t] * 128u;
+                            uint64_t da = (uint64_t)((aaddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | sbo | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                            const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 8; ++k)
+                                umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (cb > 0 || t > 0 || k > 0) ? 1u : 0u);
+                            umma2_commit(bar_emptyB + 8 * sb);
+                        }
+                    }
+                    umma2_commit(bar_emptyA + 8 * sa);
+                }
+                umma2_commit(bar_acc + 8 * buf);
+            }
+        }
+    } else {
+        // ===================================================== epilogue: 4 classes x NCHUNK chunk stores per work item
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const int iw = row % p.tw, ih = row / p.tw;
+        int it = 0, gch = 0;
+        for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
+            int q0, p0, n0, col0;
+            decode(work, q0, p0, n0, col0);
+            const uint32_t buf = (uint32_t)it & 1u;
+            const int n = n0, pp = p0 + ih, qq = q0 + iw;
+            const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
+            mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c = 0; c < cls.ncls; ++c) {
+                const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + cls.o_offy[c]) * p.FW + qq * p.o_mul + cls.o_offx[c];
+                float nz = 0.f;
+                if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
+#pragma unroll 1
+                for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
+                    if (gch >= TC5_NSTG) {
+                        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                    float v[32];
+                    tmem_ld32(tmem_base + buf * BUF_COLS + (uint32_t)(c * TC7_N + ch * 32) + ((uint32_t)(lg * 32) << 16), v);
+                    const int colb = col0 + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float t = v[j];
+                        if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
+                        t += nz;
+                        if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
+                        t *= p.epi.gain;
+                        v[j] = t;
+                    }
+                    if (p.epi.residual && valid) {
+                        const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 r = __ldg(r4 + j);
+                            v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
+                            v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
+                            v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
+                            v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
+                        }
+                    }
+                    if (p.epi.round_tf32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+                    }
+                    const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
+                    uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const bool last = (c == cls.ncls - 1) && (ch == NCHUNK - 1);
+                    if (last) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (warp == 2 && lane == 0) {
+                        tma_store_4d(&outs.m[c], base + stg_off, colb, q0, p0, n0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (last)
+                            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
+                    }
+                }
+            }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ persistent per-tap pair kernel (experimental)
 // conv_tc2_kernel (stride-2 fprop, maps too small for the shared window) with the two changes that made conv_tc5_kernel:
 // a persistent loop over (tile pair, 128-column block) work items, two accumulator buffers in TMEM and dedicated output
 // staging, so loads and MMAs of tile i+1 overlap the epilogue of tile i.  NOT YET VALIDATED ON HARDWARE: written at the
 // end of round 1 after the GPU budget was spent; off unless SAE_TC6=1 (the conv parity tests cover its shapes).
+// BLOCK_N = 128: 3 x (16 KB A + 8 KB half-B) + 2 x 16 KB staging = 104 KB, two CTAs per SM.
+// BLOCK_N = 256: ONE CTA per SM owning all 512 TMEM columns (2 x 256) and a 5-deep ring, 5 x (16 KB + 16 KB) + 32 KB = 192 KB.
+// The per-tap kernels are bound by the L2 -> SM feed (ncu, profiles/r2_prof_s2_fprop_tc6.txt: lts 58 %, tensor pipe 53 %):
+// 256 columns halve the A bytes per MAC and the deeper ring covers the L2 latency that 3 stages x 256 clk cannot.
 template <int BLOCK_N>
-constexpr int tc6_stages() { return 3; }      // 3 x (16 KB A + 8 KB half-B) + 2 x 16 KB staging = 104 KB: two CTAs per SM
+constexpr int tc6_stages() { return BLOCK_N >= 256 ? 5 : 3; }
 
 template <int BLOCK_N>
 constexpr size_t tc6_smem_bytes() {
@@ -1259,7 +1473,7 @@ constexpr size_t tc6_smem_bytes() {
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, BLOCK_N >= 256 ? 1 : 2)
 conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks, const int total_work) {
     constexpr int STAGES = tc6_stages<BLOCK_N>();
@@ -1267,7 +1481,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     constexpr int STAGE_BYTES = TC_A_BYTES + B_HALF_BYTES;                 // per CTA
     constexpr uint32_t ACC_COLS = BLOCK_N;
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                           // two accumulator buffers
-    static_assert(BLOCK_N == 128, "tc6: 128-column blocks only (2 x 128 TMEM columns per CTA, two CTAs per SM)");
+    static_assert(BLOCK_N == 128 || BLOCK_N == 256, "tc6: 2 x 128 TMEM columns at two CTAs per SM, or 2 x 256 at one");
     // D fp32, A/B tf32 K-major, N = BLOCK_N, M = 256 (128 rows from each CTA)
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
 
@@ -1588,7 +1802,8 @@ static int tc6_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
     const int n_blocks = pr.Ncol / BLOCK_N;
     cudaLaunchConfig_t cfg = {};
     const int total_work = pairs * n_blocks;
-    int clusters = sm_count();                       // persistent: one wave, 2 CTAs per SM, 2 CTAs per cluster
+    // persistent: one wave of CTA pairs — two CTAs per SM at 128 columns, one at 256
+    int clusters = BLOCK_N >= 256 ? sm_count() / 2 : sm_count();
     if (clusters > total_work) clusters = total_work;
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
@@ -1831,7 +2046,10 @@ static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st)
                 }
             }
             static int tc6 = -1;
-            if (tc6 < 0) { const char* v = getenv("SAE_TC6"); tc6 = v ? atoi(v) : 0; }     // not validated on hardware yet: opt-in
+            if (tc6 < 0) { const char* v = getenv("SAE_TC6"); tc6 = v ? atoi(v) : 2; }
+            // SAE_TC6: 0 = one-tile kernels (conv_tc2); 1 = persistent, 128-column blocks; 2 (default) = persistent, 256-column
+            // blocks with one CTA per SM where the layer has them
+            if (tc6 >= 2 && pr.Ncol % 256 == 0) return tc6_launch<256>(pr, e, st);
             if (tc6 && pr.Ncol % 128 == 0) return tc6_launch<128>(pr, e, st);
             if (pr.Ncol % 256 == 0) return tc2_launch<256>(pr, e, st);
             if (pr.Ncol % 128 == 0) return tc2_launch<128>(pr, e, st);
@@ -1909,9 +2127,10 @@ int tc_fprop(const float* x, const float* w, float* y, const sae_conv_geom* g, c
 
 // One conv_tc5m launch over the rectangle all four parity classes share, then each class's thin remainder strips through
 // the ordinary per-class path.  Returns SAE_E_UNSUPPORTED (quietly) when the shape is outside the merged kernel's reach.
-static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t st) {
+static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t st, int variant) {
     const TcProblem& p0 = cp[0];
-    if (!pair_enabled() || p0.Ncol % 128 != 0 || p0.SC % 32 != 0) return SAE_E_UNSUPPORTED;
+    const bool quad = variant >= 2;              // conv_tc7_kernel: all four classes per window, 64-column blocks
+    if (!pair_enabled() || p0.Ncol % (quad ? 64 : 128) != 0 || p0.SC % 32 != 0) return SAE_E_UNSUPPORTED;
     int MH = cp[0].OH, MW = cp[0].OW;
     int oy_min = cp[0].oy[0], oy_max = oy_min, ox_min = cp[0].ox[0], ox_max = ox_min;
     for (int c = 0; c < TC_MAX_CLS; ++c) {
@@ -1940,7 +2159,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     TcOutMaps outs;
     cls.ncls = TC_MAX_CLS;
     CUtensorMap msrc, mw, mdummy;
-    int rc = tc_encode_maps(main, p, 128 / 2, &msrc, &mw, &mdummy);      // weight map (the others are rebuilt below)
+    int rc = tc_encode_maps(main, p, (quad ? TC7_N : 128) / 2, &msrc, &mw, &mdummy);      // weight map (the others are rebuilt below)
     if (rc) return rc;
     {
         cuuint64_t dims[4] = {(cuuint64_t)main.SC, (cuuint64_t)main.SW, (cuuint64_t)main.SH, (cuuint64_t)main.SN};
@@ -1968,16 +2187,17 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
         rc = encode_map(&outs.m[c], q.out + ((int64_t)q.o_offy * q.FW + q.o_offx) * q.Ncol, 4, dims, strides, box, es);
         if (rc) return rc;
     }
-    constexpr size_t smem = tc5_smem_bytes<128>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5m_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+    const size_t smem = quad ? tc7_smem_bytes() : tc5_smem_bytes<128>();
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[quad]) {
+        if (quad) SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5m_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[quad] = true;
     }
     const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int n_blocks = main.Ncol / 128;
-    const int total_work = ((tiles + 1) / 2) * TC_MAX_CLS * n_blocks;
-    int clusters = sm_count();
+    const int n_blocks = main.Ncol / (quad ? TC7_N : 128);
+    const int total_work = ((tiles + 1) / 2) * (quad ? 1 : TC_MAX_CLS) * n_blocks;
+    int clusters = quad ? sm_count() / 2 : sm_count();       // one CTA per SM (all 512 TMEM columns) / two
     if (clusters > total_work) clusters = total_work;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
@@ -1989,8 +2209,9 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<128>, msrc, mw, outs, p, cls, n_blocks, total_work));
-    rc = check_launch("conv_tc5m");
+    if (quad) SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc7_kernel, msrc, mw, outs, p, cls, n_blocks, total_work));
+    else SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<128>, msrc, mw, outs, p, cls, n_blocks, total_work));
+    rc = check_launch(quad ? "conv_tc7" : "conv_tc5m");
     if (rc) return rc;
     // remainders of each class beyond the shared rectangle: right strip (full height, takes the corner), bottom strip
     for (int c = 0; c < TC_MAX_CLS; ++c) {
@@ -2052,9 +2273,11 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
             cls_pr[ncls++] = pr;
         }
     static int merged = -1;
-    if (merged < 0) { const char* v = getenv("SAE_DGRAD_MERGED"); merged = v ? atoi(v) : 0; }     // not validated on hardware yet
+    // SAE_DGRAD_MERGED: 0 = one launch per class; 1 = conv_tc5m (one launch, class index in the work item); 2 = conv_tc7
+    // (all four classes per input window)
+    if (merged < 0) { const char* v = getenv("SAE_DGRAD_MERGED"); merged = v ? atoi(v) : 1; }
     if (merged && ncls == TC_MAX_CLS && !need_zero) {
-        int rc = tc_dgrad_merged(cls_pr, e, st);
+        int rc = tc_dgrad_merged(cls_pr, e, st, merged);
         if (rc != SAE_E_UNSUPPORTED) return rc;
     }
     for (int c = 0; c < ncls; ++c) {

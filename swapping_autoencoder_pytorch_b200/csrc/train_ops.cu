@@ -85,41 +85,43 @@ __device__ __forceinline__ float crop_lin(int k, int S) {
 
 __global__ void __launch_bounds__(256)
 crop_gather_kernel(const float* __restrict__ x, float* __restrict__ out, const CropParams p) {
-    const int64_t total = (int64_t)p.Q * p.S * p.S;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx % p.S);
-        const int i = (int)((idx / p.S) % p.S);
-        const int q = (int)(idx / ((int64_t)p.S * p.S));
-        const float gx = (crop_lin(j, p.S) * __ldg(p.flip + q)) * __ldg(p.scale + 2 * q) + __ldg(p.offset + 2 * q);
-        const float gy = crop_lin(i, p.S) * __ldg(p.scale + 2 * q + 1) + __ldg(p.offset + 2 * q + 1);
-        const float ix = ((gx + 1.f) * (float)p.W - 1.f) * 0.5f;
-        const float iy = ((gy + 1.f) * (float)p.H - 1.f) * 0.5f;
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = (int)fx, y0 = (int)fy;
-        const float tx = ix - fx, ty = iy - fy;
-        const float w00 = (1.f - tx) * (1.f - ty), w01 = tx * (1.f - ty), w10 = (1.f - tx) * ty, w11 = tx * ty;
-        const bool vx0 = x0 >= 0 && x0 < p.W, vx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
-        const bool vy0 = y0 >= 0 && y0 < p.H, vy1 = y0 + 1 >= 0 && y0 + 1 < p.H;
-        const float* src = x + (int64_t)(q / p.num_crops) * p.xs_n;
-        float4* dst = reinterpret_cast<float4*>(out + idx * p.CP);
+    // one thread per 16-byte slot of the output (CP / 4 slots per pixel): consecutive lanes write consecutive slots, so a
+    // warp's store covers 512 contiguous bytes; only slot 0 of a pixel (channels 0..3) carries data, the others are the pad
+    const int slots = p.CP / 4;
+    const int64_t total = (int64_t)p.Q * p.S * p.S * slots;
+    for (int64_t sidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; sidx < total; sidx += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(sidx % slots);
+        const int64_t idx = sidx / slots;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c0 = 0; c0 < p.CP; c0 += 4) {
+        if (slot == 0) {
+            const int j = (int)(idx % p.S);
+            const int i = (int)((idx / p.S) % p.S);
+            const int q = (int)(idx / ((int64_t)p.S * p.S));
+            const float gx = (crop_lin(j, p.S) * __ldg(p.flip + q)) * __ldg(p.scale + 2 * q) + __ldg(p.offset + 2 * q);
+            const float gy = crop_lin(i, p.S) * __ldg(p.scale + 2 * q + 1) + __ldg(p.offset + 2 * q + 1);
+            const float ix = ((gx + 1.f) * (float)p.W - 1.f) * 0.5f;
+            const float iy = ((gy + 1.f) * (float)p.H - 1.f) * 0.5f;
+            const float fx = floorf(ix), fy = floorf(iy);
+            const int x0 = (int)fx, y0 = (int)fy;
+            const float tx = ix - fx, ty = iy - fy;
+            const float w00 = (1.f - tx) * (1.f - ty), w01 = tx * (1.f - ty), w10 = (1.f - tx) * ty, w11 = tx * ty;
+            const bool vx0 = x0 >= 0 && x0 < p.W, vx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
+            const bool vy0 = y0 >= 0 && y0 < p.H, vy1 = y0 + 1 >= 0 && y0 + 1 < p.H;
+            const float* src = x + (int64_t)(q / p.num_crops) * p.xs_n;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c0 + u;
-                float acc = 0.f;
+            for (int c = 0; c < 4; ++c) {
                 if (c < p.C) {
                     const float* sc = src + (int64_t)c * p.xs_c;
+                    float acc = 0.f;
                     if (vy0 && vx0) acc += w00 * __ldg(sc + (int64_t)y0 * p.xs_h + (int64_t)x0 * p.xs_w);
                     if (vy0 && vx1) acc += w01 * __ldg(sc + (int64_t)y0 * p.xs_h + (int64_t)(x0 + 1) * p.xs_w);
                     if (vy1 && vx0) acc += w10 * __ldg(sc + (int64_t)(y0 + 1) * p.xs_h + (int64_t)x0 * p.xs_w);
                     if (vy1 && vx1) acc += w11 * __ldg(sc + (int64_t)(y0 + 1) * p.xs_h + (int64_t)(x0 + 1) * p.xs_w);
-                    if (p.round_tf32) acc = rna_tf32(acc);
+                    v[c] = p.round_tf32 ? rna_tf32(acc) : acc;
                 }
-                v[u] = acc;
             }
-            dst[c0 / 4] = make_float4(v[0], v[1], v[2], v[3]);
         }
+        reinterpret_cast<float4*>(out)[sidx] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -236,7 +238,7 @@ extern "C" int sae_crop_gather(const float* x, const float* flip, const float* s
     if (rc) return rc;
     if (!x || !out || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SAE_E_INVALID, "crop_gather: null / unaligned pointer");
     p.xs_n = xs_n; p.xs_c = xs_c; p.xs_h = xs_h; p.xs_w = xs_w; p.round_tf32 = round_tf32;
-    crop_gather_kernel<<<grid_1d((int64_t)Q * S * S, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, out, p);
+    crop_gather_kernel<<<grid_1d((int64_t)Q * S * S * (CP / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(x, out, p);
     return check_launch("crop_gather");
 }
 

@@ -251,15 +251,21 @@ struct FirMask {
     const float* act_out;     // saved activation output, same shape as the FIR output
     float* grad_bias;         // [minor], accumulated; may be null
     float alpha, scale;
+    // MODE 2 (sae_fir_bias_act, forward): out = lrelu(FIR(x) + noise_weight * noise[pixel] + bias[c]) * scale
+    const float* bias;        // [minor] or null
+    const float* noise;       // one value per output pixel, or null
+    const float* noise_weight;
 };
 
-template <int KH, int KW, bool MASK>
+// MODE: 0 plain FIR, 1 = MASK (activation backward applied to the result), 2 = ACT (noise + bias + leaky-ReLU applied to it)
+template <int KH, int KW, int MODE>
 __global__ void __launch_bounds__(256)
 fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ out, FirParams p, SepTaps taps, int tiles_x, int tiles_y,
                int ncb, FirMask mk) {
     constexpr int WW = FT_W + KW - 1, WH = FT_H + KH - 1;
     extern __shared__ uint8_t fir_smem[];
     __shared__ __align__(8) uint64_t bar_storage;
+    constexpr bool MASK = MODE == 1;
     __shared__ float bias_part[32];
     if (MASK && threadIdx.x < 32) bias_part[threadIdx.x] = 0.f;
     const uint32_t base = (smem_u32(fir_smem) + 127u) & ~127u;
@@ -307,6 +313,12 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ ou
     const int64_t off0 = (((int64_t)n * p.out_h + oy0 + r0) * p.out_w + ox) * p.minor + cb * 32 + cvec * 4;
     float* dst = out + off0;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nw = 0.f;
+    if (MODE == 2) {
+        if (mk.bias) bias4 = __ldg(reinterpret_cast<const float4*>(mk.bias + cb * 32 + cvec * 4));
+        if (mk.noise) nw = __ldg(mk.noise_weight);
+    }
 #pragma unroll
     for (int r = 0; r < FT_H / 2; ++r) {
         w[KH - 1] = hrow(r0 + r + KH - 1);
@@ -324,6 +336,13 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ ou
                 acc.z *= (o.z > 0.f ? mk.scale : mk.alpha * mk.scale); acc.w *= (o.w > 0.f ? mk.scale : mk.alpha * mk.scale);
                 bsum.x += acc.x; bsum.y += acc.y; bsum.z += acc.z; bsum.w += acc.w;
             }
+        }
+        if (MODE == 2) {
+            float nz = 0.f;
+            if (mk.noise && inside) nz = nw * __ldg(mk.noise + ((int64_t)n * p.out_h + oy0 + r0 + r) * p.out_w + ox);
+            acc.x += bias4.x + nz; acc.y += bias4.y + nz; acc.z += bias4.z + nz; acc.w += bias4.w + nz;
+            acc.x = (acc.x > 0.f ? acc.x : acc.x * mk.alpha) * mk.scale; acc.y = (acc.y > 0.f ? acc.y : acc.y * mk.alpha) * mk.scale;
+            acc.z = (acc.z > 0.f ? acc.z : acc.z * mk.alpha) * mk.scale; acc.w = (acc.w > 0.f ? acc.w : acc.w * mk.alpha) * mk.scale;
         }
         if (p.round_tf32) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
         if (inside) *reinterpret_cast<float4*>(dst + (int64_t)r * p.out_w * p.minor) = acc;
@@ -347,7 +366,7 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ ou
     }
 }
 
-template <int KH, int KW, bool MASK = false>
+template <int KH, int KW, int MASK = 0>
 static int launch_tma(const float* x, float* out, const FirParams& p, const SepTaps& taps, cudaStream_t st, FirMask mk = FirMask()) {
     constexpr int WW = FT_W + KW - 1, WH = FT_H + KH - 1;
     CUtensorMap mx;
@@ -563,7 +582,47 @@ extern "C" int sae_fir_act_backward(const float* grad, const float* taps_y, cons
     FirMask mk;
     mk.act_out = act_out; mk.grad_bias = grad_bias; mk.alpha = alpha; mk.scale = scale;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = kernel_h == 3 ? launch_tma<3, 3, true>(grad, grad_in, p, t, st, mk) : launch_tma<4, 4, true>(grad, grad_in, p, t, st, mk);
+    mk.bias = nullptr; mk.noise = nullptr; mk.noise_weight = nullptr;
+    int rc = kernel_h == 3 ? launch_tma<3, 3, 1>(grad, grad_in, p, t, st, mk) : launch_tma<4, 4, 1>(grad, grad_in, p, t, st, mk);
     if (rc) return rc;
     return check_launch("fir_act_backward");
+}
+
+// FIR (up = down = 1, separable 3 or 4 taps) followed by NoiseInjection + bias + leaky-ReLU in ONE pass:
+//   out = lrelu(FIR(x) + noise_weight * noise[pixel] + bias[c], alpha) * scale
+// the Blur after the generator's transposed convolution and the StyledConv tail behind it
+// (stylegan2_layers.py:306-309 -> :398-405): the blurred tensor is never written to HBM.
+// Only the TMA-tiled configuration (minor % 32 == 0, output >= 8 x 8); SAE_E_UNSUPPORTED otherwise.
+extern "C" int sae_fir_bias_act(const float* x, const float* taps_y, const float* taps_x, const float* bias, const float* noise,
+                                const float* noise_weight, float* out, int64_t major, int in_h, int in_w, int minor,
+                                int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                                float alpha, float scale, int round_tf32, void* stream) {
+    using namespace sae;
+    if (major == 0) return SAE_OK;
+    if (!x || !taps_y || !taps_x || !out) return fail(SAE_E_INVALID, "fir_bias_act: null pointer");
+    if (noise && !noise_weight) return fail(SAE_E_INVALID, "fir_bias_act: noise needs its weight");
+    if ((kernel_h != 3 && kernel_h != 4) || kernel_w != kernel_h) return fail(SAE_E_UNSUPPORTED, "fir_bias_act: taps must be 3 or 4, square");
+    if (minor % 32 != 0 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15) != 0)
+        return fail(SAE_E_UNSUPPORTED, "fir_bias_act: needs minor %% 32 == 0 and 16-byte aligned pointers");
+    FirParams p;
+    p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
+    p.up_x = p.up_y = 1; p.down_x = p.down_y = 1; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.round_tf32 = round_tf32;
+    const int full_h = in_h + pad_y0 + pad_y1 - kernel_h, full_w = in_w + pad_x0 + pad_x1 - kernel_w;
+    if (full_h < 0 || full_w < 0) return fail(SAE_E_INVALID, "fir_bias_act: kernel larger than padded input");
+    p.out_h = full_h + 1;
+    p.out_w = full_w + 1;
+    if (!tc_available() || p.out_w < 8 || p.out_h < 8 ||
+        major * (int64_t)((p.out_w + FT_W - 1) / FT_W) * ((p.out_h + FT_H - 1) / FT_H) * (minor / 32) >= ((int64_t)1 << 31))
+        return fail(SAE_E_UNSUPPORTED, "fir_bias_act: shape outside the TMA-tiled configuration");
+    SepTaps t;
+    for (int i = 0; i < 8; ++i) { t.y[i] = 0.f; t.x[i] = 0.f; }
+    for (int i = 0; i < kernel_h; ++i) t.y[i] = taps_y[kernel_h - 1 - i];
+    for (int i = 0; i < kernel_w; ++i) t.x[i] = taps_x[kernel_w - 1 - i];
+    FirMask mk;
+    mk.act_out = nullptr; mk.grad_bias = nullptr; mk.alpha = alpha; mk.scale = scale;
+    mk.bias = bias; mk.noise = noise; mk.noise_weight = noise_weight;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = kernel_h == 3 ? launch_tma<3, 3, 2>(x, out, p, t, st, mk) : launch_tma<4, 4, 2>(x, out, p, t, st, mk);
+    if (rc) return rc;
+    return check_launch("fir_bias_act");
 }

@@ -16,6 +16,7 @@ images copied into a static input buffer.
 * A body that fails to capture falls back to eager execution for the rest of the run (``self.disabled`` holds why).
 """
 import gc
+import os
 import traceback
 import warnings
 
@@ -36,6 +37,10 @@ class HalfStepGraphs:
         self.last_traceback = None
         self.replayed_launches = 0     # kernels of this library executed through graph replays (bench bookkeeping)
         self.enabled = True            # bench switches to eager for its per-launch instrumentation pass
+        # data parallel: capture pack -> NCCL all-reduce -> Adam into the graph as well (one replay = one whole half-step, no
+        # host involvement between backward and the update); falls back to an eager tail if the collective cannot be captured
+        self.nccl_in_graph = os.environ.get("SAE_GRAPH_NCCL", "1") != "0"
+        self.nccl_capture_error = None
 
     # ------------------------------------------------------------------
     def _wrapper(self):
@@ -47,10 +52,9 @@ class HalfStepGraphs:
     def _optimizer(self, kind):
         return self.trainer.optimizer_G if kind == "G" else self.trainer.optimizer_D
 
-    def _finish_eagerly(self, kind):
-        """world > 1: average the static gradient buffers across ranks, then step"""
-        self._wrapper().reduce_gradients_now()
-        self._optimizer(kind).step()
+    def _tail(self, kind):
+        """world > 1: pack the static gradient buffers, all-reduce, Adam reading the bucket (optimizer.exchange_and_step)"""
+        self.trainer.exchange_and_step(self._optimizer(kind), self._params(kind))
 
     def _side(self, fn):
         """Run ``fn`` on the capture stream.  The warm-up calls must run where the capture will: autograd remembers
@@ -70,6 +74,9 @@ class HalfStepGraphs:
         self.last_traceback = traceback.format_exc()
         warnings.warn("CUDA-graph capture of the %s half-step failed (%s); continuing eagerly\n%s"
                       % (kind, self.disabled, self.last_traceback))
+        self._recover()
+
+    def _recover(self):
         torch.cuda.synchronize()
         try:
             # a capture that died half-way can leave torch's CUDA generator in "capturing" state; one empty, successful
@@ -93,11 +100,21 @@ class HalfStepGraphs:
             if n < self.warmup:
                 return self._side(lambda: body(images))
             try:
-                hit = self._capture(key, body, images)
+                try:
+                    hit = self._capture(key, body, images, self.nccl_in_graph)
+                except Exception as e:      # noqa: BLE001
+                    if not (self.nccl_in_graph and self._world() > 1):
+                        raise
+                    # the collective could not be captured on this stack: keep the graph for forward + backward and run the
+                    # exchange + Adam eagerly after every replay
+                    self.nccl_in_graph = False
+                    self.nccl_capture_error = "%s: %s" % (type(e).__name__, (str(e).splitlines() or ["?"])[0][:200])
+                    self._recover()
+                    hit = self._capture(key, body, images, False)
             except Exception as e:      # noqa: BLE001 — any capture failure means "run eagerly", never "stop training"
                 self._give_up(kind, e)
                 return body(images)
-        graph, static_in, outputs, launches, grads = hit
+        graph, static_in, outputs, launches, grads, tail_captured = hit
         # host-side state the eager body would have left behind: which group is trainable, and which gradient buffers
         # the parameters point at (every graph owns its own static set)
         self._select_group(kind)
@@ -107,13 +124,17 @@ class HalfStepGraphs:
             static_in.copy_(images, non_blocking=True)
         graph.replay()
         self.replayed_launches += launches
-        if self._world() > 1:
-            self._finish_eagerly(kind)
+        if self._world() > 1 and not tail_captured:
+            self._tail(kind)
         return dict(outputs)
 
     def describe(self, world):
         """one-line account of what a replay contains (bench.py reports it)"""
-        return "forward+backward+Adam per replay" if world == 1 else "forward+backward per replay; all-reduce and Adam eager"
+        if world == 1:
+            return "forward+backward+Adam per replay"
+        if self.nccl_in_graph:
+            return "forward+backward+bucket pack+NCCL all-reduce+Adam per replay"
+        return "forward+backward per replay; all-reduce and Adam eager (%s)" % (self.nccl_capture_error or "SAE_GRAPH_NCCL=0")
 
     def _select_group(self, kind):
         t = self.trainer
@@ -132,7 +153,7 @@ class HalfStepGraphs:
                 self.run(kind, body, images)
         torch.cuda.synchronize()
 
-    def _capture(self, key, body, images):
+    def _capture(self, key, body, images, with_tail=False):
         kind = key[0]
         world = self._world()
         wrapper = self._wrapper()
@@ -158,6 +179,8 @@ class HalfStepGraphs:
         try:
             with torch.cuda.graph(graph, pool=self.pool, stream=self.stream):
                 outputs = body(static_in, step=(world == 1))
+                if world > 1 and with_tail:
+                    self._tail(kind)
         finally:
             if gc_was_enabled:
                 gc.enable()
@@ -166,6 +189,6 @@ class HalfStepGraphs:
         launches = _lib.launch_count() - n0
         outputs = {k: v for k, v in outputs.items() if torch.is_tensor(v)}
         grads = [(p, p.grad) for p in self._params(kind)]      # None where the body produces no gradient (R1: final bias)
-        hit = (graph, static_in, outputs, launches, grads)
+        hit = (graph, static_in, outputs, launches, grads, bool(world > 1 and with_tail))
         self.captured[key] = hit
         return hit

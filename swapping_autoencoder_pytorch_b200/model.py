@@ -25,7 +25,10 @@ class BaseModel(torch.nn.Module):
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
-        self.device = torch.device('cuda:0') if opt.num_gpus > 0 else torch.device('cpu')
+        # one process per GPU: the model lives on THIS process's device (torch.cuda.current_device(), set from LOCAL_RANK by
+        # parallel.init_distributed), never on cuda:0 of every rank (the reference's single-process DataParallel uses
+        # cuda:0, models/base_model.py:18)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if opt.num_gpus > 0 else torch.device('cpu')
 
     def initialize(self):
         pass
@@ -50,9 +53,14 @@ class BaseModel(torch.nn.Module):
             os.remove(link)
         os.symlink(fname, link)
 
-    def load(self, path=None, strict_shapes=False):
-        """Copy tensors by key from a (reference-format) state_dict; missing keys are skipped, mismatching shapes
-        are copied on their common sub-block (the reference asks interactively, base_model.py:43-112)."""
+    def load(self, path=None, strict_shapes=True, partial_shapes=None):
+        """Copy tensors by key from a (reference-format) state_dict (reference base_model.py:43-112).  Keys missing from the
+        checkpoint are reported and skipped, as in the reference.  A tensor whose shape differs raises unless partial loading
+        is asked for (``strict_shapes=False`` or ``opt.partial_shape_loading``): the reference asks yes / no / all on the
+        terminal for every such key; there, as here, only tensors of rank 1, 2 or 4 are eligible and only the corner the
+        checkpoint does not cover is zeroed."""
+        if partial_shapes is None:
+            partial_shapes = (not strict_shapes) or bool(getattr(self.opt, "partial_shape_loading", False))
         if path is None:
             pretrained = getattr(self.opt, "pretrained_name", None)
             name = pretrained if (self.opt.isTrain and pretrained is not None) else self.opt.name
@@ -61,7 +69,7 @@ class BaseModel(torch.nn.Module):
             assert self.opt.isTrain, "In test mode, the checkpoint file must exist"
             print("checkpoint %s does not exist; training starts from scratch" % path)
             return False
-        ckpt = torch.load(path, map_location=str(self.device))
+        ckpt = torch.load(path, map_location="cpu")        # copied parameter by parameter onto this rank's own device
         with torch.no_grad():
             for name, own in self.state_dict().items():
                 if not self.opt.isTrain and (name.startswith("D.") or name.startswith("Dpatch.")):
@@ -73,11 +81,20 @@ class BaseModel(torch.nn.Module):
                 if own.shape == src.shape:
                     own.copy_(src)
                     continue
-                if strict_shapes or own.dim() != src.dim():
-                    raise ValueError("Key [%s]: shape %s vs checkpoint %s" % (name, tuple(own.shape), tuple(src.shape)))
-                common = tuple(slice(0, min(a, b)) for a, b in zip(own.shape, src.shape))
-                own.zero_()
-                own[common].copy_(src[common])
+                message = "Key [%s]: Shape does not match the created model (%s) and loaded checkpoint (%s)" % (
+                    name, tuple(own.shape), tuple(src.shape))
+                if not partial_shapes:
+                    raise ValueError(message + " — pass strict_shapes=False (or opt.partial_shape_loading) to force-load the "
+                                     "common sub-block, the reference's interactive 'all' answer")
+                print(message)
+                ms = [min(a, b) for a, b in zip(own.shape, src.shape)]
+                if own.dim() != src.dim() or len(ms) not in (1, 2, 4):
+                    print("Skipping min_shape of %s" % str(ms))           # e.g. the 5-D ModulatedConv2d weights
+                    continue
+                common = tuple(slice(0, m) for m in ms)
+                corner = tuple(slice(m, None) for m in ms)
+                own[common].copy_(src[common].to(own.device))
+                own[corner].zero_()                                  # only the far corner is cleared (reference :75-83)
         return True
 
     def forward(self, *args, command=None, **kwargs):
@@ -157,11 +174,16 @@ class SwappingAutoencoderModel(BaseModel):
         opt = self.opt
         if getattr(opt, "batch_discriminator_passes", False):
             # same three crop draws in the same order (the feature extractor draws nothing), one pass over all of them
-            crops = [self.get_random_crops(real), self.get_random_crops(real), self.get_random_crops(mix)]
-            feats = self.Dpatch.extract_features(torch.cat(crops)).split([c.size(0) * c.size(1) for c in crops])
-            real_feat, target_feat, mix_feat = feats
+            if real.size(1) <= 4 and real.is_cuda == mix.is_cuda:
+                crops, sizes = util.apply_random_crops_multi([real, real, mix], opt.patch_size,
+                                                             (opt.patch_min_scale, opt.patch_max_scale), opt.patch_num_crops)
+            else:
+                parts = [self.get_random_crops(real), self.get_random_crops(real), self.get_random_crops(mix)]
+                crops, sizes = torch.cat(parts), [c.size(0) for c in parts]
+            n = crops.size(1)
+            real_feat, target_feat, mix_feat = self.Dpatch.extract_features(crops).split([b * n for b in sizes])
             if opt.patch_use_aggregation:
-                real_feat = self.Dpatch.aggregate_features(real_feat, crops[0].size(0), crops[0].size(1))
+                real_feat = self.Dpatch.aggregate_features(real_feat, sizes[0], n)
         else:
             real_feat = self.Dpatch.extract_features(self.get_random_crops(real), aggregate=opt.patch_use_aggregation)
             target_feat = self.Dpatch.extract_features(self.get_random_crops(real))
@@ -249,7 +271,8 @@ class SwappingAutoencoderModel(BaseModel):
         if self.opt.isTrain:
             real = real[:2] if self.opt.num_gpus > 1 else real[:4]
         sp, gl = self.E(real)
-        return {"real": real, "rec": self.G(sp, gl), "mix": self.G(sp, self.swap(gl))}
+        layout = util.resize2d_tensor(util.visualize_spatial_code(sp), real)
+        return {"real": real, "layout": layout, "rec": self.G(sp, gl), "mix": self.G(sp, self.swap(gl))}
 
     def fix_noise(self, sample_image=None):
         if sample_image is not None:

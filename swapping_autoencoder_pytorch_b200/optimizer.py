@@ -5,9 +5,97 @@ hyper-parameters and R1 schedule) for boxes without the reference checkout.  The
 exchange is invisible here: ``MultiGPUModelWrapper`` (parallel.py) all-reduces the active parameter group at
 the end of every ``backward()``.
 """
+import os
+
 import torch
 
-from . import util
+from . import backend, util
+
+
+class MultiTensorAdam:
+    """``torch.optim.Adam`` for one parameter group as ONE kernel launch (``sae_adam_step``) — the subset of
+    the torch optimizer interface the reference driver uses (``zero_grad`` / ``step`` / ``state_dict`` / ``load_state_dict`` /
+    ``param_groups``; reference optimizers/swapping_autoencoder_optimizer.py:34-42, :76, :94).  Same arithmetic and the same
+    per-parameter semantics: a parameter without a gradient is skipped and keeps its own step count.  Moments live in two
+    flat fp32 buffers, step counts on the device, so the update is capturable in a CUDA graph.  ``step(grads=...)`` lets the
+    data-parallel path hand in views of the flat all-reduce bucket with ``grad_scale = 1 / world`` (no unpack pass)."""
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.params = list(params)
+        self.param_groups = [dict(params=self.params, lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps),
+                                  weight_decay=0, amsgrad=False, maximize=False)]
+        sizes, offsets, total = [], [], 0
+        for p in self.params:
+            sizes.append(p.numel())
+            offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4          # every segment 16-byte aligned
+        self._sizes, self._offsets, self._total = sizes, offsets, total
+        self._dev = None
+        self._cache = None
+
+    def _state(self):
+        if self._dev is None:
+            dev = self.params[0].device
+            self.exp_avg = torch.zeros(self._total, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(self._total, dtype=torch.float32, device=dev)
+            self.steps = torch.zeros(len(self.params), dtype=torch.float32, device=dev)
+            self.offsets_t = torch.tensor(self._offsets, dtype=torch.int64, device=dev)
+            self.sizes_t = torch.tensor(self._sizes, dtype=torch.int64, device=dev)
+            self._cache = backend.PointerTables(len(self.params), dev)
+            self._dev = dev
+        return self
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.detach_().zero_()
+
+    @torch.no_grad()
+    def step(self, grads=None, grad_scale=1.0):
+        st = self._state()
+        g = self.param_groups[0]
+        if grads is None:
+            grads = [p.grad for p in self.params]
+        grads = [None if t is None else (t if t.is_contiguous() else t.contiguous()) for t in grads]
+        if all(t is None for t in grads):
+            return
+        params = self.params
+        if st.exp_avg.dtype != params[0].dtype:           # fp64 runs of the CPU test-suite
+            st.exp_avg, st.exp_avg_sq = st.exp_avg.to(params[0].dtype), st.exp_avg_sq.to(params[0].dtype)
+        backend.kernels().adam_step(params, grads, st.offsets_t, st.sizes_t, st.exp_avg, st.exp_avg_sq, st.steps, g["lr"],
+                                    g["betas"][0], g["betas"][1], g["eps"], float(grad_scale), self._cache)
+
+    # torch.optim.Adam's on-disk format, so optimizer checkpoints interoperate with the stock optimizer
+    def state_dict(self):
+        st = self._state()
+        state = {}
+        for i, (o, n, p) in enumerate(zip(self._offsets, self._sizes, self.params)):
+            if float(st.steps[i]) == 0.0:
+                continue
+            state[i] = {"step": st.steps[i].detach().clone().cpu(), "exp_avg": st.exp_avg[o:o + n].view_as(p).clone(),
+                        "exp_avg_sq": st.exp_avg_sq[o:o + n].view_as(p).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self.params)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        st = self._state()
+        group = sd["param_groups"][0]
+        assert len(group["params"]) == len(self.params), "optimizer state belongs to a different parameter list"
+        for k in ("lr", "betas", "eps"):
+            if k in group:
+                self.param_groups[0][k] = tuple(group[k]) if k == "betas" else group[k]
+        st.exp_avg.zero_()
+        st.exp_avg_sq.zero_()
+        st.steps.zero_()
+        for i, entry in sd["state"].items():
+            i = int(i)
+            o, n = self._offsets[i], self._sizes[i]
+            st.exp_avg[o:o + n].copy_(entry["exp_avg"].reshape(-1))
+            st.exp_avg_sq[o:o + n].copy_(entry["exp_avg_sq"].reshape(-1))
+            st.steps[i] = float(entry["step"])
 
 
 class SwappingAutoencoderOptimizer:
@@ -33,11 +121,23 @@ class SwappingAutoencoderOptimizer:
         if on_cuda and getattr(opt, "cuda_graphs", False):
             from .graphs import HalfStepGraphs
             self.graphs = HalfStepGraphs(self)
-        fused = dict(fused=True, capturable=self.graphs is not None) if on_cuda else {}
-        self.optimizer_G = torch.optim.Adam(self.Gparams, lr=opt.lr, betas=(opt.beta1, opt.beta2), **fused)
+        # data parallel: this driver exchanges the gradients itself and hands the flat bucket to Adam (no unpack pass, the
+        # 1/world factor folded into the update); the wrapper's end-of-backward averaging into p.grad — what a stock optimizer
+        # needs — is switched off
+        self.world = getattr(model, "world", 1)
+        if self.world > 1:
+            model.defer_to_optimizer = True
+        self.optimizer_G = MultiTensorAdam(self.Gparams, lr=opt.lr, betas=(opt.beta1, opt.beta2))
         # lazy regularisation correction of lr and betas (StyleGAN2 appendix B; reference :38-42)
         c = opt.R1_once_every / (1 + opt.R1_once_every)
-        self.optimizer_D = torch.optim.Adam(self.Dparams, lr=opt.lr * c, betas=(opt.beta1 ** c, opt.beta2 ** c), **fused)
+        self.optimizer_D = MultiTensorAdam(self.Dparams, lr=opt.lr * c, betas=(opt.beta1 ** c, opt.beta2 ** c))
+
+    def exchange_and_step(self, optimizer, params):
+        """optimizer step of one half-step; with more than one rank: pack -> all-reduce (SUM) -> Adam reading the bucket"""
+        if self.world > 1:
+            optimizer.step(grads=self.model.reduce_to_bucket(params), grad_scale=1.0 / self.world)
+        else:
+            optimizer.step()
 
     @staticmethod
     def set_requires_grad(params, requires_grad):
@@ -60,7 +160,7 @@ class SwappingAutoencoderOptimizer:
             losses = self.train_discriminator_one_step(images)
         else:
             losses = self.train_generator_one_step(images)
-        return util.to_numpy(losses)
+        return util.to_numpy(losses, lazy=getattr(self.opt, "async_loss_readback", True))
 
     # ------------------------------------------------------------------ half-step bodies (eager or captured)
     def _generator_body(self, images, step=True):
@@ -70,7 +170,7 @@ class SwappingAutoencoderOptimizer:
         g_losses, g_metrics = self.model(images, None, None, command="compute_generator_losses")
         sum(v.mean() for v in g_losses.values()).backward()
         if step:
-            self.optimizer_G.step()
+            self.exchange_and_step(self.optimizer_G, self.Gparams)
         g_losses.update(g_metrics)
         return g_losses
 
@@ -84,7 +184,7 @@ class SwappingAutoencoderOptimizer:
         d_losses["_sp"], d_losses["_gl"] = sp.detach(), gl.detach()
         d_losses.update({"_metric:" + k: v for k, v in d_metrics.items()})
         if step:
-            self.optimizer_D.step()
+            self.exchange_and_step(self.optimizer_D, self.Dparams)
         return d_losses
 
     def _r1_body(self, images, step=True):
@@ -94,7 +194,7 @@ class SwappingAutoencoderOptimizer:
         r1_losses = self.model(images, command="compute_R1_loss")
         (sum(v.mean() for v in r1_losses.values()) * self.opt.R1_once_every).backward()
         if step:
-            self.optimizer_D.step()
+            self.exchange_and_step(self.optimizer_D, self.Dparams)
         return r1_losses
 
     def _run(self, kind, images):
@@ -129,5 +229,39 @@ class SwappingAutoencoderOptimizer:
         with torch.no_grad():
             return self.model(self.prepare_images(data_i), command="get_visuals_for_snapshot")
 
+    # ------------------------------------------------------------------ checkpointing
+    def state_dict(self):
+        """Adam state of both groups (torch.optim.Adam's format) + the schedule counters.  The reference never saves this
+        (optimizers/base_optimizer.py has no state I/O): resuming there restarts Adam's moments from zero."""
+        return {"optimizer_G": self.optimizer_G.state_dict(), "optimizer_D": self.optimizer_D.state_dict(),
+                "train_mode_counter": self.train_mode_counter, "discriminator_iter_counter": self.discriminator_iter_counter}
+
+    def load_state_dict(self, sd):
+        self.optimizer_G.load_state_dict(sd["optimizer_G"])
+        self.optimizer_D.load_state_dict(sd["optimizer_D"])
+        self.train_mode_counter = int(sd.get("train_mode_counter", 0))
+        self.discriminator_iter_counter = int(sd.get("discriminator_iter_counter", 0))
+
+    def _optimizer_path(self, total_steps_so_far=None):
+        inner = getattr(self.model, "singlegpu_model", self.model)
+        name = "latest_optimizer.pth" if total_steps_so_far is None else "%dk_optimizer.pth" % (total_steps_so_far // 1000)
+        return os.path.join(inner._checkpoint_dir(), name)
+
     def save(self, total_steps_so_far):
+        """model checkpoint in the reference's format (models/base_model.py:33-41) + ``<N>k_optimizer.pth`` beside it"""
         self.model.save(total_steps_so_far)
+        if getattr(self.model, "rank", 0) == 0:
+            path = self._optimizer_path(total_steps_so_far)
+            torch.save(self.state_dict(), path)
+            link = self._optimizer_path(None)
+            if os.path.lexists(link):
+                os.remove(link)
+            os.symlink(os.path.basename(path), link)
+
+    def load(self, path=None):
+        """restore the optimizer state written by ``save`` (missing file: keep the fresh state, like the reference)"""
+        path = path or self._optimizer_path(None)
+        if not os.path.exists(path):
+            return False
+        self.load_state_dict(torch.load(path, map_location=str(self.Gparams[0].device)))
+        return True

@@ -38,30 +38,44 @@ def init_distributed(backend_name=None):
 
 
 class GradientBucket:
-    """Persistent flat buffer + cached device pointer tables for one set of gradient tensors."""
+    """Persistent flat buffer + cached device tables for the gradient tensors of one parameter set."""
 
     def __init__(self, device):
         self.device = device
         self.flat = None
-        self.tables = {}     # key (tuple of data_ptrs) -> (ptrs, offsets, sizes, total)
+        self.layouts = {}     # tuple of sizes -> (offsets tensor, sizes tensor, total, offsets list)
+        self.tables = None    # backend.PointerTables, created with the first CUDA bucket
 
-    def _table(self, grads):
-        key = tuple(g.data_ptr() for g in grads)
-        hit = self.tables.get(key)
-        if hit is not None:
-            return hit
-        sizes = [g.numel() for g in grads]
-        offsets, total = [], 0
-        for s in sizes:
-            offsets.append(total)
-            total += (s + 3) // 4 * 4            # keep every segment 16-byte aligned
-        dev = self.device
-        entry = (torch.tensor(key, dtype=torch.int64, device=dev), torch.tensor(offsets, dtype=torch.int64, device=dev),
-                 torch.tensor(sizes, dtype=torch.int64, device=dev), total, offsets, sizes)
-        if len(self.tables) > 16:
-            self.tables.clear()
-        self.tables[key] = entry
-        return entry
+    def _layout(self, grads):
+        key = tuple(g.numel() for g in grads)
+        hit = self.layouts.get(key)
+        if hit is None:
+            offsets, total = [], 0
+            for s in key:
+                offsets.append(total)
+                total += (s + 3) // 4 * 4            # keep every segment 16-byte aligned
+            dev = self.device
+            hit = (torch.tensor(offsets, dtype=torch.int64, device=dev), torch.tensor(key, dtype=torch.int64, device=dev), total,
+                   offsets)
+            self.layouts[key] = hit
+        return hit
+
+    def reserve(self, total):
+        if self.flat is None or self.flat.numel() < total:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+
+    def pack_all_reduce(self, grads):
+        """SUM over ranks of the given gradient tensors, left in the flat bucket; returns one bucket view per gradient"""
+        offsets_t, sizes_t, total, offsets = self._layout(grads)
+        self.reserve(total)
+        flat = self.flat[:total]
+        if self.tables is None:
+            self.tables = backend.PointerTables(max(len(grads), 1024), self.device)
+        ptrs = self.tables.get(tuple(g.data_ptr() for g in grads))
+        k = backend.kernels()
+        k.bucket_pack(ptrs, offsets_t, sizes_t, len(grads), flat)
+        dist.all_reduce(flat)
+        return [flat[o:o + g.numel()].view_as(g) for o, g in zip(offsets, grads)], (ptrs, offsets_t, sizes_t, flat)
 
     def all_reduce_mean(self, grads, world):
         if not grads:
@@ -76,14 +90,8 @@ class GradientBucket:
                 g.copy_(flat[o:o + g.numel()].view_as(g))
                 o += g.numel()
             return
-        ptrs, offsets, sizes, total, _, _ = self._table(grads)
-        if self.flat is None or self.flat.numel() < total:
-            self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        flat = self.flat[:total]
-        k = backend.kernels()
-        k.bucket_pack(ptrs, offsets, sizes, len(grads), flat)
-        dist.all_reduce(flat)
-        k.bucket_unpack(ptrs, offsets, sizes, len(grads), flat, 1.0 / world)
+        _, (ptrs, offsets_t, sizes_t, flat) = self.pack_all_reduce(grads)
+        backend.kernels().bucket_unpack(ptrs, offsets_t, sizes_t, len(grads), flat, 1.0 / world)
 
 
 class MultiGPUModelWrapper:
@@ -98,6 +106,9 @@ class MultiGPUModelWrapper:
         self.device = next(model.parameters()).device
         self._pending = False
         self.suspend_reduce = False           # set while a half-step is being captured into a CUDA graph (graphs.py)
+        # set by an optimizer that calls reduce_to_bucket() itself and reads the bucket (optimizer.py): the end-of-backward
+        # callback, which averages INTO p.grad for a stock optimizer, is then not queued
+        self.defer_to_optimizer = False
         self._bucket = GradientBucket(self.device)
         model(command="per_gpu_initialize")
         if self.world > 1:
@@ -109,7 +120,7 @@ class MultiGPUModelWrapper:
 
     # the hook fires once per parameter per backward; only the first one queues the callback
     def _on_grad(self, param):
-        if self.suspend_reduce:
+        if self.suspend_reduce or self.defer_to_optimizer:
             return
         if not self._pending:
             self._pending = True
@@ -125,6 +136,26 @@ class MultiGPUModelWrapper:
         """explicit form of the end-of-backward callback (used after a CUDA-graph replay, where autograd does not run)"""
         if self.world > 1:
             self._reduce_gradients()
+
+    def reduce_to_bucket(self, params):
+        """Gradient exchange for an optimizer that reads the bucket directly (optimizer.MultiTensorAdam.step(grads=...)):
+        packs the existing gradients of ``params``, all-reduces (SUM) and returns a list aligned with ``params`` of views
+        into the flat bucket (None where a parameter has no gradient).  Nothing is written back to ``p.grad``: the 1/world
+        factor is the optimizer's ``grad_scale``.  On a CPU group (gloo tests) the views hold the same sums."""
+        present = [p for p in params if p.grad is not None]
+        if not present:
+            return [None] * len(params)
+        if self.device.type != "cuda":
+            flat = torch.cat([p.grad.reshape(-1) for p in present])
+            dist.all_reduce(flat)
+            views, o = [], 0
+            for p in present:
+                views.append(flat[o:o + p.numel()].view_as(p))
+                o += p.numel()
+        else:
+            views, _ = self._bucket.pack_all_reduce([p.grad for p in present])
+        it = iter(views)
+        return [next(it) if p.grad is not None else None for p in params]
 
     def get_parameters_for_mode(self, mode):
         return self.singlegpu_model.get_parameters_for_mode(mode)
@@ -143,4 +174,5 @@ class MultiGPUModelWrapper:
         return batch[self.rank * per:(self.rank + 1) * per]
 
     def __call__(self, *args, **kwargs):
+        self._pending = False        # a backward that raised after queueing the callback must not block the next one
         return self.singlegpu_model(*args, **kwargs)

@@ -19,10 +19,10 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from .stylegan2_op.blocks import FirSpec, ResBlockSpec, fused_blocks_enabled, resblock
+from .stylegan2_op.blocks import FirSpec, ResBlockSpec, fir_noise_bias_act, fused_blocks_enabled, resblock
 from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv2d_bias_act, conv2d_noise_bias_act, conv2d_residual,
                            conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, memo, modulate, reflect_pad,
-                           upfirdn2d)
+                           torgb, upfirdn2d)
 
 _SQRT2 = math.sqrt(2.0)
 
@@ -319,6 +319,21 @@ class StyledConv(nn.Module):
                                              negative_slope=act.negative_slope, scale=gain)
             out = conv2d(x, w, padding=conv.padding)
             return fused_leaky_relu(out + self.noise.weight * z, act.bias, act.negative_slope, gain)   # broadcast noise: unfused
+        if conv.upsample and not conv.blur.reflection and conv.out_channel % 4 == 0:
+            # transposed conv, then blur + noise + bias + activation as ONE pass (no standalone blur launch, the blurred tensor
+            # never reaches HBM)
+            blur = conv.blur
+            u = conv_transpose2d(conv.modulated_input(input, style), conv.filter(), stride=2, padding=0)
+            k = blur.kernel.shape[0]
+            oh, ow = u.shape[2] + blur.pad[0] + blur.pad[1] - k + 1, u.shape[3] + blur.pad[0] + blur.pad[1] - k + 1
+            z = None
+            if self.use_noise:
+                z = self.noise.resolve_noise(_ShapeOnly(torch.Size((u.shape[0], conv.out_channel, oh, ow)), u), noise)
+            if z is None or (z.shape[0] == u.shape[0] and z.shape[1] == 1 and tuple(z.shape[2:]) == (oh, ow)):
+                return fir_noise_bias_act(u, FirSpec(blur.kernel, blur.pad, blur.taps, 1), z, self.noise.weight, act.bias,
+                                          act.negative_slope, gain)
+            out = blur(u)
+            return fused_leaky_relu(out + self.noise.weight * z, act.bias, act.negative_slope, gain)   # broadcast noise: unfused
         out = conv(input, style)
         if not self.use_noise:
             return fused_leaky_relu(out, act.bias, act.negative_slope, gain)
@@ -339,7 +354,15 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
     def forward(self, input, style, skip=None):
-        out = self.conv(input, style) + self.bias
+        conv = self.conv
+        if (style.dim() <= 2 and not conv.demodulate and conv.kernel_size == 1 and conv.out_channel == 3
+                and not (conv.upsample or conv.downsample) and input.shape[1] % 4 == 0 and input.shape[1] <= 1024):
+            # one pass over the input: style scale, 1x1 conv to 3 channels and bias together (csrc/torgb.cu); no modulated
+            # copy of the generator's largest activation, no N = 3 GEMM
+            s = conv.modulation(style.reshape(input.shape[0], -1))
+            out = torgb(input, s, conv.weight[0], self.bias, conv.scale)
+        else:
+            out = conv(input, style) + self.bias
         if skip is not None:
             out = out + self.upsample(skip)
         return out

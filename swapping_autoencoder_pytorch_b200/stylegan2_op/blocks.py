@@ -123,6 +123,47 @@ class FirSpec:
         return gi, gb
 
 
+class _FirNoiseBiasAct(Function):
+    """lrelu(blur(x) + noise_weight * noise + bias) * gain — the Blur behind the generator's transposed convolution and the
+    StyledConv tail after it (stylegan2_layers.py:306-309, :398-405) in ONE kernel (``sae_fir_bias_act``): the blurred tensor
+    never exists in HBM.  Backward: masked gradient + bias / noise-weight gradients in one pass, then the adjoint FIR.
+    Generator only, hence once-differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, spec, noise, noise_weight, bias, slope, gain):
+        k = backend.kernels()
+        xh = _nhwc(x)
+        p0, p1 = spec.pad
+        noise_flat = noise.reshape(-1).contiguous() if noise is not None else None
+        nw = noise_weight.contiguous() if noise is not None else None
+        out = None
+        if spec.taps is not None and spec.down == 1:
+            out = k.fir_bias_act(xh, spec.taps, (p0, p1, p0, p1), bias.contiguous(), noise_flat, nw, slope, gain)
+        if out is None:
+            out = k.bias_act(spec.forward(k, xh), bias.contiguous(), None, 3, 0, slope, gain, noise=noise_flat, noise_weight=nw)
+        ctx.spec, ctx.cfg = spec, (slope, gain, tuple(noise.shape) if noise is not None else None, xh.shape[1], xh.shape[2])
+        ctx.save_for_backward(out, noise_flat, nw)
+        return _nchw(out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        out, noise_flat, nw = ctx.saved_tensors
+        slope, gain, noise_shape, in_h, in_w = ctx.cfg
+        k = backend.kernels()
+        gi, gb, gnw = k.bias_act_backward(_nhwc(dy), out, slope, gain, want_bias=True, noise=noise_flat)
+        dx = _nchw(ctx.spec.adjoint(k, gi, in_h, in_w)) if ctx.needs_input_grad[0] else None
+        g_noise = None
+        if noise_flat is not None and ctx.needs_input_grad[2]:
+            g_noise = (gi.sum(dim=3) * nw).reshape(noise_shape)
+        return dx, None, g_noise, gnw, gb, None, None
+
+
+def fir_noise_bias_act(x, spec, noise, noise_weight, bias, slope, gain):
+    """``fused_leaky_relu(upfirdn2d(x, kernel, pad=spec.pad) + noise_weight * noise, bias, slope, gain)`` in one pass"""
+    return _FirNoiseBiasAct.apply(x, spec, noise, noise_weight, bias, slope, gain)
+
+
 class ResBlockSpec:
     """host-side constants of one ResBlock (scales, activation constants, the two FIRs)"""
 

@@ -268,6 +268,33 @@ class _PadChannels(Function):
         return dy[:, :ctx.c_in], None
 
 
+class _ViewAsPadded(Function):
+    """[N, c, H, W] view of a channels-last buffer whose channels c..C-1 are known to be zero  ->  the [N, C, H, W] view of the
+    same memory (no kernel, no copy).  Only for buffers a producer of this library marked ``_sae_zero_padded`` (the crop
+    resampler, util._CropGather).  Adjoint = channel slice, as for _PadChannels."""
+
+    @staticmethod
+    def forward(ctx, x, c_out):
+        n, c, h, w = x.shape
+        ctx.c_in = c
+        return torch.as_strided(x, (n, c_out, h, w), (h * w * c_out, 1, w * c_out, c_out), x.storage_offset())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy[:, :ctx.c_in], None
+
+
+def _zero_padded_width(x):
+    """C when ``x`` is the leading-channels view of a channels-last [N, H, W, C] buffer marked zero-padded by its producer"""
+    base = x._base
+    cp = getattr(base, "_sae_zero_padded", 0) if base is not None else 0
+    if cp and x.dim() == 4:
+        n, c, h, w = x.shape
+        if c < cp and x.stride() == (h * w * cp, 1, w * cp, cp) and x.storage_offset() % cp == 0:
+            return cp
+    return 0
+
+
 def _pad4(input, weight):
     """RGB tensors (3 channels) are zero-padded to 4 so rows are 16-byte aligned and the kernels keep their vector
     / TMA paths (the pad and the matching slice are differentiable torch ops on tiny tensors).  Returns
@@ -277,7 +304,10 @@ def _pad4(input, weight):
         # RGB inputs go to 32 channels: one 128-byte TMA row per pixel, so FromRGB / the first Dpatch conv and their
         # weight gradients run on the tensor-core kernels (the extra zero channels cost 1/4 of the 128-channel output)
         extra = (32 - cin) if cin < 32 else 4 - cin % 4
-        input = _PadChannels.apply(input, cin + extra)
+        if _zero_padded_width(input) == cin + extra:
+            input = _ViewAsPadded.apply(input, cin + extra)        # the producer already wrote the padded layout
+        else:
+            input = _PadChannels.apply(input, cin + extra)
         weight = memo(weight, ("pad_cin", extra), lambda w=weight: F.pad(w, (0, 0, 0, 0, 0, extra)))
     cout = weight.shape[0]
     if cout % 4 != 0:
@@ -381,6 +411,41 @@ class _Modulate(Function):
 
 def modulate(x, s):
     return _Modulate.apply(x, s)
+
+
+class _ToRGB(Function):
+    """bias + conv1x1(x * s, w * wscale) with 3 output channels as ONE pass over x (csrc/torgb.cu) — the generator's ToRGB
+    (stylegan2_layers.py:408-427: ModulatedConv2d(in, 3, 1, demodulate=False) + bias).  Backward is one more pass over x:
+    dx and the per-sample outer products G[n] = sum_p dy (x) x, from which ds and dw follow on [N, 3, C] values.
+    Generator only: once-differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, s, w, bias, wscale):
+        xh, sc, wc = _nhwc(x), s.contiguous(), w.reshape(3, -1).contiguous()
+        y = backend.kernels().torgb_forward(xh, sc, wc, bias.reshape(-1).contiguous() if bias is not None else None, wscale)
+        ctx.save_for_backward(xh, sc, wc)
+        ctx.wscale, ctx.w_shape, ctx.bias_shape = wscale, tuple(w.shape), (tuple(bias.shape) if bias is not None else None)
+        return _nchw(y)[:, :3]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xh, sc, wc = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dx, gw = backend.kernels().torgb_backward(dy, xh, sc, wc, ctx.wscale, want_dx=need[0], want_gw=need[1] or need[2])
+        ds = dw = db = None
+        if need[1]:
+            ds = (gw * wc.unsqueeze(0)).sum(dim=1) * ctx.wscale
+        if need[2]:
+            dw = ((gw * sc.unsqueeze(1)).sum(dim=0) * ctx.wscale).reshape(ctx.w_shape)
+        if need[3]:
+            db = dy.sum(dim=(0, 2, 3)).reshape(ctx.bias_shape)
+        return (_nchw(dx) if dx is not None else None), ds, dw, db, None
+
+
+def torgb(x, s, w, bias, wscale):
+    """``F.conv2d(x * s[:, :, None, None], w * wscale) + bias`` for a [3, C, 1, 1] filter (C % 4 == 0, C <= 1024)"""
+    return _ToRGB.apply(x, s, w, bias, float(wscale))
 
 
 class _AddScale(Function):

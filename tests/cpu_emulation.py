@@ -159,3 +159,62 @@ class EmulatedKernels:
 
     def bucket_unpack(self, *a):
         raise NotImplementedError
+
+    # ------------------------------------------------------------------ crops / Adam
+    def crop_gather(self, x, flip, scale, offset, num_crops, size, c_pad, out=None):
+        """F.grid_sample formulation of reference util/util.py:323-343, output NHWC zero-padded to ``c_pad`` channels"""
+        if out is not None:
+            out.copy_(self.crop_gather(x, flip, scale, offset, num_crops, size, c_pad))
+            return out
+        q = flip.numel()
+        lin = torch.linspace(-1.0, 1.0, size, dtype=x.dtype)
+        gx = lin.view(1, 1, size, 1).expand(q, size, size, 1)
+        gy = lin.view(1, size, 1, 1).expand(q, size, size, 1)
+        unit = torch.cat([gx * flip.view(q, 1, 1, 1), gy], dim=3)
+        grid = unit * scale.view(q, 1, 1, 2) + offset.view(q, 1, 1, 2)
+        xx = x.unsqueeze(1).expand(-1, num_crops, -1, -1, -1).flatten(0, 1)
+        crop = F.grid_sample(xx, grid.to(x.dtype), align_corners=False)
+        out = torch.zeros(q, size, size, c_pad, dtype=x.dtype)
+        out[..., :x.shape[1]] = crop.permute(0, 2, 3, 1)
+        return out
+
+    def crop_gather_backward(self, dy, flip, scale, offset, num_crops, c, h, w):
+        q = flip.numel()
+        x = torch.zeros(q // num_crops, c, h, w, dtype=dy.dtype, requires_grad=True)
+        with torch.enable_grad():
+            y = self.crop_gather(x, flip, scale, offset, num_crops, dy.shape[2], 4)[..., :c].permute(0, 3, 1, 2)
+            gx, = torch.autograd.grad(y, x, dy[:, :c])
+        return gx
+
+    def adam_step(self, params, grads, offsets, sizes, exp_avg, exp_avg_sq, steps, lr, beta1, beta2, eps, grad_scale, cache):
+        """torch.optim.Adam's documented update, written out per parameter (include/sae_b200.h sae_adam_step)"""
+        with torch.no_grad():
+            for i, (p, g) in enumerate(zip(params, grads)):
+                if g is None:
+                    continue
+                o, n = int(offsets[i]), int(sizes[i])
+                m, v = exp_avg[o:o + n].view_as(p), exp_avg_sq[o:o + n].view_as(p)
+                steps[i] += 1
+                t = float(steps[i])
+                g = g * grad_scale
+                m.add_((1 - beta1) * (g - m))
+                v.mul_(beta2).add_((1 - beta2) * g * g)
+                p.sub_(lr / (1 - beta1 ** t) * m / (v.sqrt() / (1 - beta2 ** t) ** 0.5 + eps))
+
+    def torgb_forward(self, x, s, w, bias, wscale):
+        y = torch.einsum("nhwc,nc,oc->nhwo", x, s * wscale, w)
+        if bias is not None:
+            y = y + bias
+        return torch.cat([y, torch.zeros_like(y[..., :1])], dim=3)
+
+    def torgb_backward(self, dy, x, s, w, wscale, want_dx=True, want_gw=True):
+        d = dy.permute(0, 2, 3, 1)[..., :3]
+        dx = torch.einsum("nhwo,nc,oc->nhwc", d, s * wscale, w) if want_dx else None
+        gw = torch.einsum("nhwo,nhwc->noc", d, x) if want_gw else None
+        return dx, gw
+
+    def fir_bias_act(self, x, taps, pad, bias, noise, noise_weight, alpha, scale):
+        kernel = torch.outer(torch.tensor(taps[0]), torch.tensor(taps[1])).to(x.dtype)
+        px0, px1, py0, py1 = pad
+        y = self.upfirdn2d(x, kernel, 1, 1, 1, 1, px0, px1, py0, py1)
+        return self.bias_act(y, bias, None, 3, 0, alpha, scale, noise=noise, noise_weight=noise_weight)

@@ -26,10 +26,10 @@ def _sync_state(src, dst):
         for a, b in zip(list(ms.parameters()) + list(ms.buffers()), list(md.parameters()) + list(md.buffers())):
             b.copy_(a)
         for os_, od in ((src.optimizer_G, dst.optimizer_G), (src.optimizer_D, dst.optimizer_D)):
-            for ps, pd in zip(os_.param_groups[0]["params"], od.param_groups[0]["params"]):
-                if ps in os_.state and pd in od.state:
-                    for key, val in os_.state[ps].items():
-                        od.state[pd][key].copy_(val)
+            a, b = os_._state(), od._state()           # flat moments + per-parameter step counts (optimizer.MultiTensorAdam)
+            b.exp_avg.copy_(a.exp_avg)
+            b.exp_avg_sq.copy_(a.exp_avg_sq)
+            b.steps.copy_(a.steps)
 
 
 def _teacher_forced_run(real, det):

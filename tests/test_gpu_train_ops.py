@@ -1,0 +1,270 @@
+"""GPU (B200): the kernels either side of the network passes through the C ABI —
+``sae_crop_gather`` / ``sae_crop_gather_backward`` against the oracle's F.grid_sample formulation (reference
+util/util.py:323-343), ``sae_adam_step`` against ``torch.optim.Adam``, the lazy loss read-back, and the closed-form R1 double
+backward of the fused blocks against ordinary autograd through the per-operator nodes."""
+import pytest
+import torch
+
+from oracle import sae_oracle as O
+from oracle.fixtures import TINY, rel_err, rel_l2, rnd
+from swapping_autoencoder_pytorch_b200 import backend, default_options, util
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture
+def exact_fp32():
+    kern = backend.kernels()
+    prev, kern.round_tf32 = kern.round_tf32, False
+    yield
+    kern.round_tf32 = prev
+
+
+class _Draws:
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+
+    def draw(self, b, lo, hi):
+        r = lambda *shape: torch.rand(*shape, generator=self.gen, dtype=torch.float64)      # noqa: E731
+        flip = torch.round(r(b, 1, 1, 1)) * 2 - 1.0
+        scale = r(b, 1, 1, 2) * (hi - lo) + lo
+        offset = (r(b, 1, 1, 2) * 2 - 1) * (1 - scale)
+        return flip, scale, offset
+
+
+@pytest.mark.parametrize("b,res,size,n,strided", [(3, 256, 128, 8, False), (2, 256, 64, 8, True), (2, 64, 32, 2, False),
+                                                  (1, 96, 17, 3, True)])
+def test_crop_gather_against_oracle(b, res, size, n, strided, exact_fp32, monkeypatch):
+    """forward, the zero-padded 32-channel layout, and the adjoint; ``strided``: the source is the 3-channel view of a 4-channel
+    channels-last tensor (what the generator's ToRGB hands over)"""
+    opt = default_options(patch_size=size, patch_num_crops=n)
+    x64 = rnd(5, b, 3, res, res + (8 if strided else 0))
+    x64 = x64[..., :res] if strided else x64
+    draws = _Draws(11)
+    monkeypatch.setattr(O, "draw_crop_parameters", lambda B, o: draws.draw(B, o.patch_min_scale, o.patch_max_scale))
+    xr = x64.clone().requires_grad_()
+    ref = O.random_crops(xr, opt)
+    w = rnd(6, *ref.shape)
+    gref, = torch.autograd.grad((ref * w).sum(), xr)
+    draws2 = _Draws(11)
+    monkeypatch.setattr(util, "draw_crop_parameters",
+                        lambda B, sr, device: tuple(t.float().to(device) for t in draws2.draw(B, sr[0], sr[1])))
+    if strided:
+        base = torch.zeros(b, res, res, 4, device=DEV)
+        base[..., :3] = x64.float().to(DEV).permute(0, 2, 3, 1)
+        xg = base.permute(0, 3, 1, 2)[:, :3].requires_grad_()
+    else:
+        xg = x64.float().to(DEV).requires_grad_()
+    got = util.apply_random_crop(xg, size, (opt.patch_min_scale, opt.patch_max_scale), num_crops=n)
+    assert got.shape == ref.shape
+    # fp32 sampling coordinates (as in F.grid_sample's own fp32 path): at 256 pixels one ulp of a coordinate is 3e-5 pixel, and
+    # the white-noise test image changes by O(1) per pixel -> 1e-4 of max|ref|; the reference here is fp64 throughout
+    tol = 1e-4
+    assert rel_err(got, ref) < tol, rel_err(got, ref)
+    flat = got.flatten(0, 1)
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import conv as C
+    assert C._zero_padded_width(flat) == 32
+    assert float(flat._base[..., 3:].abs().max()) == 0.0
+    g, = torch.autograd.grad((got * w.float().to(DEV)).sum(), xg)
+    assert rel_err(g, gref) < tol, rel_err(g, gref)
+    # a convolution on the crops takes the padded buffer as it is (no pad kernel) and matches the padded reference
+    wt = rnd(7, 32, 3, 3, 3)
+    y = C.conv2d(flat, wt.float().to(DEV), padding=1)
+    yr = torch.nn.functional.conv2d(ref.detach().flatten(0, 1), wt, padding=1)
+    assert rel_err(y, yr) < 1e-3
+
+
+@pytest.mark.parametrize("betas", [(0.0, 0.99), (0.5, 0.9)])
+def test_adam_step_against_torch(betas):
+    from swapping_autoencoder_pytorch_b200.optimizer import MultiTensorAdam
+    shapes = [(64, 32, 3, 3), (7,), (1,), (33, 5), (2048, 130), (3, 1, 1, 1)]
+    torch.manual_seed(0)
+    ours = [torch.randn(s, device=DEV).requires_grad_() for s in shapes]
+    ref = [p.detach().clone().requires_grad_() for p in ours]
+    a = MultiTensorAdam(ours, lr=0.002, betas=betas)
+    b = torch.optim.Adam(ref, lr=0.002, betas=betas)
+    for it in range(6):
+        for i, (p, q) in enumerate(zip(ours, ref)):
+            g = torch.randn_like(p) * (10.0 ** (i - 3))
+            skip = (it % 2 == 1 and i in (1, 3))           # parameters without a gradient keep their own step count
+            p.grad = None if skip else g.clone()
+            q.grad = None if skip else g.clone()
+        a.step()
+        b.step()
+        for p, q in zip(ours, ref):
+            assert rel_err(p, q) < 2e-6, (it, tuple(p.shape), rel_err(p, q))
+    sd = a.state_dict()
+    ref_sd = b.state_dict()
+    for i in ref_sd["state"]:
+        assert float(sd["state"][i]["step"]) == float(ref_sd["state"][i]["step"])
+        assert rel_err(sd["state"][i]["exp_avg_sq"], ref_sd["state"][i]["exp_avg_sq"]) < 2e-6
+    # bucket-style gradients with the 1/world factor folded in
+    views = [torch.full_like(p, 4.0) for p in ours]
+    for q in ref:
+        q.grad = torch.full_like(q, 2.0)
+    a.step(grads=views, grad_scale=0.5)
+    b.step()
+    for p, q in zip(ours, ref):
+        assert rel_err(p, q) < 2e-6
+    # the stock optimizer loads this optimizer's state and continues identically
+    c = torch.optim.Adam([p.detach().clone().requires_grad_() for p in ours], lr=0.002, betas=betas)
+    c.load_state_dict(a.state_dict())
+    for p, q in zip(ours, c.param_groups[0]["params"]):
+        p.grad = torch.ones_like(p)
+        q.grad = torch.ones_like(q)
+    a.step()
+    c.step()
+    for p, q in zip(ours, c.param_groups[0]["params"]):
+        assert rel_err(p, q) < 2e-6
+
+
+def test_lazy_loss_readback():
+    losses = {"a": torch.full((4,), 2.0, device=DEV), "b": torch.arange(3.0, device=DEV)}
+    out = util.to_numpy(losses, lazy=True)
+    assert isinstance(out, util.LazyLosses) and "a" in out and list(out) == ["a", "b"] and len(out) == 2
+    assert out._pending is not None                    # nothing waited for yet
+    assert float(out["a"]) == 2.0 and float(out["b"]) == 1.0 and out._pending is None
+    eager = util.to_numpy(losses)
+    assert float(eager["a"]) == 2.0 and float(eager["b"]) == 1.0
+
+
+def test_closed_form_r1_double_backward_on_gpu():
+    """_ResBlockDataGrad (inside data_gradients_only()) against autograd through the per-operator nodes, at a discriminator
+    shape (tcgen05 kernels) and a small one: dx, the second-order gradients of all three filters and of the upstream gradient"""
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import blocks
+    import contextlib
+    for cin, cout, n, hw in ((128, 256, 2, 64), (32, 64, 3, 33)):
+        torch.manual_seed(cin)
+        m = L.ResBlock(cin, cout).to(DEV)
+        with torch.no_grad():
+            m.conv1.Act.bias.normal_(0, 0.1)
+            m.conv2.Act.bias.normal_(0, 0.1)
+        weights = [m.conv1.Conv.weight, m.conv2.Conv.weight, m.skip.Conv.weight]
+        x0 = torch.randn(n, cin, hw, hw, device=DEV)
+        w0 = torch.randn(n, cout, hw // 2, hw // 2, device=DEV)
+        res = {}
+        for mode in ("closed_form", "per_operator"):
+            prev = blocks.set_fused_blocks(mode == "closed_form")
+            try:
+                x, w = x0.clone().requires_grad_(), w0.clone().requires_grad_()
+                with (blocks.data_gradients_only() if mode == "closed_form" else contextlib.nullcontext()):
+                    gx, = torch.autograd.grad((m(x) * w).sum(), x, create_graph=True)
+                    second = torch.autograd.grad(gx.pow(2).sum(), weights + [w])
+                res[mode] = [gx.detach()] + list(second)
+            finally:
+                blocks.set_fused_blocks(prev)
+        for i, (a, b) in enumerate(zip(res["closed_form"], res["per_operator"])):
+            # same kernels, different TF32 rounding points of intermediates
+            assert rel_l2(a, b) < 2e-3 and rel_err(a, b) < 1e-2, (cin, i, rel_l2(a, b), rel_err(a, b))
+
+
+def test_r1_half_step_time_and_losses_tiny():
+    """one D step with R1 through the public driver; the R1 loss agrees between the closed-form and the general path"""
+    import swapping_autoencoder_pytorch_b200 as S
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import blocks, conv as C
+    opt = default_options(**dict(TINY, num_gpus=1, R1_once_every=1))
+    torch.manual_seed(0)
+    model = S.create_model(opt)
+    real = torch.randn(2, 3, 64, 64, device=DEV).clamp(-1, 1)
+    inner = model.singlegpu_model
+    out = {}
+    for mode in ("closed", "general"):
+        torch.manual_seed(5)
+        for p in inner.parameters():
+            p.grad = None
+        if mode == "closed":
+            r1 = inner(real.clone(), command="compute_R1_loss")["D_R1"]
+        else:
+            with blocks.per_operator_blocks():
+                prev = C.set_data_gradients_only(False)
+                try:
+                    r1 = inner._compute_R1_loss(real.clone())["D_R1"]
+                finally:
+                    C.set_data_gradients_only(prev)
+        r1.mean().backward()
+        out[mode] = (r1.detach().clone(), inner.D.stylegan2_D.convs[1].conv1.Conv.weight.grad.clone(),
+                     inner.Dpatch.convs[1].conv2.Conv.weight.grad.clone())
+    assert rel_err(out["closed"][0], out["general"][0]) < 2e-3
+    assert rel_l2(out["closed"][1], out["general"][1]) < 2e-2 and rel_l2(out["closed"][2], out["general"][2]) < 2e-2
+
+
+@pytest.mark.parametrize("n,c,hw", [(3, 128, 64), (2, 64, 33), (2, 204, 16), (1, 512, 8), (2, 1024, 5)])
+def test_torgb_kernel_against_oracle(n, c, hw, exact_fp32):
+    """csrc/torgb.cu: (1) the op with a given per-sample scale — forward and the gradients of input, scale, filter and bias
+    against fp64 (plain fp32 FMA arithmetic: 1e-5); (2) through the ToRGB module, whose style path adds a TF32 linear — against
+    the oracle's modulated_conv2d(demodulate=False) + bias at the per-op TF32 tolerance"""
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import torgb
+    x, s, w, b = rnd(5, n, c, hw, hw + 1), rnd(6, n, c) * 0.3 + 1, rnd(1, 3, c, 1, 1), rnd(4, 1, 3, 1, 1) * 0.1
+    wscale = 1.0 / c ** 0.5
+    ref_in = [t.clone().requires_grad_() for t in (x, s, w, b)]
+    y_ref = torch.nn.functional.conv2d(ref_in[0] * ref_in[1][:, :, None, None], ref_in[2] * wscale) + ref_in[3]
+    wgt = rnd(7, *y_ref.shape)
+    gref = torch.autograd.grad((y_ref * wgt).sum(), ref_in)
+    got_in = [t.float().to(DEV).requires_grad_() for t in (x, s, w, b)]
+    y = torgb(*got_in, wscale)
+    assert y.shape == y_ref.shape and rel_err(y, y_ref) < 1e-5, rel_err(y, y_ref)
+    got = torch.autograd.grad((y * wgt.float().to(DEV)).sum(), got_in)
+    for name, a, r in zip(("x", "scale", "weight", "bias"), got, gref):
+        assert rel_err(a, r) < 2e-5, (name, rel_err(a, r))
+    # the gradient may arrive in any layout (crop adjoint: NCHW-contiguous; image losses: channels-last views)
+    g2, = torch.autograd.grad(torgb(*got_in, wscale), got_in[0], wgt.float().to(DEV).contiguous())
+    assert rel_err(g2, gref[0]) < 2e-5
+    # (2) module level
+    P = {"conv.weight": w[None], "conv.modulation.weight": rnd(2, c, 16), "conv.modulation.bias": rnd(3, c) * 0.1 + 1, "bias": b}
+    m = L.ToRGB(c, 16, upsample=False)
+    sd = m.state_dict()
+    sd.update({k: v.float() for k, v in P.items()})
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    st = rnd(8, n, 16)
+    xr, sr = x.clone().requires_grad_(), st.clone().requires_grad_()
+    y_ref = O.modulated_conv2d({"t." + k: v for k, v in P.items()}, "t.conv", xr, sr, 1, demodulate=False) + P["bias"]
+    gxr, gsr = torch.autograd.grad((y_ref * wgt).sum(), [xr, sr])
+    xg, sg = x.float().to(DEV).requires_grad_(), st.float().to(DEV).requires_grad_()
+    ym = m(xg, sg)
+    gx, gs = torch.autograd.grad((ym * wgt.float().to(DEV)).sum(), [xg, sg])
+    assert rel_err(ym, y_ref) < 1e-3 and rel_err(gx, gxr) < 2e-3 and rel_err(gs, gsr) < 3e-3, (rel_err(ym, y_ref), rel_err(gx, gxr), rel_err(gs, gsr))
+
+
+@pytest.mark.parametrize("kh,c,h,pad,with_noise", [(4, 128, 65, (1, 1), True), (4, 32, 33, (1, 1), False), (3, 64, 40, (1, 1), True),
+                                                   (4, 512, 17, (1, 1), True)])
+def test_fir_bias_act_fused(kh, c, h, pad, with_noise, exact_fp32):
+    """sae_fir_bias_act == sae_upfirdn2d_separable followed by sae_fused_bias_act (noise + bias + leaky-ReLU), and the
+    autograd Function around it (forward, input / bias / noise-weight gradients) against the oracle in fp64"""
+    from swapping_autoencoder_pytorch_b200.stylegan2_op.blocks import FirSpec, fir_noise_bias_act
+    kern = backend.kernels()
+    taps1 = [1.0, 3.0, 3.0, 1.0] if kh == 4 else [1.0, 2.0, 1.0]
+    t = tuple(2.0 * v / sum(taps1) for v in taps1)                       # the generator's blur carries the x4 upsampling gain
+    kernel = torch.outer(torch.tensor(t), torch.tensor(t)).to(DEV)
+    n = 3
+    x = torch.randn(n, h, h + 2, c, device=DEV)
+    oh, ow = h + pad[0] + pad[1] - kh + 1, h + 2 + pad[0] + pad[1] - kh + 1
+    bias = torch.randn(c, device=DEV) * 0.1
+    noise = torch.randn(n, oh, ow, device=DEV) if with_noise else None
+    nw = torch.tensor([0.3], device=DEV) if with_noise else None
+    fused = kern.fir_bias_act(x, (t, t), (pad[0], pad[1], pad[0], pad[1]), bias, noise.reshape(-1) if with_noise else None, nw, 0.2, 1.3)
+    assert fused is not None
+    y = kern.upfirdn2d(x, kernel, 1, 1, 1, 1, pad[0], pad[1], pad[0], pad[1], taps=(t, t))
+    ref = kern.bias_act(y, bias, None, 3, 0, 0.2, 1.3, noise=noise.reshape(-1) if with_noise else None, noise_weight=nw)
+    assert rel_err(fused, ref) < 2e-6, rel_err(fused, ref)
+    # autograd Function against the fp64 oracle
+    xr = x.double().cpu().permute(0, 3, 1, 2).requires_grad_()
+    br = bias.double().cpu().requires_grad_()
+    nwr = nw.double().cpu().requires_grad_() if with_noise else None
+    yr = O.upfirdn2d(xr, kernel.double().cpu(), pad=pad)
+    if with_noise:
+        yr = yr + nwr * noise.double().cpu().unsqueeze(1)
+    yr = O.fused_leaky_relu(yr, br, 0.2, 1.3)
+    wgt = torch.randn_like(yr)
+    gref = torch.autograd.grad((yr * wgt).sum(), [xr, br] + ([nwr] if with_noise else []))
+    xg = x.permute(0, 3, 1, 2).requires_grad_()
+    bg = bias.clone().requires_grad_()
+    nwg = nw.clone().requires_grad_() if with_noise else None
+    out = fir_noise_bias_act(xg, FirSpec(kernel, pad, (t, t), 1), noise.unsqueeze(1) if with_noise else None, nwg, bg, 0.2, 1.3)
+    assert rel_err(out, yr) < 2e-6
+    got = torch.autograd.grad((out * wgt.float().to(DEV)).sum(), [xg, bg] + ([nwg] if with_noise else []))
+    for a, b in zip(got, gref):
+        assert rel_err(a, b) < 2e-5, rel_err(a, b)

@@ -85,3 +85,88 @@ def test_dp_gradient_exchange_gloo(tmp_path):
     assert torch.allclose(r0["b.w"], r0["ref.b.w"], atol=1e-12)
     assert torch.allclose(r0["a.w.grad"], r1["a.w.grad"], atol=1e-14)
     assert torch.allclose(r0["a.w.grad"], r0["ref.a.w"], atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the training driver over two ranks: gradients packed into the flat bucket, all-reduced, and read by MultiTensorAdam
+# straight from the bucket with the 1/world factor folded in (optimizer.exchange_and_step)
+def _tiny_trainer(seed):
+    import swapping_autoencoder_pytorch_b200 as S
+    from swapping_autoencoder_pytorch_b200 import backend, default_options
+    from tests.cpu_emulation import EmulatedKernels
+    from oracle.fixtures import TINY
+    backend.set_kernels(EmulatedKernels())
+    torch.set_default_dtype(torch.float64)
+    opt = default_options(**dict(TINY, R1_once_every=1))
+    torch.manual_seed(seed)
+    model = S.create_model(opt)
+    return opt, model, S.create_optimizer(opt, model)
+
+
+def _driver_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.fixtures import rnd
+    opt, model, trainer = _tiny_trainer(100 + rank)          # different init per rank: rank 0's is broadcast
+    assert trainer.world == 2 and model.defer_to_optimizer
+    full = rnd(900, 4, 3, 64, 64).clamp(-1, 1)
+    x = model.shard(full)
+    torch.manual_seed(7)                                      # same crop / noise draws on both ranks and in the replay below
+    trainer.train_one_step({"real_A": x}, 0)                  # D + R1
+    trainer.train_one_step({"real_A": x}, 0)                  # G
+    sd = {k: v.clone() for k, v in model.singlegpu_model.state_dict().items()}
+    torch.save(sd, os.path.join(out, "driver_r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_training_driver_two_ranks_matches_manual_gradient_average(tmp_path):
+    world = 2
+    mp.spawn(_driver_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "driver_r0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "driver_r1.pt"))
+    for k in r0:
+        assert torch.equal(r0[k], r1[k]), "ranks diverged on %s" % k
+    # single-process replay: per-shard gradients averaged by hand, stock torch.optim.Adam
+    from oracle.fixtures import rnd
+    prev = torch.get_default_dtype()
+    try:
+        opt, model, trainer = _tiny_trainer(100)             # rank 0's initialisation
+        inner = model.singlegpu_model
+        full = rnd(900, 4, 3, 64, 64).clamp(-1, 1)
+        shards = [full[:2], full[2:]]
+        c = opt.R1_once_every / (1 + opt.R1_once_every)
+        adam_d = torch.optim.Adam(trainer.Dparams, lr=opt.lr * c, betas=(opt.beta1 ** c, opt.beta2 ** c))
+        adam_g = torch.optim.Adam(trainer.Gparams, lr=opt.lr, betas=(opt.beta1, opt.beta2))
+
+        def averaged_step(params, frozen, adam, loss_fn, rng_states):
+            trainer.set_requires_grad(frozen, False)
+            trainer.set_requires_grad(params, True)
+            grads, states_after = None, []
+            for shard, state in zip(shards, rng_states):
+                torch.set_rng_state(state)
+                adam.zero_grad()
+                loss_fn(shard).backward()
+                states_after.append(torch.get_rng_state())
+                g = [None if p.grad is None else p.grad.clone() for p in params]
+                grads = g if grads is None else [a if b is None else a + b for a, b in zip(grads, g)]
+            for p, g in zip(params, grads):
+                p.grad = None if g is None else g / len(shards)
+            adam.step()
+            return states_after
+
+        torch.manual_seed(7)
+        s0 = [torch.get_rng_state()] * 2
+        s1 = averaged_step(trainer.Dparams, trainer.Gparams, adam_d,
+                           lambda x: sum(v.mean() for v in inner(x, command="compute_discriminator_losses")[0].values()), s0)
+        s2 = averaged_step(trainer.Dparams, trainer.Gparams, adam_d,
+                           lambda x: sum(v.mean() for v in inner(x, command="compute_R1_loss").values()) * opt.R1_once_every, s1)
+        averaged_step(trainer.Gparams, trainer.Dparams, adam_g,
+                      lambda x: sum(v.mean() for v in inner(x, None, None, command="compute_generator_losses")[0].values()), s2)
+        ref = inner.state_dict()
+        worst = max(float((r0[k].double() - ref[k].double()).abs().max()) for k in ref if ref[k].dtype.is_floating_point)
+        assert worst < 1e-9, worst
+    finally:
+        torch.set_default_dtype(prev)
+        from swapping_autoencoder_pytorch_b200 import backend
+        backend.set_kernels(None)
