@@ -295,7 +295,7 @@ def run_ours(args, rank, world, local):
     # each half-step runs as a CUDA graph replay (graphs.py) unless SAE_CUDA_GRAPHS=0
     use_graphs = os.environ.get("SAE_CUDA_GRAPHS", "1") != "0"
     opt = S.default_options(num_gpus=1, batch_size=PER_GPU_BATCH * world, crop_size=RES, cuda_graphs=use_graphs,
-                            batch_discriminator_passes=os.environ.get("SAE_BATCH_D", "0") == "1")
+                            batch_discriminator_passes=os.environ.get("SAE_BATCH_D", "1") == "1")
     torch.manual_seed(0)
     model = S.create_model(opt)
     trainer = S.create_optimizer(opt, model)
@@ -377,14 +377,21 @@ def run_ours(args, rank, world, local):
                   "value": args.steps * 32 / (sdev["ms"] * 1e-3), "ms_per_step": sdev["ms"] / args.steps,
                   "e2e_value": args.steps * 32 / (se2e["ms"] * 1e-3), "r1_evaluations": sdev["r1"], "unit": "images/s"}
 
-    if trainer.graphs is not None:
-        trainer.graphs.enabled = False            # the per-launch instrumentation pass needs eager launches ...
-        for _ in range(2):                        # ... and a warm caching allocator under them
-            trainer.train_one_step({"real_A": resident}, 0)
-        torch.cuda.synchronize(device)
-    trainer.train_mode_counter = 0
-    trainer.discriminator_iter_counter = 0
-    roof, mem, per_shape = kernel_rooflines(trainer, resident, device)
+    # the per-launch instrumentation pass needs eager launches.  It runs on the stream the half-steps were warmed up and
+    # captured on: autograd binds a parameter's gradient-accumulation node to the stream it was created on, and running
+    # the eager pass elsewhere would make every backward hop streams (torch warns about exactly that)
+    side = trainer.graphs.stream if (trainer.graphs is not None and trainer.graphs.stream is not None) else torch.cuda.current_stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        if trainer.graphs is not None:
+            trainer.graphs.enabled = False
+            for _ in range(2):                    # a warm caching allocator under the eager launches
+                trainer.train_one_step({"real_A": resident}, 0)
+            torch.cuda.synchronize(device)
+        trainer.train_mode_counter = 0
+        trainer.discriminator_iter_counter = 0
+        roof, mem, per_shape = kernel_rooflines(trainer, resident, device)
+    torch.cuda.current_stream().wait_stream(side)
     graph_state = "off"
     if trainer.graphs is not None:
         g = trainer.graphs
@@ -431,6 +438,8 @@ def run_ours(args, rank, world, local):
                     "note": "algorithmic bytes (each operand read once, each result written once) / CUDA-event time, "
                             "eager instrumented D + G half-step"}
 
+    if trainer.graphs is not None:
+        trainer.graphs.release()          # no captured kernels (possibly NCCL ones) outlive the measurements
     if rank != 0:
         return
     # bounded CPU sample (one D + one G half-step on 2 images, plus BASELINE configs[0]); N = 1 only
@@ -521,7 +530,10 @@ def main():
     try:
         run_ours(args, rank, world, local)
     finally:
+        import gc
         import torch.distributed as dist
+        gc.collect()
+        torch.cuda.synchronize()
         if dist.is_initialized():
             dist.destroy_process_group()
 

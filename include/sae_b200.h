@@ -239,6 +239,30 @@ int sae_bucket_unpack(float* const* ptrs, const int64_t* offsets, const int64_t*
                       const float* bucket, int64_t total, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Style-modulated convolution WITHOUT a modulated copy of the activation.
+ * Reference ModulatedConv2d.forward (stylegan2_layers.py:266-325) scales the input by the style ("input * style", :284) and
+ * runs a grouped convolution over `batch` copies of the filter (:286, :321); a first B200 design scaled the input in a
+ * separate pass.  Here the style goes into the FILTER the tensor-core kernel reads: image n is convolved with
+ *   Wn[k,r,s,c] = W[k,r,s,c] * s[n,c]           (sae_filter_modulate: [N,K,R,S,C] and, for the data gradient, [N,C,R,S,K])
+ * selected per pixel tile inside the implicit-GEMM kernel (sae_conv2d_fprop_per_sample / sae_conv2d_dgrad_per_sample; same
+ * epilogue as sae_conv2d_fprop).  The weight gradient takes x UNSCALED and drains its accumulators once per image:
+ *   dW[k,r,s,c] += s[n,c] * Gn[k,r,s,c],   ds[n,c] += sum_{k,r,s} W[k,r,s,c] * Gn[k,r,s,c],   Gn = sum_pixels dy (x) x
+ * (sae_conv2d_wgrad_modulated; dw and ds zero-initialised by the caller).  Pays when N * |W| << |x| (the 128- and 256-channel
+ * 3x3 layers at 256^2 / 128^2).  sae_conv2d_query_modulated: 1 when all three kernels take the geometry (stride 1, map a
+ * multiple of 16 x 8 tiles with an even tile count per image, Q % 32 == 0, channels % 32 == 0), 0 otherwise — the caller
+ * then scales the input (sae_modulate).
+ * ------------------------------------------------------------------------------------------ */
+int sae_filter_modulate(const float* w_krsc, const float* s, float* out_nkrsc, float* out_ncrsk, int n, int k, int c, int r,
+                        int s_, int round_tf32, void* stream);
+int sae_conv2d_query_modulated(const sae_conv_geom* g);
+int sae_conv2d_fprop_per_sample(const float* x, const float* w_nkrsc, float* y, const sae_conv_geom* g,
+                                const sae_conv_epilogue* epi, void* stream);
+int sae_conv2d_dgrad_per_sample(const float* dy, const float* w_ncrsk, float* dx, const sae_conv_geom* g,
+                                const sae_conv_epilogue* epi, void* stream);
+int sae_conv2d_wgrad_modulated(const float* dy, const float* x, const float* s, const float* w_krsc, float* dw, float* ds,
+                               const sae_conv_geom* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-tensor Adam.  Replaces the two torch.optim.Adam instances of
  * optimizers/swapping_autoencoder_optimizer.py:34-42 with one launch per parameter group.
  * torch.optim.Adam semantics (amsgrad off, no weight decay):  for every tensor t with g_ptrs[t] != NULL

@@ -376,6 +376,53 @@ class CudaKernels:
                                             self.conv_impl if impl is None else impl, _stream()), "sae_conv2d_wgrad")
         return dw
 
+    # ------------------------------------------------ style-modulated conv, per-sample filters
+    def conv_modulated_ok(self, g):
+        """True when the per-sample-filter kernels (fprop, dgrad, modulated wgrad) all take this geometry"""
+        return bool(self.lib.sae_conv2d_query_modulated(ctypes.byref(g)))
+
+    def filter_modulate(self, w_krsc, s, want_krsc=True, want_crsk=False):
+        """prepared filter [K,R,S,C] x per-sample scale [N,C] -> ([N,K,R,S,C] or None, [N,C,R,S,K] or None)"""
+        _need_cuda(w_krsc, s)
+        k, r, s_, c = w_krsc.shape
+        n = s.shape[0]
+        a = torch.empty((n, k, r, s_, c), device=s.device, dtype=s.dtype) if want_krsc else None
+        b = torch.empty((n, c, r, s_, k), device=s.device, dtype=s.dtype) if want_crsk else None
+        with torch.cuda.device(s.device):
+            check(self.lib.sae_filter_modulate(_ptr(w_krsc), _ptr(s), _ptr(a), _ptr(b), n, k, c, r, s_, int(self.round_tf32),
+                                               _stream()), "sae_filter_modulate")
+        return a, b
+
+    def conv_fprop_per_sample(self, x, w_nkrsc, g, **epi):
+        """x [N,H,W,C], per-sample filters [N,K,R,S,C] -> y [N,P,Q,K]"""
+        _need_cuda(x, w_nkrsc)
+        y = torch.empty((g.N, g.P, g.Q, g.K), device=x.device, dtype=x.dtype)
+        e = self._epi(**epi)
+        with torch.cuda.device(x.device):
+            check(self.lib.sae_conv2d_fprop_per_sample(_ptr(x), _ptr(w_nkrsc), _ptr(y), ctypes.byref(g), ctypes.byref(e), _stream()),
+                  "sae_conv2d_fprop_per_sample")
+        return y
+
+    def conv_dgrad_per_sample(self, dy, w_ncrsk, g, **epi):
+        """dy [N,P,Q,K], per-sample transposed filters [N,C,R,S,K] -> dx [N,H,W,C]"""
+        _need_cuda(dy, w_ncrsk)
+        dx = torch.empty((g.N, g.H, g.W, g.C), device=dy.device, dtype=dy.dtype)
+        e = self._epi(**epi)
+        with torch.cuda.device(dy.device):
+            check(self.lib.sae_conv2d_dgrad_per_sample(_ptr(dy), _ptr(w_ncrsk), _ptr(dx), ctypes.byref(g), ctypes.byref(e), _stream()),
+                  "sae_conv2d_dgrad_per_sample")
+        return dx
+
+    def conv_wgrad_modulated(self, dy, x, s, w_krsc, g):
+        """dy [N,P,Q,K], UNSCALED x [N,H,W,C], s [N,C], forward filter [K,R,S,C] -> (dw [K,R,S,C], ds [N,C])"""
+        _need_cuda(dy, x, s, w_krsc)
+        dw = torch.zeros((g.K, g.R, g.S, g.C), device=dy.device, dtype=dy.dtype)
+        ds = torch.zeros((g.N, g.C), device=dy.device, dtype=dy.dtype)
+        with torch.cuda.device(dy.device):
+            check(self.lib.sae_conv2d_wgrad_modulated(_ptr(dy), _ptr(x), _ptr(s), _ptr(w_krsc), _ptr(dw), _ptr(ds), ctypes.byref(g),
+                                                      _stream()), "sae_conv2d_wgrad_modulated")
+        return dw, ds
+
     def conv_impl_for(self, g, direction):
         return int(self.lib.sae_conv2d_query_impl(ctypes.byref(g), direction))
 

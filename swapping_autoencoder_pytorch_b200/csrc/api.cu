@@ -95,3 +95,39 @@ extern "C" int sae_conv2d_wgrad(const float* dy, const float* x, float* dw, cons
     if (impl != 1 && tc_ok) return tc_wgrad(dy, x, dw, g, st);
     return conv_wgrad_generic(dy, x, dw, g, st);
 }
+
+// ---- style-modulated convolution with per-sample filters (no modulated copy of the activation) --------------------------
+extern "C" int sae_conv2d_query_modulated(const sae_conv_geom* g) {
+    if (validate_geom(g, "query_modulated") != SAE_OK) return 0;
+    return (tc_available() && tc_per_sample_eligible(g, 0) && tc_per_sample_eligible(g, 1) && tc_wgrad_modulated_eligible(g)) ? 1 : 0;
+}
+
+extern "C" int sae_conv2d_fprop_per_sample(const float* x, const float* w_nkrsc, float* y, const sae_conv_geom* g,
+                                           const sae_conv_epilogue* epi, void* stream) {
+    int rc = validate_geom(g, "conv2d_fprop_per_sample");
+    if (rc) return rc;
+    if (g->N == 0) return SAE_OK;
+    if (!x || !w_nkrsc || !y) return fail(SAE_E_INVALID, "conv2d_fprop_per_sample: null pointer");
+    if (!tc_available()) return fail(SAE_E_UNSUPPORTED, "conv2d_fprop_per_sample: needs the tcgen05 path");
+    return tc_conv_per_sample(x, w_nkrsc, y, g, 0, make_epi(epi), (cudaStream_t)stream);
+}
+
+extern "C" int sae_conv2d_dgrad_per_sample(const float* dy, const float* w_ncrsk, float* dx, const sae_conv_geom* g,
+                                           const sae_conv_epilogue* epi, void* stream) {
+    int rc = validate_geom(g, "conv2d_dgrad_per_sample");
+    if (rc) return rc;
+    if (g->N == 0) return SAE_OK;
+    if (!dy || !w_ncrsk || !dx) return fail(SAE_E_INVALID, "conv2d_dgrad_per_sample: null pointer");
+    if (!tc_available()) return fail(SAE_E_UNSUPPORTED, "conv2d_dgrad_per_sample: needs the tcgen05 path");
+    return tc_conv_per_sample(dy, w_ncrsk, dx, g, 1, make_epi(epi), (cudaStream_t)stream);
+}
+
+extern "C" int sae_conv2d_wgrad_modulated(const float* dy, const float* x, const float* s, const float* w_krsc, float* dw, float* ds,
+                                          const sae_conv_geom* g, void* stream) {
+    int rc = validate_geom(g, "conv2d_wgrad_modulated");
+    if (rc) return rc;
+    if (g->N == 0) return SAE_OK;
+    if (!dy || !x || !s || !w_krsc || !dw || !ds) return fail(SAE_E_INVALID, "conv2d_wgrad_modulated: null pointer");
+    if (!tc_available()) return fail(SAE_E_UNSUPPORTED, "conv2d_wgrad_modulated: needs the tcgen05 path");
+    return tc_wgrad_modulated(dy, x, s, w_krsc, dw, ds, g, (cudaStream_t)stream);
+}

@@ -71,8 +71,49 @@ struct TcParams {
     // shared-window kernel only: one (wh x ww)-pixel input window per channel block serves every tap
     int ww, wh, oy_min, ox_min;
     unsigned short arow[TC_MAX_TAPS];   // first window row of tap t: (oy_t - oy_min) * ww + (ox_t - ox_min)
+    int w_nstride;                      // shared-window kernel: filter rows between consecutive images (0 = one filter for the
+                                        // batch; Ncol = per-sample filters [N, Ncol, Ktot], the style-modulated convolution)
     EpiParams epi;
 };
+
+// ------------------------------------------------------------------------------------------------ epilogue pieces shared by all kernels
+// One 32-column chunk of one accumulator row (= one output pixel): bias / NoiseInjection / leaky-ReLU / gain / residual merge /
+// TF32 rounding on the 32 values a thread read from TMEM, then the 128-byte row into the chunk's staging tile
+// ([128 rows][128 bytes], 16-byte pieces XOR-swizzled by (row & 7): the layout the SWIZZLE_128B output tensor map reads).
+__device__ __forceinline__ void tc_epilogue_math(float (&v)[32], const EpiParams& e, int colb, int64_t pixel, int ncol, bool valid, float nz) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float t = v[j];
+        if (e.bias) t += __ldg(e.bias + colb + j);
+        t += nz;
+        if (e.act == 3) t = t > 0.f ? t : t * e.alpha;
+        t *= e.gain;
+        v[j] = t;
+    }
+    if (e.residual && valid) {
+        const float4* r4 = reinterpret_cast<const float4*>(e.residual + pixel * ncol + colb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 r = __ldg(r4 + j);
+            v[4 * j + 0] = (v[4 * j + 0] + r.x) * e.res_scale;
+            v[4 * j + 1] = (v[4 * j + 1] + r.y) * e.res_scale;
+            v[4 * j + 2] = (v[4 * j + 2] + r.z) * e.res_scale;
+            v[4 * j + 3] = (v[4 * j + 3] + r.w) * e.res_scale;
+        }
+    }
+    if (e.round_tf32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+    }
+}
+
+__device__ __forceinline__ void tc_stage_row(uint8_t* stg_row, int row, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(stg_row + ((j ^ (row & 7)) << 4)) = o;
+    }
+}
 
 template <int BLOCK_N>
 constexpr int tc_stages() { return BLOCK_N >= 128 ? 3 : 4; }   // <= 96 KB of ring per CTA: two CTAs co-reside on an SM,
@@ -189,37 +230,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
             const int colb = col0 + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j];
-                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                t += nz;
-                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                t *= p.epi.gain;
-                v[j] = t;
-            }
-            if (p.epi.residual && valid) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 r = __ldg(r4 + j);
-                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                }
-            }
-            if (p.epi.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-            }
+            tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
             // staging tile for this 32-column chunk: [128 rows][128 bytes], 16-byte chunks XOR-swizzled by (row & 7)
             uint8_t* stg = smem_gen + (size_t)ch * TC_A_BYTES + (size_t)row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-            }
+            tc_stage_row(stg, row, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && lane == 0) {
@@ -237,608 +251,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     }
 }
 
-// ------------------------------------------------------------------------------------------------ CTA-pair kernel
-// Same algorithm with tcgen05 cta_group::2: two CTAs of a cluster (two consecutive pixel tiles, same output-channel
-// block) act as one 256-row MMA.  Each CTA loads its own A tile and HALF of the B (filter) tile; the pair's leader
-// issues M = 256 instructions that read A and B from both CTAs' shared memory, so per CTA the L2->SM traffic per MAC
-// halves on the filter side:  (16 KB A + BLOCK_N/2 * 128 B) per 128 x BLOCK_N x 32 MACs.  With BLOCK_N = 256 that is
-// 64 B/clk/SM at full tensor rate (the 1-CTA 128x128 tile needs 128 B/clk/SM and is L2-feed bound at ~45 %).
-template <int BLOCK_N>
-constexpr int tc2_stages() { return 3; }      // <= 96 KB per CTA: two pair-CTAs co-reside per SM (2 x 256 TMEM columns),
-                                              // one drains its accumulators while the other feeds the tensor core
-
-template <int BLOCK_N>
-constexpr size_t tc2_smem_bytes() {
-    // the epilogue staging cycles through the ring's 16 KB slots (see NBUF below), so the ring size is all that counts
-    return (size_t)tc2_stages<BLOCK_N>() * (TC_A_BYTES + (BLOCK_N / 2) * 128) + 1024 + 256;
-}
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks) {
-    constexpr int STAGES = tc2_stages<BLOCK_N>();
-    constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
-    constexpr int STAGE_BYTES = TC_A_BYTES + B_HALF_BYTES;                 // per CTA
-    constexpr uint32_t TMEM_COLS = BLOCK_N;
-    // D fp32, A/B tf32 K-major, N = BLOCK_N, M = 256 (128 rows from each CTA)
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    constexpr uint32_t RING = (uint32_t)STAGES * STAGE_BYTES;
-    constexpr uint32_t BAR_OFF = RING;
-    constexpr int NCHUNK = BLOCK_N / 32;
-    constexpr int NBUF = (int)(RING / TC_A_BYTES) < NCHUNK ? (int)(RING / TC_A_BYTES) : NCHUNK;   // 16 KB staging slots
-    const uint32_t bar_full = base + BAR_OFF;
-    const uint32_t bar_empty = bar_full + 8 * STAGES;
-    const uint32_t bar_acc = bar_empty + 8 * STAGES;
-    const uint32_t tmem_slot = bar_acc + 8;
-    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-
-    // linear CTA id -> (pair of consecutive pixel tiles, output-channel block); the channel block is the fast index so
-    // the CTAs that re-read one activation tile run at the same time and hit it in L2
-    const int pair_id = blockIdx.x >> 1;
-    const int nblk = pair_id % n_blocks;
-    int tile = (pair_id / n_blocks) * 2 + (int)rank;
-    const int tq = tile % p.tiles_w; tile /= p.tiles_w;
-    const int tp = tile % p.tiles_h; tile /= p.tiles_h;
-    const int q0 = tq * p.tw, p0 = tp * p.th, n0 = tile * p.tn;          // beyond the batch for the padding tile: all OOB
-    const int col0 = nblk * BLOCK_N;
-    const int KB = p.ntaps * p.num_cblk;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
-        }
-        mbar_init(bar_acc, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();                      // both CTAs' barriers exist before any remote complete_tx / commit arrives
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
-
-    if (warp == 0) {
-        // ===================================================== TMA producer (both CTAs)
-        if (elect_one()) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                const int t = kb / p.num_cblk, cb = kb - t * p.num_cblk;
-                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
-                if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
-                tma2_load_4d(sa, &map_src, bar_full + 8 * s, cb * TC_BK, q0 * p.stride + p.ox[t], p0 * p.stride + p.oy[t], n0);
-                tma2_load_2d(sb, &map_w, bar_full + 8 * s, p.wk[t] + cb * TC_BK, col0 + (int)rank * (BLOCK_N / 2));
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer (leader CTA only)
-        if (leader && elect_one()) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(bar_full + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES, sb = sa + TC_A_BYTES;
-                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k)
-                    umma2_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-                umma2_commit(bar_empty + 8 * s);          // frees stage s in both CTAs
-            }
-            umma2_commit(bar_acc);                        // accumulators complete in both CTAs
-        }
-    } else {
-        // ===================================================== epilogue: identical to the 1-CTA kernel (own 128 rows)
-        const int lg = warp & 3;
-        const int row = lg * 32 + lane;
-        const int iw = row % p.tw, ih = (row / p.tw) % p.th, in_ = row / (p.tw * p.th);
-        const int n = n0 + in_, pp = p0 + ih, qq = q0 + iw;
-        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
-        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
-        mbar_wait(bar_acc, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float nz = 0.f;
-        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
-#pragma unroll 1
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-            if (NBUF < NCHUNK && ch >= NBUF) {
-                // staging slot (ch % NBUF) is still being read by the TMA store of chunk ch - NBUF: wait for it
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
-            const int colb = col0 + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j];
-                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                t += nz;
-                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                t *= p.epi.gain;
-                v[j] = t;
-            }
-            if (p.epi.residual && valid) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 r = __ldg(r4 + j);
-                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                }
-            }
-            if (p.epi.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-            }
-            uint8_t* stg = smem_gen + (size_t)(ch % NBUF) * TC_A_BYTES + (size_t)row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2 && lane == 0) {
-                tma_store_4d(&map_out, base + (uint32_t)(ch % NBUF) * TC_A_BYTES, colb, q0, p0, n0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        }
-        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();                      // nobody leaves (or frees TMEM) while the peer may still touch this CTA
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ shared-window pair kernel
-// The 1-CTA and pair kernels above fetch one 128-pixel A tile PER TAP: a 3x3 convolution reads every input pixel nine
-// times from L2, and at ~57 B/clk/SM of L2->SM bandwidth that — not the tensor core — bounds them (ncu: tensor pipe
-// 40-75 % busy, lts ~55 %).  Here the pixel tile is 16 rows x 8 columns of one image, and ONE TMA box of
-// (16 + oy_range) x (8 + ox_range) pixels (18 x 10 for a 3x3 filter, 22.5 KB per 32-channel block) serves ALL taps:
-// tap (r, s) is the same shared-memory window read through a UMMA descriptor whose start address is shifted by
-// (r * ww + s) 128-byte pixel rows and whose 8-row atoms are `ww` rows apart (SBO = ww * 128 B).  The 128-byte
-// swizzle is a function of the absolute shared-memory address, so a row-shifted start needs no re-layout.
-// L2->SM traffic per channel block drops from 9 x 16 KB (A) + 9 x B to 22.5 KB + 9 x B: with BLOCK_N = 256 in a CTA
-// pair that is ~36 B/clk/SM at full tensor rate — the kernel becomes tensor-bound.
+// ------------------------------------------------------------------------------------------------ shared-window persistent pair kernel
+// CTA pairs (tcgen05 cta_group::2, cluster 2 x 1): two consecutive pixel tiles of the same output-channel block act as one
+// 256-row MMA; each CTA loads its own A tile and HALF of the B (filter) tile, the leader issues M = 256 instructions that read
+// both CTAs' shared memory, accumulators live in the TMEM of both SMs.
+// Shared window: the pixel tile is 16 rows x 8 columns of one image, and ONE TMA box of (16 + oy_range) x (8 + ox_range)
+// pixels (18 x 10 for a 3x3 filter, 22.5 KB per 32-channel block) serves ALL taps: tap (r, s) is the same shared-memory
+// window read through a UMMA descriptor whose start address is shifted by (r * ww + s) 128-byte pixel rows and whose 8-row
+// atoms are `ww` rows apart (SBO = ww * 128 B).  The 128-byte swizzle is a function of the absolute shared-memory address, so
+// a row-shifted start needs no re-layout.  L2 -> SM traffic per channel block drops from 9 x 16 KB (A) to 22.5 KB.
+// Persistent: one wave of CTA pairs loops over (pixel-tile pair, channel block) work items; TMEM, barriers and tensor-map
+// prefetches are set up once and the mbarrier rings keep running across tiles.
 constexpr int TC3_NA = 2;                           // A-window ring slots
-template <int BLOCK_N> constexpr int tc3_nb() { return BLOCK_N >= 256 ? 4 : 8; }   // B ring slots: 64 KB either way — deep
-                                                                                   // enough to cover L2 latency per tap
 constexpr int TC3_ASLOT = 23 * 1024;                // >= 18 * 10 * 128 B, multiple of 1024
 
-template <int BLOCK_N>
-constexpr size_t tc3_smem_bytes() { return (size_t)tc3_nb<BLOCK_N>() * (BLOCK_N / 2) * 128 + (size_t)TC3_NA * TC3_ASLOT + 1024 + 256; }
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-conv_tc3_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks) {
-    constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
-    constexpr int TC3_NB = tc3_nb<BLOCK_N>();
-    constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
-    constexpr uint32_t RING = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
-    constexpr uint32_t TMEM_COLS = BLOCK_N;
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
-    constexpr int NCHUNK = BLOCK_N / 32;
-    constexpr int NBUF = (int)(RING / TC_A_BYTES) < NCHUNK ? (int)(RING / TC_A_BYTES) : NCHUNK;
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_ring = base + B_RING;
-    const uint32_t bar_fullA = base + RING;
-    const uint32_t bar_emptyA = bar_fullA + 8 * TC3_NA;
-    const uint32_t bar_fullB = bar_emptyA + 8 * TC3_NA;
-    const uint32_t bar_emptyB = bar_fullB + 8 * TC3_NB;
-    const uint32_t bar_acc = bar_emptyB + 8 * TC3_NB;
-    const uint32_t tmem_slot = bar_acc + 8;
-    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-
-    const int pair_id = blockIdx.x >> 1;
-    const int nblk = pair_id % n_blocks;
-    int tile = (pair_id / n_blocks) * 2 + (int)rank;
-    const int tq = tile % p.tiles_w; tile /= p.tiles_w;
-    const int tp = tile % p.tiles_h; tile /= p.tiles_h;
-    const int q0 = tq * p.tw, p0 = tp * p.th, n0 = tile;                 // tn == 1
-    const int col0 = nblk * BLOCK_N;
-    const uint32_t a_bytes = (uint32_t)(p.ww * p.wh) * 128u;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
-        for (int s = 0; s < TC3_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
-        for (int s = 0; s < TC3_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
-        mbar_init(bar_acc, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
-
-    if (warp == 0) {
-        // ===================================================== TMA producer (both CTAs)
-        if (elect_one()) {
-            int ib = 0;
-            for (int cb = 0; cb < p.num_cblk; ++cb) {
-                const int sa = cb % TC3_NA;
-                mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(cb / TC3_NA)) & 1u) ^ 1u);
-                if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
-                tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
-                for (int t = 0; t < p.ntaps; ++t, ++ib) {
-                    const int sb = ib % TC3_NB;
-                    mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
-                    if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
-                    tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, p.wk[t] + cb * TC_BK,
-                                 col0 + (int)rank * (BLOCK_N / 2));
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer (leader CTA only)
-        if (leader && elect_one()) {
-            const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;        // 8-row atoms are one window row apart
-            int ib = 0;
-            for (int cb = 0; cb < p.num_cblk; ++cb) {
-                const int sa = cb % TC3_NA;
-                mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(cb / TC3_NA)) & 1u);
-                const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
-                for (int t = 0; t < p.ntaps; ++t, ++ib) {
-                    const int sb = ib % TC3_NB;
-                    mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // A descriptor: start = window row arow[t]; same 128B-swizzle K-major layout, SBO = ww * 128 B
-                    const uint32_t aaddr = a0 + (uint32_t)p.arow[t] * 128u;
-                    uint64_t da = (uint64_t)((aaddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | sbo | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-                    const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)
-                        umma2_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (ib > 0 || k > 0) ? 1u : 0u);
-                    umma2_commit(bar_emptyB + 8 * sb);
-                }
-                umma2_commit(bar_emptyA + 8 * sa);
-            }
-            umma2_commit(bar_acc);
-        }
-    } else {
-        // ===================================================== epilogue (identical to the pair kernel)
-        const int lg = warp & 3;
-        const int row = lg * 32 + lane;
-        const int iw = row % p.tw, ih = row / p.tw;
-        const int n = n0, pp = p0 + ih, qq = q0 + iw;
-        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
-        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
-        mbar_wait(bar_acc, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float nz = 0.f;
-        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
-#pragma unroll 1
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-            if (NBUF < NCHUNK && ch >= NBUF) {
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
-            const int colb = col0 + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j];
-                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                t += nz;
-                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                t *= p.epi.gain;
-                v[j] = t;
-            }
-            if (p.epi.residual && valid) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 r = __ldg(r4 + j);
-                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                }
-            }
-            if (p.epi.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-            }
-            uint8_t* stg = smem_gen + (size_t)(ch % NBUF) * TC_A_BYTES + (size_t)row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2 && lane == 0) {
-                tma_store_4d(&map_out, base + (uint32_t)(ch % NBUF) * TC_A_BYTES, colb, q0, p0, n0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        }
-        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ persistent shared-window pair kernel
-// Same data path as conv_tc3_kernel, but the grid is one wave of CTA pairs (two per SM pair-slot) that LOOP over
-// (pixel-tile pair, channel block) work items: TMEM, barriers and tensor-map prefetches are set up once, the mbarrier
-// rings keep running across tiles, and the only per-tile synchronisation is (i) epilogue -> MMA "accumulators drained"
-// (both CTAs arrive on the leader's barrier) and (ii) epilogue -> producer "staging shared memory free".  That removes
-// the per-tile launch / TMEM-allocation / cluster-barrier cost, which dominates the narrow (32-64 channel) layers whose
-// per-tile main loop is only ~1-2k cycles, and trims the 128-channel layers.
-template <int BLOCK_N> constexpr int tc4_nb() { return BLOCK_N >= 256 ? 4 : 8; }
-template <int BLOCK_N>
-constexpr size_t tc4_smem_bytes() {
-    size_t ring = (size_t)tc4_nb<BLOCK_N>() * (BLOCK_N / 2) * 128 + (size_t)TC3_NA * TC3_ASLOT;
-    size_t epi = (size_t)(BLOCK_N / 32 < 1 ? 1 : BLOCK_N / 32) * TC_A_BYTES;
-    if (ring < epi) ring = epi;
-    return ring + 1024 + 256;
-}
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-conv_tc4_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks, const int total_work) {
-    constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
-    constexpr int TC3_NB = tc4_nb<BLOCK_N>();
-    constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
-    constexpr uint32_t RING0 = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
-    constexpr uint32_t RING = RING0 < (uint32_t)TC_A_BYTES ? (uint32_t)TC_A_BYTES : RING0;
-    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
-    constexpr int NCHUNK = BLOCK_N / 32;
-    constexpr int NBUF = (int)(RING / TC_A_BYTES) < NCHUNK ? (int)(RING / TC_A_BYTES) : NCHUNK;
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_ring = base + B_RING;
-    const uint32_t bar_fullA = base + RING;
-    const uint32_t bar_emptyA = bar_fullA + 8 * TC3_NA;
-    const uint32_t bar_fullB = bar_emptyA + 8 * TC3_NA;
-    const uint32_t bar_emptyB = bar_fullB + 8 * TC3_NB;
-    const uint32_t bar_acc = bar_emptyB + 8 * TC3_NB;
-    const uint32_t bar_tmem_empty = bar_acc + 8;      // leader's copy is the one in use: both CTAs' epilogues arrive on it
-    const uint32_t bar_stage_free = bar_tmem_empty + 8;
-    const uint32_t tmem_slot = bar_stage_free + 8;
-    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const uint32_t a_bytes = (uint32_t)(p.ww * p.wh) * 128u;
-    // work item -> (pixel tile of this CTA, channel block); the channel block is the fast index
-    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0) {
-        const int nblk = work % n_blocks;
-        int tile = (work / n_blocks) * 2 + (int)rank;
-        const int tq = tile % p.tiles_w; tile /= p.tiles_w;
-        const int tp = tile % p.tiles_h; tile /= p.tiles_h;
-        q0 = tq * p.tw; p0 = tp * p.th; n0 = tile; col0 = nblk * BLOCK_N;
-    };
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
-        for (int s = 0; s < TC3_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
-        for (int s = 0; s < TC3_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_tmem_empty, 2);
-        mbar_init(bar_stage_free, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
-
-    if (warp == 0) {
-        // ===================================================== TMA producer (both CTAs)
-        if (elect_one()) {
-            int ia = 0, ib = 0, it = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-                int q0, p0, n0, col0;
-                decode(work, q0, p0, n0, col0);
-                // the rings double as the previous tile's output staging: wait until its TMA stores have read them
-                if (it > 0) mbar_wait(bar_stage_free, (uint32_t)(it - 1) & 1u);
-                for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
-                    const int sa = ia % TC3_NA;
-                    mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC3_NA)) & 1u) ^ 1u);
-                    if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
-                    tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
-                    for (int t = 0; t < p.ntaps; ++t, ++ib) {
-                        const int sb = ib % TC3_NB;
-                        mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
-                        if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
-                        tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, p.wk[t] + cb * TC_BK,
-                                     col0 + (int)rank * (BLOCK_N / 2));
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer (leader CTA only)
-        if (leader && elect_one()) {
-            const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;        // 8-row atoms are one window row apart
-            int ia = 0, ib = 0, it = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-            // both CTAs' epilogues must have drained the previous tile's accumulators before they are overwritten
-            if (it > 0) { mbar_wait(bar_tmem_empty, (uint32_t)(it - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-            int tstep = 0;
-            for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
-                const int sa = ia % TC3_NA;
-                mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC3_NA)) & 1u);
-                const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
-                for (int t = 0; t < p.ntaps; ++t, ++ib, ++tstep) {
-                    const int sb = ib % TC3_NB;
-                    mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // A descriptor: start = window row arow[t]; same 128B-swizzle K-major layout, SBO = ww * 128 B
-                    const uint32_t aaddr = a0 + (uint32_t)p.arow[t] * 128u;
-                    uint64_t da = (uint64_t)((aaddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | sbo | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-                    const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)
-                        umma2_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (tstep > 0 || k > 0) ? 1u : 0u);
-                    umma2_commit(bar_emptyB + 8 * sb);
-                }
-                umma2_commit(bar_emptyA + 8 * sa);
-            }
-            umma2_commit(bar_acc);
-            }
-        }
-    } else {
-        // ===================================================== epilogue (identical to the pair kernel)
-        const int lg = warp & 3;
-        const int row = lg * 32 + lane;
-        const int iw = row % p.tw, ih = row / p.tw;
-        int it = 0;
-        for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-        int q0, p0, n0, col0;
-        decode(work, q0, p0, n0, col0);
-        const int n = n0, pp = p0 + ih, qq = q0 + iw;
-        const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
-        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
-        mbar_wait(bar_acc, (uint32_t)it & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float nz = 0.f;
-        if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
-#pragma unroll 1
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-            if (NBUF < NCHUNK && ch >= NBUF) {
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
-            const int colb = col0 + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j];
-                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                t += nz;
-                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                t *= p.epi.gain;
-                v[j] = t;
-            }
-            if (p.epi.residual && valid) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 r = __ldg(r4 + j);
-                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                }
-            }
-            if (p.epi.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-            }
-            uint8_t* stg = smem_gen + (size_t)(ch % NBUF) * TC_A_BYTES + (size_t)row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2 && lane == 0) {
-                tma_store_4d(&map_out, base + (uint32_t)(ch % NBUF) * TC_A_BYTES, colb, q0, p0, n0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (ch == NCHUNK - 1) {
-                    // all 128 epilogue threads have finished reading TMEM: tell the leader's MMA warp (remote for rank 1)
-                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_tmem_empty & kPeerBitMask) : "memory");
-                }
-            }
-        }
-        if (warp == 2 && lane == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_stage_free) : "memory");     // staging free again
-        }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ persistent kernel, overlapped epilogue
-// conv_tc4_kernel serialises each CTA's tiles: the producer may not refill the rings while the previous tile's output is
-// staged in them, and the MMA warp waits for the epilogue to drain the single accumulator.  This variant (BLOCK_N <= 128)
-// gives the epilogue its own two 16 KB staging buffers and double-buffers the accumulators in TMEM (2 x BLOCK_N columns,
-// still two CTAs per SM), so a CTA loads and multiplies tile i+1 while tile i streams out — the shape the memory-bound
-// layers need (1x1 convs, 32/64-channel layers, the 1- and 2-tap parity classes of a stride-2 data gradient), where the
-// epilogue's stores ARE the critical path and nothing else may wait for them.
+// Overlapped epilogue: the epilogue owns two 16 KB staging buffers and the accumulators are double-buffered in TMEM
+// (2 x BLOCK_N columns, two CTAs per SM), so a CTA loads and multiplies tile i + 1 while tile i streams out — what the
+// memory-bound layers need (1x1 convs, 32/64-channel layers, the 1- and 2-tap parity classes of a stride-2 data gradient),
+// where the stores ARE the critical path, and what lets the 3x3 layers keep the tensor pipe fed across tile boundaries.
+// Timing experiments on 128 -> 128 at 256^2 x 32 (profiles/r2_tc5_time_split.txt): whole kernel 0.794 ms; without the output
+// stores 0.691; loads + epilogue without any MMA 0.492; the MMAs alone need >= 0.64 ms at the 1.6 GHz the SMs hold under this
+// load — the kernel sits at ~80 % of the tensor-pipe bound, the rest is imperfect overlap of the three engines.
 template <int BLOCK_N> constexpr int tc5_nb() { return BLOCK_N >= 128 ? 4 : 8; }     // B ring: 32 KB at N = 128 / 64, 16 KB at 32
 constexpr int TC5_NSTG = 2;                          // dedicated 16 KB output staging buffers
-template <int BLOCK_N>
+// Template parameters beyond the column-block width: NACC accumulator buffers in TMEM, NA window slots, NB filter-tile slots,
+// CTAS resident CTAs per SM.  Instantiated as <N, 2, 2, tc5_nb<N>(), 2>.  (Measured and dropped, round 2: one CTA per SM
+// pooling the SM's shared memory with 4 accumulators and 4 + 8 slots, <128, 4, 4, 8, 1>: 757 vs 779 TFLOP/s on
+// 128 -> 128 at 256^2; 256-column blocks at one CTA per SM, <256, 2, 4, 5, 1>: +3 % on 256 -> 256 / 512 -> 512, -5 % on the
+// 32^2 maps, no change of the training step.)
+template <int BLOCK_N, int NA, int NB>
 constexpr size_t tc5_smem_bytes() {
-    return (size_t)tc5_nb<BLOCK_N>() * (BLOCK_N / 2) * 128 + (size_t)TC3_NA * TC3_ASLOT + (size_t)TC5_NSTG * TC_A_BYTES + 1024 + 256;
+    return (size_t)NB * (BLOCK_N / 2) * 128 + (size_t)NA * TC3_ASLOT + (size_t)TC5_NSTG * TC_A_BYTES + 1024 /*alignment*/ +
+           8 * (size_t)(2 * NA + 2 * NB + 4 * 2) + 64 /*barriers incl. up to 4 accumulator pairs, TMEM slot*/;
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int BLOCK_N, int NACC, int NA, int NB, int CTAS>
+__global__ void __launch_bounds__(TC_THREADS, CTAS)
 conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks, const int total_work) {
     constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
-    constexpr int TC3_NB = tc5_nb<BLOCK_N>();
+    constexpr int TC3_NB = NB;
+    constexpr int TC3_NA = NA;                                          // (shadows the file-level constant inside this kernel)
     constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
     constexpr uint32_t RING0 = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
     constexpr uint32_t STG_OFF = RING0;                                  // staging follows the rings (1024-byte aligned)
     constexpr uint32_t RING = RING0 + (uint32_t)TC5_NSTG * TC_A_BYTES;
     constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                         // two accumulator buffers
+    constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;                      // NACC accumulator buffers
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
     constexpr int NCHUNK = BLOCK_N / 32;
-    static_assert(BLOCK_N <= 128 && (B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc5: layout");
+    static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && (B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc5: layout");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -847,9 +309,9 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     const uint32_t bar_emptyA = bar_fullA + 8 * TC3_NA;
     const uint32_t bar_fullB = bar_emptyA + 8 * TC3_NA;
     const uint32_t bar_emptyB = bar_fullB + 8 * TC3_NB;
-    const uint32_t bar_acc = bar_emptyB + 8 * TC3_NB;              // [2]: accumulator buffer b is complete
-    const uint32_t bar_tmem_empty = bar_acc + 16;                  // [2]: leader's copy in use, both CTAs' epilogues arrive on it
-    const uint32_t tmem_slot = bar_tmem_empty + 16;
+    const uint32_t bar_acc = bar_emptyB + 8 * TC3_NB;              // [NACC]: accumulator buffer b is complete
+    const uint32_t bar_tmem_empty = bar_acc + 8 * NACC;            // [NACC]: leader's copy in use, both CTAs' epilogues arrive on it
+    const uint32_t tmem_slot = bar_tmem_empty + 8 * NACC;
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -873,8 +335,7 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
         for (int s = 0; s < TC3_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
         for (int s = 0; s < TC3_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
-        mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
-        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
+        for (int s = 0; s < NACC; ++s) { mbar_init(bar_acc + 8 * s, 1); mbar_init(bar_tmem_empty + 8 * s, 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -903,8 +364,10 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
                         const int sb = ib % TC3_NB;
                         mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
                         if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
+                        // (per-sample filters: both tiles of a pair lie in the same image — the launcher checks that the number
+                        // of tiles per image is even — so the two CTAs agree on n0)
                         tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, p.wk[t] + cb * TC_BK,
-                                     col0 + (int)rank * (BLOCK_N / 2));
+                                     col0 + (int)rank * (BLOCK_N / 2) + n0 * p.w_nstride);
                     }
                 }
             }
@@ -915,9 +378,9 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
             const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;        // 8-row atoms are one window row apart
             int ia = 0, ib = 0, it = 0;
             for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-            // accumulator buffer (it & 1): both CTAs' epilogues must have drained its previous tile (it - 2)
-            const uint32_t buf = (uint32_t)it & 1u;
-            if (it > 1) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            // accumulator buffer it % NACC: both CTAs' epilogues must have drained its previous tile (it - NACC)
+            const uint32_t buf = (uint32_t)(it % NACC);
+            if (it >= NACC) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it / NACC) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
             int tstep = 0;
             for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
@@ -951,11 +414,11 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
         int q0, p0, n0, col0;
         decode(work, q0, p0, n0, col0);
-        const uint32_t buf = (uint32_t)it & 1u;
+        const uint32_t buf = (uint32_t)(it % NACC);
         const int n = n0, pp = p0 + ih, qq = q0 + iw;
         const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
         const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + p.o_offy) * p.FW + qq * p.o_mul + p.o_offx;
-        mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        mbar_wait(bar_acc + 8 * buf, (uint32_t)(it / NACC) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float nz = 0.f;
         if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
@@ -969,37 +432,10 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
             float v[32];
             tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
             const int colb = col0 + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j];
-                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                t += nz;
-                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                t *= p.epi.gain;
-                v[j] = t;
-            }
-            if (p.epi.residual && valid) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 r = __ldg(r4 + j);
-                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                }
-            }
-            if (p.epi.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-            }
+            tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
             const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
             uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-            }
+            tc_stage_row(stg, row, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1023,12 +459,13 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     }
 }
 
-// ------------------------------------------------------------------------------------------------ conv_tc5 over several parity classes (experimental)
+// ------------------------------------------------------------------------------------------------ conv_tc5 over the parity classes of a stride-2 data gradient
 // The stride-2 data gradient (and the generator's transposed convolution) is four dense stride-1 problems — the parity classes
 // of the output — over the SAME input.  conv_tc5m_kernel is conv_tc5_kernel whose work items carry a class index: each class
 // has its own tap list, output sub-grid offset and output tensor map; the input window is the union window of all taps.
 // One launch instead of four (plus strips), and the input tile of a pixel block travels from HBM once instead of four times.
-// NOT YET VALIDATED ON HARDWARE (written after round 1's GPU budget was spent): opt-in via SAE_DGRAD_MERGED=1.
+// (A variant keeping all four class accumulators in TMEM per window, 4 x 64 columns at one CTA per SM, was measured in
+// round 2 and dropped: 333 vs 416 TFLOP/s, profiles/r2_prof_s2_dgrad_tc7.txt.)
 constexpr int TC_MAX_CLS = 4;
 struct TcOutMaps { CUtensorMap m[TC_MAX_CLS]; };
 struct TcClasses {
@@ -1191,37 +628,10 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
             float v[32];
             tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
             const int colb = col0 + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j];
-                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                t += nz;
-                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                t *= p.epi.gain;
-                v[j] = t;
-            }
-            if (p.epi.residual && valid) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 r = __ldg(r4 + j);
-                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                }
-            }
-            if (p.epi.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-            }
+            tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
             const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
             uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-            }
+            tc_stage_row(stg, row, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1245,221 +655,10 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
     }
 }
 
-// ------------------------------------------------------------------------------------------------ stride-2 data gradient, all four parity classes per window
-// conv_tc5m_kernel still loads the input window of a pixel tile once PER CLASS, and a class's K loop is only 1, 2 or 4 taps
-// per channel block: the window ring (two slots) then covers a few hundred cycles of latency and the tensor pipe idles (ncu,
-// profiles/r2_prof_s2_dgrad_tc5m.txt: tensor 40 %, L2 32 %, DRAM 47 % — nothing saturated).  Here ONE CTA pair per SM pair
-// keeps all four class accumulators in TMEM at once — 4 classes x 64 columns, double-buffered = 512 columns — so per
-// 32-channel block the window is loaded once and all nine taps run against it (the same 72-step K loop as a stride-1 3x3
-// layer); loads of the next window are four slots ahead.  Work item = (pixel tile pair, 64-column block); the epilogue of
-// item i (eight 32-column chunk stores into the four interleaved output sub-grids) overlaps the main loop of item i + 1.
-constexpr int TC7_NA = 4;                           // window ring slots
-constexpr int TC7_NB = 8;                           // B ring slots of 4 KB (32 filter rows per CTA)
-constexpr int TC7_N = 64;                           // columns per class accumulator
-constexpr size_t tc7_smem_bytes() {
-    return (size_t)TC7_NB * (TC7_N / 2) * 128 + (size_t)TC7_NA * TC3_ASLOT + (size_t)TC5_NSTG * TC_A_BYTES + 1024 + 256;
-}
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc7_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ TcOutMaps outs, const TcParams p, const __grid_constant__ TcClasses cls, const int n_blocks,
-                const int total_work) {
-    constexpr int B_HALF_BYTES = (TC7_N / 2) * 128;
-    constexpr uint32_t B_RING = (uint32_t)TC7_NB * B_HALF_BYTES;
-    constexpr uint32_t RING0 = B_RING + (uint32_t)TC7_NA * TC3_ASLOT;
-    constexpr uint32_t STG_OFF = RING0;
-    constexpr uint32_t RING = RING0 + (uint32_t)TC5_NSTG * TC_A_BYTES;
-    constexpr uint32_t BUF_COLS = TC_MAX_CLS * TC7_N;                    // 256 columns per accumulator set
-    constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;                         // two sets: the whole TMEM of the SM
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC7_N >> 3) << 17) | ((256u >> 4) << 24);
-    constexpr int NCHUNK = TC7_N / 32;
-    static_assert((B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc7: layout");
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_ring = base + B_RING;
-    const uint32_t bar_fullA = base + RING;
-    const uint32_t bar_emptyA = bar_fullA + 8 * TC7_NA;
-    const uint32_t bar_fullB = bar_emptyA + 8 * TC7_NA;
-    const uint32_t bar_emptyB = bar_fullB + 8 * TC7_NB;
-    const uint32_t bar_acc = bar_emptyB + 8 * TC7_NB;              // [2]
-    const uint32_t bar_tmem_empty = bar_acc + 16;                  // [2], leader's copy in use
-    const uint32_t tmem_slot = bar_tmem_empty + 16;
-    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const uint32_t a_bytes = (uint32_t)(p.ww * p.wh) * 128u;
-    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0) {
-        const int nblk = work % n_blocks;
-        int tile = (work / n_blocks) * 2 + (int)rank;
-        const int tq = tile % p.tiles_w; tile /= p.tiles_w;
-        const int tp = tile % p.tiles_h; tile /= p.tiles_h;
-        q0 = tq * p.tw; p0 = tp * p.th; n0 = tile; col0 = nblk * TC7_N;
-    };
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        for (int c = 0; c < cls.ncls; ++c) asm volatile("prefetch.tensormap [%0];" ::"l"(&outs.m[c]) : "memory");
-        for (int s = 0; s < TC7_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
-        for (int s = 0; s < TC7_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
-        mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
-        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
-
-    if (warp == 0) {
-        // ===================================================== TMA producer (both CTAs)
-        if (elect_one()) {
-            int ia = 0, ib = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters) {
-                int q0, p0, n0, col0;
-                decode(work, q0, p0, n0, col0);
-                for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
-                    const int sa = ia % TC7_NA;
-                    mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC7_NA)) & 1u) ^ 1u);
-                    if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
-                    tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
-                    for (int c = 0; c < cls.ncls; ++c)
-                        for (int t = 0; t < cls.ntaps[c]; ++t, ++ib) {
-                            const int sb = ib % TC7_NB;
-                            mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC7_NB)) & 1u) ^ 1u);
-                            if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
-                            tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, cls.wk[c][t] + cb * TC_BK,
-                                         col0 + (int)rank * (TC7_N / 2));
-                        }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer (leader CTA only)
-        if (leader && elect_one()) {
-            const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;
-            int ia = 0, ib = 0, it = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-                const uint32_t buf = (uint32_t)it & 1u;
-                if (it > 1) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-                for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
-                    const int sa = ia % TC7_NA;
-                    mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC7_NA)) & 1u);
-                    const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
-                    for (int c = 0; c < cls.ncls; ++c) {
-                        const uint32_t tmem_acc = tmem_base + buf * BUF_COLS + (uint32_t)c * TC7_N;
-                        for (int t = 0; t < cls.ntaps[c]; ++t, ++ib) {
-                            const int sb = ib % TC7_NB;
-                            mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC7_NB)) & 1u);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t aaddr = a0 + (uint32_t)cls.arow[c][t] * 128u;
-                            uint64_t da = (uint64_t)((aaddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | sbo | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-                            const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
-#pragma unroll
-                            for (int k = 0; k < TC_BK / 8; ++k)
-                                umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (cb > 0 || t > 0 || k > 0) ? 1u : 0u);
-                            umma2_commit(bar_emptyB + 8 * sb);
-                        }
-                    }
-                    umma2_commit(bar_emptyA + 8 * sa);
-                }
-                umma2_commit(bar_acc + 8 * buf);
-            }
-        }
-    } else {
-        // ===================================================== epilogue: 4 classes x NCHUNK chunk stores per work item
-        const int lg = warp & 3;
-        const int row = lg * 32 + lane;
-        const int iw = row % p.tw, ih = row / p.tw;
-        int it = 0, gch = 0;
-        for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-            int q0, p0, n0, col0;
-            decode(work, q0, p0, n0, col0);
-            const uint32_t buf = (uint32_t)it & 1u;
-            const int n = n0, pp = p0 + ih, qq = q0 + iw;
-            const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
-            mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int c = 0; c < cls.ncls; ++c) {
-                const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + cls.o_offy[c]) * p.FW + qq * p.o_mul + cls.o_offx[c];
-                float nz = 0.f;
-                if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
-#pragma unroll 1
-                for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
-                    if (gch >= TC5_NSTG) {
-                        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                    }
-                    float v[32];
-                    tmem_ld32(tmem_base + buf * BUF_COLS + (uint32_t)(c * TC7_N + ch * 32) + ((uint32_t)(lg * 32) << 16), v);
-                    const int colb = col0 + ch * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = v[j];
-                        if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                        t += nz;
-                        if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                        t *= p.epi.gain;
-                        v[j] = t;
-                    }
-                    if (p.epi.residual && valid) {
-                        const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 r = __ldg(r4 + j);
-                            v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                            v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                            v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                            v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                        }
-                    }
-                    if (p.epi.round_tf32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-                    }
-                    const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
-                    uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    const bool last = (c == cls.ncls - 1) && (ch == NCHUNK - 1);
-                    if (last) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (warp == 2 && lane == 0) {
-                        tma_store_4d(&outs.m[c], base + stg_off, colb, q0, p0, n0);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        if (last)
-                            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
-                    }
-                }
-            }
-        }
-        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ persistent per-tap pair kernel (experimental)
-// conv_tc2_kernel (stride-2 fprop, maps too small for the shared window) with the two changes that made conv_tc5_kernel:
-// a persistent loop over (tile pair, 128-column block) work items, two accumulator buffers in TMEM and dedicated output
-// staging, so loads and MMAs of tile i+1 overlap the epilogue of tile i.  NOT YET VALIDATED ON HARDWARE: written at the
-// end of round 1 after the GPU budget was spent; off unless SAE_TC6=1 (the conv parity tests cover its shapes).
+// ------------------------------------------------------------------------------------------------ persistent per-tap pair kernel
+// Stride-2 fprop and maps too small for the shared window: CTA pairs, one 4-D TMA box per tap (the conv stride is the TMA
+// element stride), a persistent loop over (tile pair, column block) work items, two accumulator buffers in TMEM and dedicated
+// output staging, so loads and MMAs of tile i + 1 overlap the epilogue of tile i.
 // BLOCK_N = 128: 3 x (16 KB A + 8 KB half-B) + 2 x 16 KB staging = 104 KB, two CTAs per SM.
 // BLOCK_N = 256: ONE CTA per SM owning all 512 TMEM columns (2 x 256) and a 5-deep ring, 5 x (16 KB + 16 KB) + 32 KB = 192 KB.
 // The per-tap kernels are bound by the L2 -> SM feed (ncu, profiles/r2_prof_s2_fprop_tc6.txt: lts 58 %, tensor pipe 53 %):
@@ -1606,37 +805,10 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
             float v[32];
             tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
             const int colb = col0 + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j];
-                if (p.epi.bias) t += __ldg(p.epi.bias + colb + j);
-                t += nz;
-                if (p.epi.act == 3) t = t > 0.f ? t : t * p.epi.alpha;
-                t *= p.epi.gain;
-                v[j] = t;
-            }
-            if (p.epi.residual && valid) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.epi.residual + pixel * p.Ncol + colb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 r = __ldg(r4 + j);
-                    v[4 * j + 0] = (v[4 * j + 0] + r.x) * p.epi.res_scale;
-                    v[4 * j + 1] = (v[4 * j + 1] + r.y) * p.epi.res_scale;
-                    v[4 * j + 2] = (v[4 * j + 2] + r.z) * p.epi.res_scale;
-                    v[4 * j + 3] = (v[4 * j + 3] + r.w) * p.epi.res_scale;
-                }
-            }
-            if (p.epi.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-            }
+            tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
             const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
             uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                *reinterpret_cast<float4*>(stg + ((j ^ (row & 7)) << 4)) = o;
-            }
+            tc_stage_row(stg, row, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1672,6 +844,7 @@ int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims
 struct TcProblem {
     const float* src; int SN, SH, SW, SC;      // source activation [SN,SH,SW,SC]
     const float* wmat; int Ncol, Ktot;          // filter matrix [Ncol, Ktot = ntaps*SC]
+    int w_per_sample;                           // 1: wmat holds one filter matrix per image, [SN, Ncol, Ktot]
     float* out; int OH, OW;                     // output sub-grid [SN, OH, OW, Ncol] ...
     int o_mul, o_offy, o_offx, FH, FW;          // ... placed at (o_mul*p + o_offy, o_mul*q + o_offx) of the full [SN,FH,FW,Ncol]
     int stride, ntaps;
@@ -1702,6 +875,7 @@ static void tc_fill_params(const TcProblem& pr, const EpiParams& e, TcParams& p)
     p.ON = pr.SN; p.OH = pr.OH; p.OW = pr.OW; p.Ncol = pr.Ncol; p.src_c = pr.SC;
     for (int t = 0; t < pr.ntaps; ++t) { p.oy[t] = (short)pr.oy[t]; p.ox[t] = (short)pr.ox[t]; p.wk[t] = pr.wk[t]; }
     p.o_mul = pr.o_mul; p.o_offy = pr.o_offy; p.o_offx = pr.o_offx; p.FH = pr.FH; p.FW = pr.FW;
+    p.w_nstride = pr.w_per_sample ? pr.Ncol : 0;
     p.epi = e;
 }
 
@@ -1715,7 +889,7 @@ static int tc_encode_maps(const TcProblem& pr, const TcParams& p, int b_rows, CU
         if (rc) return rc;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)pr.Ktot, (cuuint64_t)pr.Ncol};
+        cuuint64_t dims[2] = {(cuuint64_t)pr.Ktot, (cuuint64_t)pr.Ncol * (cuuint64_t)(pr.w_per_sample ? pr.SN : 1)};
         cuuint64_t strides[1] = {(cuuint64_t)pr.Ktot * 4};
         cuuint32_t box[2] = {32, (cuuint32_t)b_rows};
         cuuint32_t es[2] = {1, 1};
@@ -1752,38 +926,7 @@ static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
     return check_launch("conv_tc");
 }
 
-// CTA-pair (cta_group::2) launch: cluster of 2 along x
-template <int BLOCK_N>
-static int tc2_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
-    TcParams p;
-    tc_fill_params(pr, e, p);
-    CUtensorMap msrc, mw, mout;
-    int rc = tc_encode_maps(pr, p, BLOCK_N / 2, &msrc, &mw, &mout);
-    if (rc) return rc;
-    constexpr size_t smem = tc2_smem_bytes<BLOCK_N>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int pairs = (tiles + 1) / 2;
-    const int n_blocks = pr.Ncol / BLOCK_N;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(pairs * n_blocks * 2), 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks));
-    return check_launch("conv_tc2");
-}
-
-// experimental persistent variant of tc2_launch (conv_tc6_kernel): SAE_TC6=1
+// persistent per-tap pair launch (conv_tc6_kernel): stride-2 fprop, small maps — everything the shared window does not take
 template <int BLOCK_N>
 static int tc6_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
     TcParams p;
@@ -1818,115 +961,9 @@ static int tc6_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
     return check_launch("conv_tc6");
 }
 
-// shared-window pair launch: tile = 16 rows x 8 columns of one image; window = tile + tap offset range
-template <int BLOCK_N>
-static int tc3_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
-    TcParams p;
-    tc_fill_params(pr, e, p);
-    p.tw = 8; p.th = 16; p.tn = 1;
-    p.tiles_w = (pr.OW + p.tw - 1) / p.tw;
-    p.tiles_h = (pr.OH + p.th - 1) / p.th;
-    p.tiles_n = pr.SN;
-    int oy_min = pr.oy[0], oy_max = pr.oy[0], ox_min = pr.ox[0], ox_max = pr.ox[0];
-    for (int t = 1; t < pr.ntaps; ++t) {
-        oy_min = pr.oy[t] < oy_min ? pr.oy[t] : oy_min; oy_max = pr.oy[t] > oy_max ? pr.oy[t] : oy_max;
-        ox_min = pr.ox[t] < ox_min ? pr.ox[t] : ox_min; ox_max = pr.ox[t] > ox_max ? pr.ox[t] : ox_max;
-    }
-    p.oy_min = oy_min; p.ox_min = ox_min;
-    p.ww = p.tw + (ox_max - ox_min);
-    p.wh = p.th + (oy_max - oy_min);
-    for (int t = 0; t < pr.ntaps; ++t) p.arow[t] = (unsigned short)((pr.oy[t] - oy_min) * p.ww + (pr.ox[t] - ox_min));
-
-    CUtensorMap msrc, mw, mout;
-    int rc = tc_encode_maps(pr, p, BLOCK_N / 2, &msrc, &mw, &mout);      // weight + output maps as usual
-    if (rc) return rc;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)pr.SC, (cuuint64_t)pr.SW, (cuuint64_t)pr.SH, (cuuint64_t)pr.SN};
-        cuuint64_t strides[3] = {(cuuint64_t)pr.SC * 4, (cuuint64_t)pr.SW * pr.SC * 4, (cuuint64_t)pr.SH * pr.SW * pr.SC * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)p.ww, (cuuint32_t)p.wh, 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
-        rc = encode_map(&msrc, pr.src, 4, dims, strides, box, es);
-        if (rc) return rc;
-    }
-    constexpr size_t smem = tc3_smem_bytes<BLOCK_N>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int pairs = (tiles + 1) / 2;
-    const int n_blocks = pr.Ncol / BLOCK_N;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(pairs * n_blocks * 2), 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks));
-    return check_launch("conv_tc3");
-}
-
-// persistent launch: one wave of CTA pairs (two CTAs per SM) looping over the work items
-template <int BLOCK_N>
-static int tc4_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
-    TcParams p;
-    tc_fill_params(pr, e, p);
-    p.tw = 8; p.th = 16; p.tn = 1;
-    p.tiles_w = (pr.OW + p.tw - 1) / p.tw;
-    p.tiles_h = (pr.OH + p.th - 1) / p.th;
-    p.tiles_n = pr.SN;
-    int oy_min = pr.oy[0], oy_max = pr.oy[0], ox_min = pr.ox[0], ox_max = pr.ox[0];
-    for (int t = 1; t < pr.ntaps; ++t) {
-        oy_min = pr.oy[t] < oy_min ? pr.oy[t] : oy_min; oy_max = pr.oy[t] > oy_max ? pr.oy[t] : oy_max;
-        ox_min = pr.ox[t] < ox_min ? pr.ox[t] : ox_min; ox_max = pr.ox[t] > ox_max ? pr.ox[t] : ox_max;
-    }
-    p.oy_min = oy_min; p.ox_min = ox_min;
-    p.ww = p.tw + (ox_max - ox_min);
-    p.wh = p.th + (oy_max - oy_min);
-    for (int t = 0; t < pr.ntaps; ++t) p.arow[t] = (unsigned short)((pr.oy[t] - oy_min) * p.ww + (pr.ox[t] - ox_min));
-    CUtensorMap msrc, mw, mout;
-    int rc = tc_encode_maps(pr, p, BLOCK_N / 2, &msrc, &mw, &mout);
-    if (rc) return rc;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)pr.SC, (cuuint64_t)pr.SW, (cuuint64_t)pr.SH, (cuuint64_t)pr.SN};
-        cuuint64_t strides[3] = {(cuuint64_t)pr.SC * 4, (cuuint64_t)pr.SW * pr.SC * 4, (cuuint64_t)pr.SH * pr.SW * pr.SC * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)p.ww, (cuuint32_t)p.wh, 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
-        rc = encode_map(&msrc, pr.src, 4, dims, strides, box, es);
-        if (rc) return rc;
-    }
-    constexpr size_t smem = tc4_smem_bytes<BLOCK_N>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc4_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int n_blocks = pr.Ncol / BLOCK_N;
-    const int total_work = ((tiles + 1) / 2) * n_blocks;
-    int clusters = sm_count();                       // 2 CTAs per SM, 2 CTAs per cluster
-    if (clusters > total_work) clusters = total_work;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc4_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks, total_work));
-    return check_launch("conv_tc4");
-}
-
-// persistent launch with overlapped epilogue (conv_tc5_kernel): same grid as tc4_launch
-template <int BLOCK_N>
+// shared-window persistent launch (conv_tc5_kernel): tile = 16 rows x 8 columns of one image; window = tile + tap offset range;
+// one wave of CTA pairs, CTAS CTAs per SM
+template <int BLOCK_N, int NACC = 2, int NA = TC3_NA, int NB = tc5_nb<BLOCK_N>(), int CTAS = 2>
 static int tc5_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
     TcParams p;
     tc_fill_params(pr, e, p);
@@ -1954,16 +991,16 @@ static int tc5_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
         rc = encode_map(&msrc, pr.src, 4, dims, strides, box, es);
         if (rc) return rc;
     }
-    constexpr size_t smem = tc5_smem_bytes<BLOCK_N>();
+    constexpr size_t smem = tc5_smem_bytes<BLOCK_N, NA, NB>();
     static bool attr_done = false;
     if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5_kernel<BLOCK_N, NACC, NA, NB, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int n_blocks = pr.Ncol / BLOCK_N;
     const int total_work = ((tiles + 1) / 2) * n_blocks;
-    int clusters = sm_count();                       // 2 CTAs per SM, 2 CTAs per cluster
+    int clusters = sm_count() * CTAS / 2;            // CTAS CTAs per SM, 2 CTAs per cluster
     if (clusters > total_work) clusters = total_work;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
@@ -1975,20 +1012,13 @@ static int tc5_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5_kernel<BLOCK_N>, msrc, mw, mout, p, n_blocks, total_work));
+    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5_kernel<BLOCK_N, NACC, NA, NB, CTAS>, msrc, mw, mout, p, n_blocks, total_work));
     return check_launch("conv_tc5");
 }
 
-static int tc4_mode() {
-    static int mode = -1;
-    if (mode < 0) { const char* v = getenv("SAE_TC_PERSISTENT"); mode = v ? atoi(v) : 1; }
-    return mode;
-}
-
-static bool tc3_ok(const TcProblem& pr) {
-    static int mode = -1;
-    if (mode < 0) { const char* v = getenv("SAE_TC_WINDOW"); mode = (v && v[0] == '0') ? 0 : 1; }
-    if (!mode || pr.stride != 1 || pr.OW < 8 || pr.OH < 16 || pr.Ncol % 32 != 0) return false;
+// can the shared-window kernel take the problem?  (stride 1, a tile of 16 x 8 output pixels exists, tap offsets span <= 2)
+static bool window_ok(const TcProblem& pr) {
+    if (pr.stride != 1 || pr.OW < 8 || pr.OH < 16 || pr.Ncol % 32 != 0) return false;
     int oy_min = pr.oy[0], oy_max = pr.oy[0], ox_min = pr.ox[0], ox_max = pr.ox[0];
     for (int t = 1; t < pr.ntaps; ++t) {
         oy_min = pr.oy[t] < oy_min ? pr.oy[t] : oy_min; oy_max = pr.oy[t] > oy_max ? pr.oy[t] : oy_max;
@@ -1997,63 +1027,19 @@ static bool tc3_ok(const TcProblem& pr) {
     return (oy_max - oy_min) <= 2 && (ox_max - ox_min) <= 2;
 }
 
-static int g_pair_mode = -1;     // -1 unread, 0 off, 1 on
-static bool pair_enabled() {
-    if (g_pair_mode < 0) {
-        const char* v = getenv("SAE_TC_PAIR");
-        g_pair_mode = (v && v[0] == '0') ? 0 : 1;
-    }
-    return g_pair_mode == 1;
-}
-
 static int tc_dispatch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
-    if (pair_enabled()) {
-        // enough pixel tiles to make pairs worthwhile; 256-wide channel blocks when the layer has them
-        const int64_t pixels = (int64_t)pr.SN * pr.OH * pr.OW;
-        if (pixels >= 2 * 128) {
-            if (tc3_ok(pr)) {
-                // measured (profiles/r1_conv_bench.txt): with >= 128 output channels the one-tile-per-CTA kernel wins (fresh
-                // CTAs prefetch while their SM neighbour drains; the persistent loop serialises load -> MMA -> epilogue per
-                // CTA and the two co-resident CTAs tend to run in lock-step); the narrow 32/64-channel layers, whose
-                // main loop is ~1k cycles per tile, are faster persistent (setup cost amortised).  SAE_TC_PERSISTENT=2
-                // forces the persistent kernel everywhere, 0 disables it.
-                const int mode = tc4_mode();
-                // SAE_TC5: 0 = off; 1 = the overlapped-epilogue persistent kernel replaces conv_tc4 on the narrow layers only;
-                // 2 (default) = it also takes every wide layer whose K loop has at most SAE_TC5_KB 32-channel blocks, as
-                // 128-column blocks.  Measured (profiles/r1_conv_bench_tc5.txt): it wins at EVERY depth — +18 % on 128 -> 128 at
-                // 256^2 (epilogue-bound before), +7 % on 256 -> 256, +3 % on 512 -> 512 against the 256-column one-tile kernel,
-                // 1.2-1.6x on the HBM-bound 1x1 / narrow / short-loop stride-2 dgrad shapes — so the default threshold is "all".
-                static int tc5 = -1, tc5_kb = -1;
-                if (tc5 < 0) { const char* v = getenv("SAE_TC5"); tc5 = v ? atoi(v) : 2; }
-                if (tc5_kb < 0) { const char* v = getenv("SAE_TC5_KB"); tc5_kb = v ? atoi(v) : (1 << 20); }
-                if (tc5 && mode) {
-                    if (pr.Ncol % 128 != 0) return pr.Ncol % 64 == 0 ? tc5_launch<64>(pr, e, st) : tc5_launch<32>(pr, e, st);
-                    if (tc5 >= 2 && pr.ntaps * (pr.SC / TC_BK) <= tc5_kb) return tc5_launch<128>(pr, e, st);
-                }
-                // short main loops (1x1 convs, the 1- and 2-tap parity classes of a stride-2 data gradient): per-tile setup
-                // dominates just as it does for the narrow layers -> persistent kernel when the K loop has at most
-                // SAE_TC_PERSIST_KB 32-channel blocks
-                static int persist_kb = -1;
-                if (persist_kb < 0) { const char* v = getenv("SAE_TC_PERSIST_KB"); persist_kb = v ? atoi(v) : 0; }
-                const bool short_loop = pr.ntaps * (pr.SC / TC_BK) <= persist_kb;
-                if (pr.Ncol % 128 == 0 && mode != 2 && !(mode && short_loop))
-                    return pr.Ncol % 256 == 0 ? tc3_launch<256>(pr, e, st) : tc3_launch<128>(pr, e, st);
-                if (mode) {
-                    if (pr.Ncol % 256 == 0) return tc4_launch<256>(pr, e, st);
-                    if (pr.Ncol % 128 == 0) return tc4_launch<128>(pr, e, st);
-                    if (pr.Ncol % 64 == 0) return tc4_launch<64>(pr, e, st);
-                    return tc4_launch<32>(pr, e, st);
-                }
-            }
-            static int tc6 = -1;
-            if (tc6 < 0) { const char* v = getenv("SAE_TC6"); tc6 = v ? atoi(v) : 2; }
-            // SAE_TC6: 0 = one-tile kernels (conv_tc2); 1 = persistent, 128-column blocks; 2 (default) = persistent, 256-column
-            // blocks with one CTA per SM where the layer has them
-            if (tc6 >= 2 && pr.Ncol % 256 == 0) return tc6_launch<256>(pr, e, st);
-            if (tc6 && pr.Ncol % 128 == 0) return tc6_launch<128>(pr, e, st);
-            if (pr.Ncol % 256 == 0) return tc2_launch<256>(pr, e, st);
-            if (pr.Ncol % 128 == 0) return tc2_launch<128>(pr, e, st);
+    // enough pixel tiles to make CTA pairs worthwhile
+    if ((int64_t)pr.SN * pr.OH * pr.OW >= 2 * 128) {
+        if (window_ok(pr)) {
+            // every stride-1 shared-window problem: 3x3 / 1x1 fprop and dgrad at all widths, the parity classes of a stride-2
+            // data gradient (measured against the one-tile kernels it replaced: profiles/r1_conv_bench_tc5.txt)
+            if (pr.Ncol % 128 == 0) return tc5_launch<128>(pr, e, st);
+            return pr.Ncol % 64 == 0 ? tc5_launch<64>(pr, e, st) : tc5_launch<32>(pr, e, st);
         }
+        // per-tap loads (the conv stride is the TMA element stride): 256-column blocks at one CTA per SM where the layer has
+        // them (565 -> 722 TFLOP/s on 128 -> 256 at 257^2 stride 2, profiles/r2_conv_bench_s2.txt), 128-column blocks otherwise
+        if (pr.Ncol % 256 == 0) return tc6_launch<256>(pr, e, st);
+        if (pr.Ncol % 128 == 0) return tc6_launch<128>(pr, e, st);
     }
     if (pr.Ncol % 128 == 0) return tc_launch<128>(pr, e, st);
     if (pr.Ncol % 64 == 0) return tc_launch<64>(pr, e, st);
@@ -2075,9 +1061,7 @@ static TcProblem tc_subproblem(const TcProblem& pr, int r0, int r1, int c0, int 
 // row and column of mostly empty 128-pixel tiles (33 x 33 outputs -> 15 tiles instead of 8.5).  Such thin remainders are
 // split off and run as their own launches, whose tiles gather the strip across images (tn > 1) instead.
 static int tc_dispatch_split(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
-    static int mode = -1;
-    if (mode < 0) { const char* v = getenv("SAE_TC_SPLIT"); mode = (v && v[0] == '0') ? 0 : 1; }
-    if (!mode || !pair_enabled() || !tc3_ok(pr)) return tc_dispatch(pr, e, st);
+    if (!window_ok(pr)) return tc_dispatch(pr, e, st);
     const int rem_h = pr.OH % 16, rem_w = pr.OW % 8;
     const int main_h = (rem_h >= 1 && rem_h <= 4 && pr.OH >= 32) ? pr.OH - rem_h : pr.OH;
     const int main_w = (rem_w >= 1 && rem_w <= 2 && pr.OW >= 16) ? pr.OW - rem_w : pr.OW;
@@ -2112,6 +1096,7 @@ bool tc_dgrad_eligible(const sae_conv_geom* g) {
 int tc_fprop(const float* x, const float* w, float* y, const sae_conv_geom* g, const EpiParams& e, cudaStream_t st) {
     if (!ptr_ok(x, w, y)) return fail(SAE_E_INVALID, "conv2d_fprop(tcgen05): pointers must be 16-byte aligned");
     TcProblem pr;
+    pr.w_per_sample = 0;
     pr.src = x; pr.SN = g->N; pr.SH = g->H; pr.SW = g->W; pr.SC = g->C;
     pr.wmat = w; pr.Ncol = g->K; pr.Ktot = g->R * g->S * g->C;
     pr.out = y; pr.OH = g->P; pr.OW = g->Q;
@@ -2125,12 +1110,51 @@ int tc_fprop(const float* x, const float* w, float* y, const sae_conv_geom* g, c
     return tc_dispatch_split(pr, e, st);
 }
 
+// Per-sample filters (the style-modulated convolution, stylegan2_layers.py:284-323): image n is convolved with filter matrix n.
+// Only the shared-window kernel implements it, for stride-1 problems whose 16 x 8 tiles cover the map exactly with an even
+// number of tiles per image (both CTAs of a pair then read the same filter); anything else reports UNSUPPORTED and the
+// caller scales the input instead.
+bool tc_per_sample_eligible(const sae_conv_geom* g, int dgrad) {
+    if (g->stride != 1 || g->R * g->S > TC_MAX_TAPS) return false;
+    const int src_c = dgrad ? g->K : g->C, ncol = dgrad ? g->C : g->K;
+    const int oh = dgrad ? g->H : g->P, ow = dgrad ? g->W : g->Q;
+    if (src_c % 32 != 0 || ncol % 32 != 0 || oh % 16 != 0 || ow % 8 != 0) return false;
+    if (((oh / 16) * (ow / 8)) % 2 != 0) return false;
+    if (g->R > 3 || g->S > 3) return false;
+    return (int64_t)g->N * oh * ow >= 2 * 128;
+}
+
+int tc_conv_per_sample(const float* src, const float* w, float* out, const sae_conv_geom* g, int dgrad, const EpiParams& e, cudaStream_t st) {
+    if (!tc_per_sample_eligible(g, dgrad)) return fail(SAE_E_UNSUPPORTED, "per-sample conv: shape outside the shared-window kernel");
+    if (!ptr_ok(src, w, out)) return fail(SAE_E_INVALID, "per-sample conv: pointers must be 16-byte aligned");
+    TcProblem pr;
+    pr.w_per_sample = 1;
+    pr.stride = 1; pr.o_mul = 1; pr.o_offy = 0; pr.o_offx = 0; pr.ntaps = g->R * g->S;
+    pr.src = src; pr.wmat = w; pr.out = out; pr.SN = g->N;
+    if (!dgrad) {
+        pr.SH = g->H; pr.SW = g->W; pr.SC = g->C; pr.Ncol = g->K; pr.Ktot = g->R * g->S * g->C;
+        pr.OH = g->P; pr.OW = g->Q; pr.FH = g->P; pr.FW = g->Q;
+    } else {
+        pr.SH = g->P; pr.SW = g->Q; pr.SC = g->K; pr.Ncol = g->C; pr.Ktot = g->R * g->S * g->K;
+        pr.OH = g->H; pr.OW = g->W; pr.FH = g->H; pr.FW = g->W;
+    }
+    for (int r = 0; r < g->R; ++r)
+        for (int s_ = 0; s_ < g->S; ++s_) {
+            const int t = r * g->S + s_;
+            pr.oy[t] = dgrad ? g->pad_t - r : r - g->pad_t;
+            pr.ox[t] = dgrad ? g->pad_l - s_ : s_ - g->pad_l;
+            pr.wk[t] = t * pr.SC;
+        }
+    if (!window_ok(pr)) return fail(SAE_E_UNSUPPORTED, "per-sample conv: tap offsets outside the shared window");
+    if (pr.Ncol % 128 == 0) return tc5_launch<128>(pr, e, st);
+    return pr.Ncol % 64 == 0 ? tc5_launch<64>(pr, e, st) : tc5_launch<32>(pr, e, st);
+}
+
 // One conv_tc5m launch over the rectangle all four parity classes share, then each class's thin remainder strips through
 // the ordinary per-class path.  Returns SAE_E_UNSUPPORTED (quietly) when the shape is outside the merged kernel's reach.
-static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t st, int variant) {
+static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t st) {
     const TcProblem& p0 = cp[0];
-    const bool quad = variant >= 2;              // conv_tc7_kernel: all four classes per window, 64-column blocks
-    if (!pair_enabled() || p0.Ncol % (quad ? 64 : 128) != 0 || p0.SC % 32 != 0) return SAE_E_UNSUPPORTED;
+    if (p0.Ncol % 128 != 0 || p0.SC % 32 != 0) return SAE_E_UNSUPPORTED;
     int MH = cp[0].OH, MW = cp[0].OW;
     int oy_min = cp[0].oy[0], oy_max = oy_min, ox_min = cp[0].ox[0], ox_max = ox_min;
     for (int c = 0; c < TC_MAX_CLS; ++c) {
@@ -2159,7 +1183,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     TcOutMaps outs;
     cls.ncls = TC_MAX_CLS;
     CUtensorMap msrc, mw, mdummy;
-    int rc = tc_encode_maps(main, p, (quad ? TC7_N : 128) / 2, &msrc, &mw, &mdummy);      // weight map (the others are rebuilt below)
+    int rc = tc_encode_maps(main, p, 128 / 2, &msrc, &mw, &mdummy);      // weight map (the others are rebuilt below)
     if (rc) return rc;
     {
         cuuint64_t dims[4] = {(cuuint64_t)main.SC, (cuuint64_t)main.SW, (cuuint64_t)main.SH, (cuuint64_t)main.SN};
@@ -2187,17 +1211,16 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
         rc = encode_map(&outs.m[c], q.out + ((int64_t)q.o_offy * q.FW + q.o_offx) * q.Ncol, 4, dims, strides, box, es);
         if (rc) return rc;
     }
-    const size_t smem = quad ? tc7_smem_bytes() : tc5_smem_bytes<128>();
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[quad]) {
-        if (quad) SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5m_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[quad] = true;
+    constexpr size_t smem = tc5_smem_bytes<128, TC3_NA, tc5_nb<128>()>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5m_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
     }
     const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int n_blocks = main.Ncol / (quad ? TC7_N : 128);
-    const int total_work = ((tiles + 1) / 2) * (quad ? 1 : TC_MAX_CLS) * n_blocks;
-    int clusters = quad ? sm_count() / 2 : sm_count();       // one CTA per SM (all 512 TMEM columns) / two
+    const int n_blocks = main.Ncol / 128;
+    const int total_work = ((tiles + 1) / 2) * TC_MAX_CLS * n_blocks;
+    int clusters = sm_count();
     if (clusters > total_work) clusters = total_work;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
@@ -2209,9 +1232,8 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (quad) SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc7_kernel, msrc, mw, outs, p, cls, n_blocks, total_work));
-    else SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<128>, msrc, mw, outs, p, cls, n_blocks, total_work));
-    rc = check_launch(quad ? "conv_tc7" : "conv_tc5m");
+    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<128>, msrc, mw, outs, p, cls, n_blocks, total_work));
+    rc = check_launch("conv_tc5m");
     if (rc) return rc;
     // remainders of each class beyond the shared rectangle: right strip (full height, takes the corner), bottom strip
     for (int c = 0; c < TC_MAX_CLS; ++c) {
@@ -2225,6 +1247,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
 int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g, const EpiParams& e, cudaStream_t st) {
     if (!ptr_ok(dy, wt, dx)) return fail(SAE_E_INVALID, "conv2d_dgrad(tcgen05): pointers must be 16-byte aligned");
     TcProblem pr;
+    pr.w_per_sample = 0;
     pr.src = dy; pr.SN = g->N; pr.SH = g->P; pr.SW = g->Q; pr.SC = g->K;
     pr.wmat = wt; pr.Ncol = g->C; pr.Ktot = g->R * g->S * g->K;
     pr.stride = 1; pr.FH = g->H; pr.FW = g->W;
@@ -2273,11 +1296,11 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
             cls_pr[ncls++] = pr;
         }
     static int merged = -1;
-    // SAE_DGRAD_MERGED: 0 = one launch per class; 1 = conv_tc5m (one launch, class index in the work item); 2 = conv_tc7
-    // (all four classes per input window)
+    // SAE_DGRAD_MERGED: 1 (default) = conv_tc5m, one launch with the class index in the work item (386 -> 416, 441 -> 506
+    // TFLOP/s on the discriminator shapes, profiles/r2_conv_bench_s2.txt); 0 = one launch per class (A/B runs)
     if (merged < 0) { const char* v = getenv("SAE_DGRAD_MERGED"); merged = v ? atoi(v) : 1; }
     if (merged && ncls == TC_MAX_CLS && !need_zero) {
-        int rc = tc_dgrad_merged(cls_pr, e, st, merged);
+        int rc = tc_dgrad_merged(cls_pr, e, st);
         if (rc != SAE_E_UNSUPPORTED) return rc;
     }
     for (int c = 0; c < ncls; ++c) {

@@ -422,6 +422,29 @@ filter_prep_kernel(const float* __restrict__ w, float* __restrict__ krsc, float*
     }
 }
 
+// Per-sample filters of the style-modulated convolution (stylegan2_layers.py:284-323): out[n,k,r,s,c] = w[k,r,s,c] * s[n,c]
+// (fprop, "KRSC" per image) and out_t[n,c,r,s,k] = the same values transposed (dgrad).  w is the prepared [K,R,S,C] filter
+// (scaled, demodulated, TF32-rounded); the product is rounded again.  One block column per image.
+__global__ void __launch_bounds__(256)
+filter_modulate_kernel(const float* __restrict__ w_krsc, const float* __restrict__ s, float* __restrict__ out, float* __restrict__ out_t,
+                       int K, int C, int RS, int round_tf32) {
+    const int n = blockIdx.y;
+    const int total = K * C * RS;
+    const float* sn = s + (size_t)n * C;
+    float* on = out ? out + (size_t)n * total : nullptr;
+    float* otn = out_t ? out_t + (size_t)n * total : nullptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % C;
+        int t = i / C;
+        const int rs = t % RS;
+        const int k = t / RS;
+        float v = __ldg(w_krsc + i) * __ldg(sn + c);
+        if (round_tf32) v = rna_tf32(v);
+        if (on) on[i] = v;
+        if (otn) otn[((size_t)c * RS + rs) * K + k] = v;
+    }
+}
+
 // adjoint: d_w[k,c,r,s] = scale * d_krsc[k,r,s,c]
 __global__ void __launch_bounds__(256)
 filter_unprep_kernel(const float* __restrict__ g, float* __restrict__ dw, int K, int C, int RS, float scale) {
@@ -651,6 +674,17 @@ extern "C" int sae_filter_prep(const float* w, float* out_krsc, float* out_crsk,
     filter_prep_kernel<<<grid_for((int64_t)k * c * r * s_, 256), 256, 0, (cudaStream_t)stream>>>(w, out_krsc, out_crsk, k, c, r * s_, scale,
                                                                                                round_tf32);
     return check_launch("filter_prep");
+}
+
+extern "C" int sae_filter_modulate(const float* w_krsc, const float* s, float* out_krsc, float* out_crsk, int n, int k, int c,
+                                   int r, int s_, int round_tf32, void* stream) {
+    if (n == 0) return SAE_OK;
+    if (!w_krsc || !s || (!out_krsc && !out_crsk) || n < 0 || k <= 0 || c <= 0 || r <= 0 || s_ <= 0)
+        return fail(SAE_E_INVALID, "filter_modulate: bad arguments");
+    if ((int64_t)k * c * r * s_ >= ((int64_t)1 << 31) || n > 65535) return fail(SAE_E_UNSUPPORTED, "filter_modulate: too large");
+    dim3 grid(grid_for((int64_t)k * c * r * s_, 256, 2), (unsigned)n);
+    filter_modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_krsc, s, out_krsc, out_crsk, k, c, r * s_, round_tf32);
+    return check_launch("filter_modulate");
 }
 
 extern "C" int sae_filter_unprep(const float* d_krsc, float* d_w, int k, int c, int r, int s_, float scale, void* stream) {

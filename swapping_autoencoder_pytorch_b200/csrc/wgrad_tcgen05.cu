@@ -39,6 +39,14 @@ struct WgParams {
                                      // (narrow layers pack 4/cpt taps side by side into the 128 N-columns)
     int shared_b;                    // 1: the 3 horizontal taps of a filter row read ONE 40-pixel x window per sub-tile
                                      //    (descriptor start shifted by s pixel rows) instead of 3 separate 32-pixel boxes
+    // style-modulated convolution (stylegan2_layers.py:284-323 as "dense conv of x * s with a shared filter W"): x arrives
+    // UNSCALED.  The accumulators are drained once per image n (a CTA's chunk range is cut at image boundaries), and the
+    // drain forms both gradients from G_n[k,tap,c] = sum_pixels dy x:   dW[k,tap,c] += s[n,c] G_n,
+    // ds[n,c] += sum_{k,tap} W[k,tap,c] G_n.  No modulated copy of x, no per-sample weight-gradient array.
+    int chunks_per_image;            // > 0 selects that mode (tn == 1)
+    const float* mod_s;              // [N, C]
+    const float* mod_w;              // [Ko, taps, C], the filter the forward pass used
+    float* mod_ds;                   // [N, C], accumulated
 };
 
 constexpr int WG_WIN = 40;                         // pixels per shared window (32 + 2 halo, rounded up to a multiple of 8)
@@ -83,7 +91,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const uint32_t bar_full = base + WG_STAGES * STAGE_BYTES;
     const uint32_t bar_empty = bar_full + 8 * WG_STAGES;
     const uint32_t bar_acc = bar_empty + 8 * WG_STAGES;
-    const uint32_t tmem_slot = bar_acc + 8;
+    const uint32_t bar_drained = bar_acc + 8;          // modulated mode: the epilogue has emptied the accumulators
+    const uint32_t tmem_slot = bar_drained + 8;
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,6 +116,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
+        mbar_init(bar_drained, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -153,7 +163,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             }
         } else if (warp == 1) {
             if (elect_one()) {
+                int seg = 0;
                 for (int kb = 0; kb < KB; ++kb) {
+                    // modulated mode: a new image starts at this chunk -> hand the finished accumulators to the epilogue and
+                    // wait until they are drained; the first MMAs of the segment then overwrite instead of accumulating
+                    const bool seg_start = kb == 0 || (p.chunks_per_image > 0 && (chunk_begin + kb) % p.chunks_per_image == 0);
+                    if (seg_start && kb > 0) {
+                        umma_commit(bar_acc);
+                        mbar_wait(bar_drained, (uint32_t)seg & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        ++seg;
+                    }
                     const int s = kb % WG_STAGES;
                     const uint32_t ph = (uint32_t)(kb / WG_STAGES) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
@@ -166,7 +186,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                             for (int k = 0; k < WG_KPIX / 8; ++k) {
                                 // tap s = g reads window rows [g + 8k, g + 8k + 8)
                                 const uint64_t db = make_desc_mn_win(sa + WG_OPER + (uint32_t)(g + 8 * k) * 128u, p.shared_b == 1);
-                                umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                                umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db, IDESC, (!seg_start || k > 0) ? 1u : 0u);
                             }
                             continue;
                         }
@@ -175,7 +195,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                         for (int k = 0; k < WG_KPIX / 8; ++k) {
                             // next 8 pixels along K: +1024 B = +64 in the (addr >> 4) field
                             umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), IDESC,
-                                      (kb > 0 || k > 0) ? 1u : 0u);
+                                      (!seg_start || k > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(bar_empty + 8 * s);
@@ -186,22 +206,50 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             const int lg = warp & 3;
             const int row = lg * 32 + lane;
             const int o = o0 + row;
-            mbar_wait(bar_acc, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t ld = (int64_t)p.ntaps * p.C;
-            for (int q = 0; q < nslots; ++q) {
-                {
+            // segments of the chunk range = images (modulated mode) or the whole range
+            int seg = 0;
+            for (int kb0 = 0; kb0 < KB; ++seg) {
+                int kb1 = KB;
+                if (p.chunks_per_image > 0) {
+                    const int next = ((chunk_begin + kb0) / p.chunks_per_image + 1) * p.chunks_per_image - chunk_begin;
+                    if (next < kb1) kb1 = next;
+                }
+                const int img = p.chunks_per_image > 0 ? (chunk_begin + kb0) / p.chunks_per_image : 0;
+                mbar_wait(bar_acc, (uint32_t)seg & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int q = 0; q < nslots; ++q) {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(q * 32), v);
                     const int c = c0 + 32 * (q % p.cpt);
-                    if (o < p.Ko && c < p.C) {
-                        float* dst = dw + (int64_t)o * ld + (int64_t)(tap0 + q / p.cpt) * p.C + c;
+                    const bool in_range = o < p.Ko && c < p.C;
+                    const int64_t off = (int64_t)o * ld + (int64_t)(tap0 + q / p.cpt) * p.C + c;
+                    if (p.chunks_per_image > 0) {
+                        // ds[img, c + j] += sum over this warp's 32 filter rows of W * G; then the row's share of dW, scaled
+                        const float* sv = p.mod_s + (int64_t)img * p.C + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float t = in_range ? v[j] * __ldg(p.mod_w + off + j) : 0.f;
+                            t = warp_sum(t);
+                            if (lane == 0 && c < p.C) atomicAdd(p.mod_ds + (int64_t)img * p.C + c + j, t);
+                            v[j] *= (c < p.C) ? __ldg(sv + j) : 0.f;
+                        }
+                    }
+                    if (in_range) {
+                        float* dst = dw + off;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j]),
                                          "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
                         }
                     }
+                }
+                kb0 = kb1;
+                if (kb0 < KB) {
+                    // more segments follow: tell the MMA warp that the accumulators may be overwritten
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (warp == 2 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_drained) : "memory");
                 }
             }
         }
@@ -353,10 +401,30 @@ bool tc_wgrad_eligible(const sae_conv_geom* g) {
     return true;
 }
 
+bool tc_wgrad_modulated_eligible(const sae_conv_geom* g) {
+    // the shared-window configuration of wgrad_tc_kernel with whole 32-pixel chunks inside one image
+    return tc_wgrad_eligible(g) && g->stride == 1 && g->Q % 32 == 0 && g->C % 32 == 0 && g->C >= 64 && g->K % 32 == 0;
+}
+
+static int tc_wgrad_impl(const float* dy, const float* x, float* dw, const sae_conv_geom* g, cudaStream_t st, const float* mod_s,
+                         const float* mod_w, float* mod_ds);
+
 int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g, cudaStream_t st) {
+    return tc_wgrad_impl(dy, x, dw, g, st, nullptr, nullptr, nullptr);
+}
+
+int tc_wgrad_modulated(const float* dy, const float* x, const float* s, const float* w_krsc, float* dw, float* ds,
+                       const sae_conv_geom* g, cudaStream_t st) {
+    if (!tc_wgrad_modulated_eligible(g)) return fail(SAE_E_UNSUPPORTED, "modulated wgrad: shape outside the tcgen05 configuration");
+    return tc_wgrad_impl(dy, x, dw, g, st, s, w_krsc, ds);
+}
+
+static int tc_wgrad_impl(const float* dy, const float* x, float* dw, const sae_conv_geom* g, cudaStream_t st, const float* mod_s,
+                         const float* mod_w, float* mod_ds) {
     if (((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) != 0)
         return fail(SAE_E_INVALID, "conv2d_wgrad(tcgen05): pointers must be 16-byte aligned");
     WgParams p;
+    p.chunks_per_image = 0; p.mod_s = mod_s; p.mod_w = mod_w; p.mod_ds = mod_ds;
     p.tw = pow2_ceil(g->Q) < 32 ? pow2_ceil(g->Q) : 32;
     int th = 32 / p.tw;
     if (pow2_ceil(g->P) < th) th = pow2_ceil(g->P);
@@ -385,9 +453,10 @@ int tc_wgrad(const float* dy, const float* x, float* dw, const sae_conv_geom* g,
     p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
     splits = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
 
+    if (mod_s != nullptr) p.chunks_per_image = p.tiles_w * p.tiles_h;       // tn == 1 (Q % 32 == 0)
     static int narrow_mode = -1;
     if (narrow_mode < 0) { const char* v = getenv("SAE_WGRAD_NARROW"); narrow_mode = (v && v[0] == '0') ? 0 : 1; }
-    if (narrow_mode && g->C == 32 && g->stride == 1 && g->S == 3 && g->R <= 3 && p.tw == 32 && g->K <= 128) {
+    if (mod_s == nullptr && narrow_mode && g->C == 32 && g->stride == 1 && g->S == 3 && g->R <= 3 && p.tw == 32 && g->K <= 128) {
         // C == 32: x window as the A operand with pixel-shifted M-atoms (see wgrad_narrow_kernel)
         CUtensorMap mdy, mx;
         {

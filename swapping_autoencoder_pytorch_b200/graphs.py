@@ -37,9 +37,12 @@ class HalfStepGraphs:
         self.last_traceback = None
         self.replayed_launches = 0     # kernels of this library executed through graph replays (bench bookkeeping)
         self.enabled = True            # bench switches to eager for its per-launch instrumentation pass
-        # data parallel: capture pack -> NCCL all-reduce -> Adam into the graph as well (one replay = one whole half-step, no
-        # host involvement between backward and the update); falls back to an eager tail if the collective cannot be captured
-        self.nccl_in_graph = os.environ.get("SAE_GRAPH_NCCL", "1") != "0"
+        # data parallel, opt-in (SAE_GRAPH_NCCL=1): capture pack -> NCCL all-reduce -> Adam into the graph as well (one replay = one
+        # whole half-step); falls back to the eager tail if the collective cannot be captured.  Default off: with the lazy loss
+        # read-back the host already runs ahead, so the eager tail (3 launches + the collective) costs only its device time —
+        # measured on 2 B200s 711.0 images/s with the eager tail vs 705.9 with the captured one (profiles/r2_bench_n2_*.json) —
+        # and a process that holds captured NCCL kernels hung in destroy_process_group at exit in that run.
+        self.nccl_in_graph = os.environ.get("SAE_GRAPH_NCCL", "0") == "1"
         self.nccl_capture_error = None
 
     # ------------------------------------------------------------------
@@ -128,13 +131,22 @@ class HalfStepGraphs:
             self._tail(kind)
         return dict(outputs)
 
+    def release(self):
+        """drop every captured graph (call before tearing the process group down when collectives were captured)"""
+        torch.cuda.synchronize()
+        self.captured.clear()
+        self.pool = None
+        gc.collect()
+        torch.cuda.synchronize()
+
     def describe(self, world):
         """one-line account of what a replay contains (bench.py reports it)"""
         if world == 1:
             return "forward+backward+Adam per replay"
         if self.nccl_in_graph:
             return "forward+backward+bucket pack+NCCL all-reduce+Adam per replay"
-        return "forward+backward per replay; all-reduce and Adam eager (%s)" % (self.nccl_capture_error or "SAE_GRAPH_NCCL=0")
+        return "forward+backward per replay; bucket pack, NCCL all-reduce and Adam (reading the bucket) issued after it%s" % (
+            " (%s)" % self.nccl_capture_error if self.nccl_capture_error else "")
 
     def _select_group(self, kind):
         t = self.trainer

@@ -21,8 +21,8 @@ from torch.nn import functional as F
 
 from .stylegan2_op.blocks import FirSpec, ResBlockSpec, fir_noise_bias_act, fused_blocks_enabled, resblock
 from .stylegan2_op import (FusedLeakyReLU, add_scale, conv2d, conv2d_bias_act, conv2d_noise_bias_act, conv2d_residual,
-                           conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, memo, modulate, reflect_pad,
-                           torgb, upfirdn2d)
+                           conv_transpose2d, fused_leaky_relu, fused_noise_bias_leaky_relu, linear, memo, modulate,
+                           modulated_conv2d, modulated_conv_ok, reflect_pad, torgb, upfirdn2d)
 
 _SQRT2 = math.sqrt(2.0)
 
@@ -216,6 +216,21 @@ class ModulatedConv2d(nn.Module):
         # the filter does not depend on the style: built once per loss evaluation, shared by every call of the layer
         return memo(self.weight, "demod", build)
 
+    def style_scale(self, style, batch):
+        """the per-sample, per-input-channel scale s [N, Cin] of a non-spatial style (reference :278-283)"""
+        s = self.modulation(style.reshape(batch, -1))
+        if self.demodulate:
+            s = s * torch.rsqrt(s.square().mean(dim=1, keepdim=True) + 1e-8)
+        return s
+
+    def per_sample_geom(self, input, style):
+        """geometry object when the plain (no up / down sampling) convolution can run on per-sample filters (no modulated copy
+        of the input), else None"""
+        if self.upsample or self.downsample or style.dim() > 2 or not torch.is_floating_point(input):
+            return None
+        w = self.weight[0]
+        return modulated_conv_ok(input, w, self.padding)
+
     def modulated_input(self, input, style):
         """input * (RMS-normalised) style — reference :269-284"""
         batch = input.shape[0]
@@ -226,12 +241,12 @@ class ModulatedConv2d(nn.Module):
             if self.demodulate:
                 style = style * torch.rsqrt(style.square().mean(dim=1, keepdim=True) + 1e-8)
             return input * style
-        s = self.modulation(style.reshape(batch, -1))
-        if self.demodulate:
-            s = s * torch.rsqrt(s.square().mean(dim=1, keepdim=True) + 1e-8)
-        return modulate(input, s)
+        return modulate(input, self.style_scale(style, batch))
 
     def forward(self, input, style):
+        g = self.per_sample_geom(input, style)
+        if g is not None:
+            return modulated_conv2d(input, self.style_scale(style, input.shape[0]), self.filter(), g)
         input = self.modulated_input(input, style)
         w = self.filter()
         if self.upsample:
@@ -307,6 +322,16 @@ class StyledConv(nn.Module):
         conv, act = self.conv, self.activate
         gain = act.scale * out_scale
         if not (conv.upsample or conv.downsample):
+            g = conv.per_sample_geom(input, style)
+            if g is not None:
+                # style scale in the per-sample filters, noise + bias + activation in the epilogue: ONE kernel touches the
+                # activation (no modulated copy of it exists in either direction)
+                z = None
+                if self.use_noise:
+                    z = self.noise.resolve_noise(_ShapeOnly(torch.Size((input.shape[0], conv.out_channel, g.P, g.Q)), input), noise)
+                if z is None or (z.shape[0] == input.shape[0] and z.shape[1] == 1 and tuple(z.shape[2:]) == (g.P, g.Q)):
+                    return modulated_conv2d(input, conv.style_scale(style, input.shape[0]), conv.filter(), g, z, self.noise.weight,
+                                            act.bias, act.negative_slope, gain)
             # plain 3x3: noise + bias + activation ride in the conv kernel's epilogue
             x = conv.modulated_input(input, style)
             w = conv.filter()

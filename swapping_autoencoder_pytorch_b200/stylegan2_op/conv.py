@@ -413,6 +413,79 @@ def modulate(x, s):
     return _Modulate.apply(x, s)
 
 
+class _ModulatedConv(Function):
+    """ModulatedConv2d's core (stylegan2_layers.py:284-323) WITHOUT a modulated copy of the activation: the style scale goes into
+    per-sample filters W_n = W * s[n] that the tensor-core kernel selects per pixel tile (``sae_conv2d_fprop_per_sample``),
+    optionally with the StyledConv tail (noise + bias + leaky-ReLU) in the same kernel's epilogue.  Backward: the data gradient
+    with the transposed per-sample filters; the weight gradient takes x UNSCALED and forms  dW = sum_n s[n] G_n  and
+    ds[n] = <W, G_n>  while draining its accumulators once per image (``sae_conv2d_wgrad_modulated``).
+    Inputs: x [N,C,H,W], s [N,C] (already normalised), w [K,R,S,C] prepared (scaled, demodulated, rounded).
+    Generator only, hence once-differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, s, w, g, noise, noise_weight, bias, negative_slope, gain):
+        k = backend.kernels()
+        xh, sc = _nhwc(x), s.contiguous()
+        w_n, _ = k.filter_modulate(w.contiguous(), sc, want_krsc=True, want_crsk=False)
+        act = bias is not None
+        epi = {}
+        noise_flat = None
+        if act:
+            epi = dict(bias=bias.contiguous(), act=3, alpha=negative_slope, gain=gain)
+            if noise is not None:
+                noise_flat = noise.reshape(-1).contiguous()
+                epi.update(noise=noise_flat, noise_weight=noise_weight.contiguous())
+        out = k.conv_fprop_per_sample(xh, w_n, g, **epi)
+        ctx.g, ctx.cfg = g, (act, negative_slope, gain, tuple(noise.shape) if noise is not None else None)
+        ctx.save_for_backward(xh, sc, w, out if act else None, noise_flat, noise_weight if noise is not None else None)
+        return _nchw(out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xh, sc, w, out, noise_flat, noise_weight = ctx.saved_tensors
+        act, negative_slope, gain, noise_shape = ctx.cfg
+        k = backend.kernels()
+        gi, gb, gnw = _nhwc(dy), None, None
+        if act:
+            gi, gb, gnw = k.bias_act_backward(gi, out, negative_slope, gain, want_bias=True, noise=noise_flat)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, w_nt = k.filter_modulate(w.contiguous(), sc, want_krsc=False, want_crsk=True)
+            dx = _nchw(k.conv_dgrad_per_sample(gi, w_nt, ctx.g))
+        dw = ds = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, ds = k.conv_wgrad_modulated(gi, xh, sc, w.contiguous(), ctx.g)
+        g_noise = None
+        if noise_flat is not None and ctx.needs_input_grad[4]:
+            g_noise = (gi.sum(dim=3) * noise_weight).reshape(noise_shape)
+        return dx, ds, dw, None, g_noise, gnw, gb, None, None
+
+
+def modulated_conv_ok(input, weight, padding):
+    """does the per-sample-filter path take ``F.conv2d(input * s, weight, padding=padding)``?  Needs kernel support for the
+    geometry AND a filter set much smaller than the activation (N |W| written + read  vs  |x| read + written by a scaling pass)"""
+    n, c, h, w_ = input.shape
+    k, c2, r, s_ = weight.shape
+    if c != c2 or r != s_ or padding != r // 2 or c % 32 != 0 or k % 32 != 0:
+        return None
+    if 4 * k * r * s_ > h * w_:
+        return None
+    kern = backend.kernels()
+    if not hasattr(kern, "conv_modulated_ok"):
+        return None
+    g = make_geom(n, h, w_, c, k, r, s_, 1, padding, padding)
+    return g if kern.conv_modulated_ok(g) else None
+
+
+def modulated_conv2d(input, s, weight, g, noise=None, noise_weight=None, bias=None, negative_slope=0.2, scale=2 ** 0.5, wscale=1.0):
+    """``F.conv2d(input * s[:, :, None, None], weight * wscale, padding=k // 2)`` — optionally followed by
+    ``fused_leaky_relu(. + noise_weight * noise, bias, negative_slope, scale)`` — on per-sample filters; ``g`` from
+    ``modulated_conv_ok``"""
+    w, _ = prep_filter(weight, wscale)
+    return _ModulatedConv.apply(input, s, w, g, noise, noise_weight, bias, negative_slope, scale)
+
+
 class _ToRGB(Function):
     """bias + conv1x1(x * s, w * wscale) with 3 output channels as ONE pass over x (csrc/torgb.cu) — the generator's ToRGB
     (stylegan2_layers.py:408-427: ModulatedConv2d(in, 3, 1, demodulate=False) + bias).  Backward is one more pass over x:

@@ -218,3 +218,34 @@ class EmulatedKernels:
         px0, px1, py0, py1 = pad
         y = self.upfirdn2d(x, kernel, 1, 1, 1, 1, px0, px1, py0, py1)
         return self.bias_act(y, bias, None, 3, 0, alpha, scale, noise=noise, noise_weight=noise_weight)
+
+    # ------------------------------------------------ style-modulated conv, per-sample filters (include/sae_b200.h)
+    def conv_modulated_ok(self, g):
+        return g.stride == 1 and g.P % 16 == 0 and g.Q % 32 == 0 and g.C % 32 == 0 and g.K % 32 == 0 and g.R <= 3
+
+    def filter_modulate(self, w_krsc, s, want_krsc=True, want_crsk=False):
+        wn = w_krsc.unsqueeze(0) * s[:, None, None, None, :]
+        return (wn if want_krsc else None), (wn.permute(0, 4, 2, 3, 1).contiguous() if want_crsk else None)
+
+    def conv_fprop_per_sample(self, x, w_nkrsc, g, **epi):
+        outs = []
+        g1 = type(g)(1, *g.key()[1:])
+        for n in range(g.N):
+            e = dict(epi)
+            if e.get("noise") is not None:
+                e["noise"] = e["noise"].reshape(g.N, -1)[n]
+            if e.get("residual") is not None:
+                e["residual"] = e["residual"][n:n + 1]
+            outs.append(self.conv_fprop(x[n:n + 1], w_nkrsc[n], g1, **e))
+        return torch.cat(outs)
+
+    def conv_dgrad_per_sample(self, dy, w_ncrsk, g, **epi):
+        g1 = type(g)(1, *g.key()[1:])
+        return torch.cat([self.conv_dgrad(dy[n:n + 1], w_ncrsk[n].permute(3, 1, 2, 0).contiguous(), g1, **epi) for n in range(g.N)])
+
+    def conv_wgrad_modulated(self, dy, x, s, w_krsc, g):
+        g1 = type(g)(1, *g.key()[1:])
+        gn = torch.stack([self.conv_wgrad(dy[n:n + 1], x[n:n + 1], g1) for n in range(g.N)])       # [N,K,R,S,C]
+        dw = (gn * s[:, None, None, None, :]).sum(0)
+        ds = (gn * w_krsc.unsqueeze(0)).sum(dim=(1, 2, 3))
+        return dw, ds

@@ -77,6 +77,47 @@ class ShadowKernels:
                 self.log.append(("fir_act_backward", "g%s pad%s out%d" % (tuple(grad.shape), pad, i), _err(o, r)))
         return out
 
+    def fir_bias_act(self, x, taps, pad, bias, noise, noise_weight, alpha, scale):
+        out = self.real.fir_bias_act(x, taps, pad, bias, noise, noise_weight, alpha, scale)
+        if out is None:           # shape outside the fused kernel: the caller issues the two separate (shadowed) calls
+            return None
+        ref = self.emu.fir_bias_act(_cpu(x), taps, pad, _cpu(bias), _cpu(noise), _cpu(noise_weight), alpha, scale)
+        self.log.append(("fir_bias_act", "x%s pad%s noise%s" % (tuple(x.shape), pad, noise is not None), _err(out, ref)))
+        return out
+
+    def torgb_forward(self, x, s, w, bias, wscale):
+        return self._both("torgb_forward", "x%s" % (tuple(x.shape),), (x, s, w, bias, wscale), {})
+
+    def torgb_backward(self, dy, x, s, w, wscale, want_dx=True, want_gw=True):
+        return self._both("torgb_backward", "x%s" % (tuple(x.shape),), (dy, x, s, w, wscale), dict(want_dx=want_dx, want_gw=want_gw))
+
+    def crop_gather(self, x, flip, scale, offset, num_crops, size, c_pad, out=None):
+        res = self.real.crop_gather(x, flip, scale, offset, num_crops, size, c_pad, out=out)
+        ref = self.emu.crop_gather(_cpu(x), _cpu(flip), _cpu(scale), _cpu(offset), num_crops, size, c_pad)
+        self.log.append(("crop_gather", "x%s -> %d" % (tuple(x.shape), size), _err(res, ref)))
+        return res
+
+    def crop_gather_backward(self, dy, flip, scale, offset, num_crops, c, h, w):
+        return self._both("crop_gather_backward", "dy%s" % (tuple(dy.shape),), (dy, flip, scale, offset, num_crops, c, h, w), {})
+
+    def conv_modulated_ok(self, g):
+        return self.real.conv_modulated_ok(g)
+
+    def filter_modulate(self, w_krsc, s, want_krsc=True, want_crsk=False):
+        return self._both("filter_modulate", "w%s" % (tuple(w_krsc.shape),), (w_krsc, s), dict(want_krsc=want_krsc, want_crsk=want_crsk))
+
+    def conv_fprop_per_sample(self, x, w, g, **epi):
+        return self._both("conv_fprop_per_sample", "g%s epi%s" % (g.key(), sorted(epi)), (x, w, g), dict(epi))
+
+    def conv_dgrad_per_sample(self, dy, w, g, **epi):
+        return self._both("conv_dgrad_per_sample", "g%s" % (g.key(),), (dy, w, g), dict(epi))
+
+    def conv_wgrad_modulated(self, dy, x, s, w, g):
+        return self._both("conv_wgrad_modulated", "g%s" % (g.key(),), (dy, x, s, w, g), {})
+
+    def adam_step(self, *a, **kw):
+        return self.real.adam_step(*a, **kw)         # checked against torch.optim.Adam in tests/test_gpu_train_ops.py
+
     def modulate(self, x, s):
         return self._both("modulate", "x%s" % (tuple(x.shape),), (x, s), {})
 

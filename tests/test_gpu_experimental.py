@@ -1,8 +1,8 @@
 """GPU: alternative kernel selections, each run against the ordinary conv parity suite in a subprocess with the selecting
 switch set (the library reads its switches once per process).  The DEFAULT selection is covered by the main suite; this file
-keeps the alternatives honest: ``SAE_TC6=0`` (one-tile conv_tc2 kernels), ``SAE_TC6=1`` (persistent 128-column blocks),
-``SAE_DGRAD_MERGED=0`` (one launch per parity class) and ``SAE_DGRAD_MERGED=2`` (conv_tc7: all four classes per window).
-Opt-in (``SAE_TEST_EXPERIMENTAL=1``) because each case repeats a few minutes of tests."""
+keeps the alternatives honest: ``SAE_DGRAD_MERGED=0`` (stride-2 data gradient as one launch per parity class),
+``SAE_DISABLE_TCGEN05=1`` (every convolution on the generic mma.sync kernel), ``SAE_FUSED_BLOCKS=0`` (per-operator autograd
+nodes in the discriminators' ResBlocks).  Opt-in (``SAE_TEST_EXPERIMENTAL=1``) because each case repeats a few minutes of tests."""
 import os
 import subprocess
 import sys
@@ -14,7 +14,7 @@ pytestmark = [pytest.mark.gpu,
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{"SAE_TC6": "0"}, {"SAE_TC6": "1"}, {"SAE_DGRAD_MERGED": "0"}, {"SAE_DGRAD_MERGED": "2"}],
+@pytest.mark.parametrize("env", [{"SAE_DGRAD_MERGED": "0"}, {"SAE_DISABLE_TCGEN05": "1"}, {"SAE_FUSED_BLOCKS": "0"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_alternative_kernel_selection(env):
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q",

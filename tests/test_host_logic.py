@@ -388,3 +388,44 @@ def test_resblock_closed_form_double_backward_matches_autograd():
         blocks.set_fused_blocks(prev)
         k.conv_wgrad = orig
     assert not C.data_gradients_only_active()
+
+
+def test_modulated_conv_on_per_sample_filters_matches_scaled_input_path():
+    """ModulatedConv2d / StyledConv on per-sample filters (stylegan2_op/conv.py ``_ModulatedConv``: no modulated copy of the
+    activation; weight gradient from the unscaled input with a per-image drain) against the input-scaling formulation the
+    goldens pin — output and the gradients of input, style, filter, modulation weights, noise weight and bias"""
+    from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import conv as C
+    for use_noise in (True, False):
+        torch.manual_seed(0)
+        m = L.StyledConv(32, 32, 3, 16, use_noise=use_noise).double()
+        with torch.no_grad():
+            m.noise.weight.fill_(0.3)
+            m.activate.bias.normal_(0, 0.1)
+        x, st = rnd(1, 2, 32, 32, 64).requires_grad_(), rnd(2, 2, 16).requires_grad_()
+        nz = rnd(3, 2, 1, 32, 64) if use_noise else None
+        assert m.conv.per_sample_geom(x, st) is not None
+        params = [m.conv.weight, m.conv.modulation.weight, m.conv.modulation.bias, m.activate.bias] + ([m.noise.weight] if use_noise else [])
+        res = {}
+        saved = (C.modulated_conv_ok, L.modulated_conv_ok)
+        for mode in ("per_sample", "scaled_input"):
+            if mode == "scaled_input":
+                C.modulated_conv_ok = L.modulated_conv_ok = lambda *a: None
+            try:
+                y = m(x, st, noise=nz)
+                res[mode] = [y] + list(torch.autograd.grad((y * rnd(4, *y.shape)).sum(), [x, st] + params))
+            finally:
+                C.modulated_conv_ok, L.modulated_conv_ok = saved
+        for a, b in zip(res["per_sample"], res["scaled_input"]):
+            assert rel_err(a, b) < 1e-12
+    # the bare ModulatedConv2d (no activation tail) takes the same path
+    mc = L.ModulatedConv2d(32, 32, 3, 16).double()
+    x, st = rnd(5, 2, 32, 32, 64).requires_grad_(), rnd(6, 2, 16).requires_grad_()
+    y = mc(x, st)
+    saved = (C.modulated_conv_ok, L.modulated_conv_ok)
+    C.modulated_conv_ok = L.modulated_conv_ok = lambda *a: None
+    try:
+        y2 = mc(x, st)
+    finally:
+        C.modulated_conv_ok, L.modulated_conv_ok = saved
+    assert rel_err(y, y2) < 1e-12
