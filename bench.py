@@ -318,6 +318,8 @@ def run_ours(args, rank, world, local):
         if sampler:
             sampler.start()
         n0 = _lib.launch_count() + (trainer.graphs.replayed_launches if trainer.graphs else 0)
+        if trainer.graphs is not None:
+            trainer.graphs.phase_events = []
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         kinds = []
         ev[0].record()
@@ -332,11 +334,20 @@ def run_ours(args, rank, world, local):
             per_kind.setdefault(kd, []).append(ev[i].elapsed_time(ev[i + 1]))
         launches = _lib.launch_count() + (trainer.graphs.replayed_launches if trainer.graphs else 0) - n0
         clocks = sampler.stop() if sampler else None
+        # per-phase device time of the replayed half-steps on this rank: graph replay (forward + backward [+ Adam at N = 1]),
+        # then bucket pack + all-reduce + Adam (N > 1); "gap" = what is left of the step (input copy, host gaps, waiting for peers)
+        phases = None
+        if trainer.graphs is not None and trainer.graphs.phase_events:
+            pe, trainer.graphs.phase_events = trainer.graphs.phase_events, None
+            rep = sum(e[0].elapsed_time(e[1]) for _, e in pe) / len(pe)
+            tail = sum(e[1].elapsed_time(e[2]) for _, e in pe) / len(pe)
+            phases = {"graph_replay_ms": rep, "exchange_and_adam_ms": tail, "gap_ms": ms / args.steps - (rep + tail) * len(pe) / args.steps,
+                      "replays": len(pe)}
         if world > 1:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return {"ms": ms, "launches": launches, "clocks": clocks, "r1": kinds.count("D+R1"),
+        return {"ms": ms, "launches": launches, "clocks": clocks, "r1": kinds.count("D+R1"), "phases": phases,
                 "per_kind_ms": {kd: sum(v) / len(v) for kd, v in per_kind.items()}}
 
     def warm(resident):
@@ -493,6 +504,7 @@ def run_ours(args, rank, world, local):
         "e2e": {"value": images / (e2e["ms"] * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": loss_bytes},
         "gpu_launches": int(dev["launches"]),
+        "phases_rank0": dev["phases"],
         "roofline": roofline,
         "roofline_hbm": roofline_hbm,
     }

@@ -73,6 +73,8 @@ struct TcParams {
     unsigned short arow[TC_MAX_TAPS];   // first window row of tap t: (oy_t - oy_min) * ww + (ox_t - ox_min)
     int w_nstride;                      // shared-window kernel: filter rows between consecutive images (0 = one filter for the
                                         // batch; Ncol = per-sample filters [N, Ncol, Ktot], the style-modulated convolution)
+    int b_resident;                     // shared-window kernel: the whole filter slice of this CTA's column block (ntaps x
+                                        // num_cblk tiles) fits the B ring and is loaded ONCE per CTA instead of once per pixel tile
     EpiParams epi;
 };
 
@@ -272,7 +274,8 @@ constexpr int TC3_ASLOT = 23 * 1024;                // >= 18 * 10 * 128 B, multi
 // Timing experiments on 128 -> 128 at 256^2 x 32 (profiles/r2_tc5_time_split.txt): whole kernel 0.794 ms; without the output
 // stores 0.691; loads + epilogue without any MMA 0.492; the MMAs alone need >= 0.64 ms at the 1.6 GHz the SMs hold under this
 // load — the kernel sits at ~80 % of the tensor-pipe bound, the rest is imperfect overlap of the three engines.
-template <int BLOCK_N> constexpr int tc5_nb() { return BLOCK_N >= 128 ? 4 : 8; }     // B ring: 32 KB at N = 128 / 64, 16 KB at 32
+template <int BLOCK_N> constexpr int tc5_nb() { return BLOCK_N >= 128 ? 4 : (BLOCK_N >= 64 ? 8 : 12); }   // B ring: 32 KB at N = 128 / 64, 24 KB at 32
+                                                                     // (12 x 2 KB: a whole 3x3 x 32-channel filter slice, see b_resident)
 constexpr int TC5_NSTG = 2;                          // dedicated 16 KB output staging buffers
 // Template parameters beyond the column-block width: NACC accumulator buffers in TMEM, NA window slots, NB filter-tile slots,
 // CTAS resident CTAs per SM.  Instantiated as <N, 2, 2, tc5_nb<N>(), 2>.  (Measured and dropped, round 2: one CTA per SM
@@ -351,6 +354,18 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         // ===================================================== TMA producer (both CTAs)
         if (elect_one()) {
             int ia = 0, ib = 0, it = 0;
+            if (p.b_resident && cluster_id < total_work) {
+                // narrow layers / 1x1 convs: the filter slice of this CTA's column block is small enough to live in the B ring for
+                // the whole kernel (the launcher makes every work item of a cluster use the same column block): ONE barrier,
+                // ntaps x num_cblk tile loads, then per pixel tile only the activation window travels
+                int q0, p0, n0, col0;
+                decode(cluster_id, q0, p0, n0, col0);
+                if (leader) mbar_expect_tx(bar_fullB, 2u * (uint32_t)(p.ntaps * p.num_cblk) * B_HALF_BYTES);
+                for (int cb = 0; cb < p.num_cblk; ++cb)
+                    for (int t = 0; t < p.ntaps; ++t)
+                        tma2_load_2d(base + (uint32_t)(cb * p.ntaps + t) * B_HALF_BYTES, &map_w, bar_fullB, p.wk[t] + cb * TC_BK,
+                                     col0 + (int)rank * (BLOCK_N / 2));
+            }
             for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
                 int q0, p0, n0, col0;
                 decode(work, q0, p0, n0, col0);
@@ -360,6 +375,7 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
                     mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC3_NA)) & 1u) ^ 1u);
                     if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
                     tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
+                    if (p.b_resident) continue;
                     for (int t = 0; t < p.ntaps; ++t, ++ib) {
                         const int sb = ib % TC3_NB;
                         mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
@@ -377,6 +393,7 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         if (leader && elect_one()) {
             const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;        // 8-row atoms are one window row apart
             int ia = 0, ib = 0, it = 0;
+            if (p.b_resident && cluster_id < total_work) mbar_wait(bar_fullB, 0);        // the resident filter slice has landed
             for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
             // accumulator buffer it % NACC: both CTAs' epilogues must have drained its previous tile (it - NACC)
             const uint32_t buf = (uint32_t)(it % NACC);
@@ -388,8 +405,8 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
                 mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC3_NA)) & 1u);
                 const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
                 for (int t = 0; t < p.ntaps; ++t, ++ib, ++tstep) {
-                    const int sb = ib % TC3_NB;
-                    mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
+                    const int sb = p.b_resident ? cb * p.ntaps + t : ib % TC3_NB;
+                    if (!p.b_resident) mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     // A descriptor: start = window row arow[t]; same 128B-swizzle K-major layout, SBO = ww * 128 B
                     const uint32_t aaddr = a0 + (uint32_t)p.arow[t] * 128u;
@@ -398,7 +415,7 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k)
                         umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (tstep > 0 || k > 0) ? 1u : 0u);
-                    umma2_commit(bar_emptyB + 8 * sb);
+                    if (!p.b_resident) umma2_commit(bar_emptyB + 8 * sb);
                 }
                 umma2_commit(bar_emptyA + 8 * sa);
             }
@@ -876,6 +893,7 @@ static void tc_fill_params(const TcProblem& pr, const EpiParams& e, TcParams& p)
     for (int t = 0; t < pr.ntaps; ++t) { p.oy[t] = (short)pr.oy[t]; p.ox[t] = (short)pr.ox[t]; p.wk[t] = pr.wk[t]; }
     p.o_mul = pr.o_mul; p.o_offy = pr.o_offy; p.o_offx = pr.o_offx; p.FH = pr.FH; p.FW = pr.FW;
     p.w_nstride = pr.w_per_sample ? pr.Ncol : 0;
+    p.b_resident = 0;
     p.epi = e;
 }
 
@@ -1002,6 +1020,14 @@ static int tc5_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
     const int total_work = ((tiles + 1) / 2) * n_blocks;
     int clusters = sm_count() * CTAS / 2;            // CTAS CTAs per SM, 2 CTAs per cluster
     if (clusters > total_work) clusters = total_work;
+    // resident filter slice: it must fit the B ring, be shared by the batch, and every work item of a cluster must use the same
+    // column block (work = cluster + i * clusters, column block = work % n_blocks)
+    static int resident = -1;
+    if (resident < 0) { const char* v = getenv("SAE_TC_RESIDENT_B"); resident = (v && v[0] == '0') ? 0 : 1; }
+    // (measured, profiles/r2_resident_b.txt: +5 .. +13 % on the 32-channel 3x3 layers, -4 .. -9 % on 1x1 convs, whose single
+    // filter tile per channel block was never the bottleneck — hence ntaps > 1)
+    if (resident && !pr.w_per_sample && pr.ntaps > 1 && pr.ntaps * p.num_cblk <= NB && clusters % n_blocks == 0 && total_work >= 4 * clusters)
+        p.b_resident = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);

@@ -44,23 +44,40 @@ torgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ s, const
         }
         const float* xn = x + (int64_t)n * HW * C;
         float* yn = y + (int64_t)n * HW * 4;
-        for (int64_t p = p_begin; p < p_end; ++p) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        // four pixels per trip: their loads are issued back to back before any of them is consumed
+        constexpr int UP = 4;
+        for (int64_t p0 = p_begin; p0 < p_end; p0 += UP) {
+            float4 v[UP][NJ];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int c = 4 * lane + 128 * j;
-                if (c < C) {
-                    const float4 v = ldg_stream(reinterpret_cast<const float4*>(xn + p * C + c));
-                    a0 += v.x * wc[j][0][0] + v.y * wc[j][0][1] + v.z * wc[j][0][2] + v.w * wc[j][0][3];
-                    a1 += v.x * wc[j][1][0] + v.y * wc[j][1][1] + v.z * wc[j][1][2] + v.w * wc[j][1][3];
-                    a2 += v.x * wc[j][2][0] + v.y * wc[j][2][1] + v.z * wc[j][2][2] + v.w * wc[j][2][3];
+            for (int u = 0; u < UP; ++u)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int c = 4 * lane + 128 * j;
+                    v[u][j] = (c < C && p0 + u < p_end) ? __ldg(reinterpret_cast<const float4*>(xn + (p0 + u) * C + c))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            float a[UP][3];
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                a[u][0] = a[u][1] = a[u][2] = 0.f;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                    for (int o = 0; o < 3; ++o)
+                        a[u][o] += v[u][j].x * wc[j][o][0] + v[u][j].y * wc[j][o][1] + v[u][j].z * wc[j][o][2] + v[u][j].w * wc[j][o][3];
             }
-            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-            if (lane == 0) {
-                a0 += b0; a1 += b1; a2 += b2;
-                if (round_tf32) { a0 = rna_tf32(a0); a1 = rna_tf32(a1); a2 = rna_tf32(a2); }
-                *reinterpret_cast<float4*>(yn + p * 4) = make_float4(a0, a1, a2, 0.f);
+#pragma unroll
+            for (int u = 0; u < UP; ++u)
+#pragma unroll
+                for (int o = 0; o < 3; ++o) a[u][o] = warp_sum(a[u][o]);
+            // lane u stores pixel p0 + u
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                if (lane == u && p0 + u < p_end) {
+                    float r0 = a[u][0] + b0, r1 = a[u][1] + b1, r2 = a[u][2] + b2;
+                    if (round_tf32) { r0 = rna_tf32(r0); r1 = rna_tf32(r1); r2 = rna_tf32(r2); }
+                    *reinterpret_cast<float4*>(yn + (p0 + u) * 4) = make_float4(r0, r1, r2, 0.f);
+                }
             }
         }
     }

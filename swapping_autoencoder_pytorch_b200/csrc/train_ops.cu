@@ -85,18 +85,20 @@ __device__ __forceinline__ float crop_lin(int k, int S) {
 
 __global__ void __launch_bounds__(256)
 crop_gather_kernel(const float* __restrict__ x, float* __restrict__ out, const CropParams p) {
-    // one thread per 16-byte slot of the output (CP / 4 slots per pixel): consecutive lanes write consecutive slots, so a
-    // warp's store covers 512 contiguous bytes; only slot 0 of a pixel (channels 0..3) carries data, the others are the pad
-    const int slots = p.CP / 4;
-    const int64_t total = (int64_t)p.Q * p.S * p.S * slots;
-    for (int64_t sidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; sidx < total; sidx += (int64_t)gridDim.x * blockDim.x) {
-        const int slot = (int)(sidx % slots);
-        const int64_t idx = sidx / slots;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (slot == 0) {
-            const int j = (int)(idx % p.S);
-            const int i = (int)((idx / p.S) % p.S);
-            const int q = (int)(idx / ((int64_t)p.S * p.S));
+    // A warp owns 32 consecutive output pixels.  Phase 1: lane l resamples pixel base + l (all lanes busy, 32-bit index
+    // arithmetic — the launcher checks the extent).  Phase 2: the warp writes those 32 pixels' 128-byte rows cooperatively,
+    // 4 pixels x 8 sixteen-byte slots per store instruction (512 contiguous bytes); slot 0 carries the three channels
+    // (fetched from the owning lane with shuffles), slots 1..7 are the zero pad.  CP == 32 here.
+    const uint32_t pixels = (uint32_t)p.Q * (uint32_t)p.S * (uint32_t)p.S;
+    const uint32_t SS = (uint32_t)p.S * (uint32_t)p.S;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp_global * 32; base < pixels; base += warps_total * 32) {
+        const uint32_t idx = base + lane;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (idx < pixels) {
+            const uint32_t q = idx / SS, rem = idx - q * SS;
+            const int i = (int)(rem / (uint32_t)p.S), j = (int)(rem - (uint32_t)i * (uint32_t)p.S);
             const float gx = (crop_lin(j, p.S) * __ldg(p.flip + q)) * __ldg(p.scale + 2 * q) + __ldg(p.offset + 2 * q);
             const float gy = crop_lin(i, p.S) * __ldg(p.scale + 2 * q + 1) + __ldg(p.offset + 2 * q + 1);
             const float ix = ((gx + 1.f) * (float)p.W - 1.f) * 0.5f;
@@ -107,21 +109,31 @@ crop_gather_kernel(const float* __restrict__ x, float* __restrict__ out, const C
             const float w00 = (1.f - tx) * (1.f - ty), w01 = tx * (1.f - ty), w10 = (1.f - tx) * ty, w11 = tx * ty;
             const bool vx0 = x0 >= 0 && x0 < p.W, vx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
             const bool vy0 = y0 >= 0 && y0 < p.H, vy1 = y0 + 1 >= 0 && y0 + 1 < p.H;
-            const float* src = x + (int64_t)(q / p.num_crops) * p.xs_n;
+            const float* src = x + (int64_t)(q / (uint32_t)p.num_crops) * p.xs_n;
+            const int64_t o00 = (int64_t)y0 * p.xs_h + (int64_t)x0 * p.xs_w;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if (c < p.C) {
-                    const float* sc = src + (int64_t)c * p.xs_c;
+                    const float* sc = src + (int64_t)c * p.xs_c + o00;
                     float acc = 0.f;
-                    if (vy0 && vx0) acc += w00 * __ldg(sc + (int64_t)y0 * p.xs_h + (int64_t)x0 * p.xs_w);
-                    if (vy0 && vx1) acc += w01 * __ldg(sc + (int64_t)y0 * p.xs_h + (int64_t)(x0 + 1) * p.xs_w);
-                    if (vy1 && vx0) acc += w10 * __ldg(sc + (int64_t)(y0 + 1) * p.xs_h + (int64_t)x0 * p.xs_w);
-                    if (vy1 && vx1) acc += w11 * __ldg(sc + (int64_t)(y0 + 1) * p.xs_h + (int64_t)(x0 + 1) * p.xs_w);
-                    v[c] = p.round_tf32 ? rna_tf32(acc) : acc;
+                    if (vy0 && vx0) acc += w00 * __ldg(sc);
+                    if (vy0 && vx1) acc += w01 * __ldg(sc + p.xs_w);
+                    if (vy1 && vx0) acc += w10 * __ldg(sc + p.xs_h);
+                    if (vy1 && vx1) acc += w11 * __ldg(sc + p.xs_h + p.xs_w);
+                    a[c] = p.round_tf32 ? rna_tf32(acc) : acc;
                 }
             }
         }
-        reinterpret_cast<float4*>(out)[sidx] = make_float4(v[0], v[1], v[2], v[3]);
+        const uint32_t slots = (uint32_t)p.CP / 4;                 // 8
+        float4* dst = reinterpret_cast<float4*>(out) + (size_t)base * slots;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t owner = 4 * k + (lane >> 3), slot = lane & 7;
+            const float r0 = __shfl_sync(0xffffffffu, a[0], owner), r1 = __shfl_sync(0xffffffffu, a[1], owner);
+            const float r2 = __shfl_sync(0xffffffffu, a[2], owner), r3 = __shfl_sync(0xffffffffu, a[3], owner);
+            if (base + owner < pixels)
+                dst[owner * slots + slot] = slot == 0 ? make_float4(r0, r1, r2, r3) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -237,8 +249,10 @@ extern "C" int sae_crop_gather(const float* x, const float* flip, const float* s
     int rc = crop_params(p, flip, scale, offset, Q, num_crops, C, H, W, S, CP, "crop_gather");
     if (rc) return rc;
     if (!x || !out || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SAE_E_INVALID, "crop_gather: null / unaligned pointer");
+    if ((int64_t)Q * S * S * (CP / 4) >= ((int64_t)1 << 32)) return fail(SAE_E_UNSUPPORTED, "crop_gather: more than 2^32 output slots");
+    if (CP != 32) return fail(SAE_E_UNSUPPORTED, "crop_gather: the padded width must be 32 channels (one 128-byte row per pixel)");
     p.xs_n = xs_n; p.xs_c = xs_c; p.xs_h = xs_h; p.xs_w = xs_w; p.round_tf32 = round_tf32;
-    crop_gather_kernel<<<grid_1d((int64_t)Q * S * S * (CP / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(x, out, p);
+    crop_gather_kernel<<<grid_1d((int64_t)Q * S * S, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, out, p);
     return check_launch("crop_gather");
 }
 

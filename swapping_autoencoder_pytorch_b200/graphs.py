@@ -44,6 +44,8 @@ class HalfStepGraphs:
         # and a process that holds captured NCCL kernels hung in destroy_process_group at exit in that run.
         self.nccl_in_graph = os.environ.get("SAE_GRAPH_NCCL", "0") == "1"
         self.nccl_capture_error = None
+        # bench.py sets this to a list to get (start, replay done, exchange + Adam done) CUDA events of every replayed half-step
+        self.phase_events = None
 
     # ------------------------------------------------------------------
     def _wrapper(self):
@@ -125,10 +127,19 @@ class HalfStepGraphs:
             p.grad = g
         with torch.no_grad():            # the R1 body marks its input as requiring grad
             static_in.copy_(images, non_blocking=True)
+        ev = None
+        if self.phase_events is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         graph.replay()
         self.replayed_launches += launches
+        if ev is not None:
+            ev[1].record()
         if self._world() > 1 and not tail_captured:
             self._tail(kind)
+        if ev is not None:
+            ev[2].record()
+            self.phase_events.append((kind, ev))
         return dict(outputs)
 
     def release(self):

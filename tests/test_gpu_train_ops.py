@@ -272,28 +272,51 @@ def test_fir_bias_act_fused(kh, c, h, pad, with_noise, exact_fp32):
 
 @pytest.mark.parametrize("n,cin,cout,h,w", [(2, 128, 128, 128, 128), (3, 64, 128, 64, 128), (4, 256, 256, 128, 128), (2, 64, 64, 64, 64)])
 def test_modulated_conv_per_sample_filters(n, cin, cout, h, w):
-    """sae_filter_modulate + sae_conv2d_fprop_per_sample / dgrad_per_sample / wgrad_modulated through StyledConv: output and
-    every gradient against the oracle's styled_conv in fp64 (TF32 tensor-core tolerance, default rounding mode).  Batch sizes
-    and maps chosen so that weight-gradient CTAs cross image boundaries (several accumulator drains per CTA)."""
+    """sae_filter_modulate + sae_conv2d_fprop_per_sample / dgrad_per_sample / wgrad_modulated.  (1) ModulatedConv2d alone — a
+    bilinear map, so every gradient is held to the per-op TF32 tolerance against the oracle in fp64: output, dx, dstyle, dweight,
+    d(modulation weights).  Batch sizes and maps are chosen so that weight-gradient CTAs cross image boundaries (several
+    accumulator drains per CTA).  (2) Through StyledConv (noise + bias + leaky-ReLU in the same kernel's epilogue): output at
+    1e-3; gradients in relative L2 only — a TF32-level difference in a pre-activation near zero flips that element's mask."""
     from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
     P = {"conv.weight": rnd(1, 1, cout, cin, 3, 3), "conv.modulation.weight": rnd(2, cin, 16), "conv.modulation.bias": rnd(3, cin) * 0.1 + 1,
          "noise.weight": torch.tensor([0.3], dtype=torch.float64), "activate.bias": rnd(4, cout) * 0.1}
+    x, st, nz = rnd(5, n, cin, h, w), rnd(6, n, 16), rnd(7, n, 1, h, w)
+    # (1) bare modulated convolution
+    mc = L.ModulatedConv2d(cin, cout, 3, 16)
+    sd = mc.state_dict()
+    sd.update({k[len("conv."):]: v.float() for k, v in P.items() if k.startswith("conv.")})
+    mc.load_state_dict(sd)
+    mc = mc.to(DEV)
+    xg, sg = x.float().to(DEV).requires_grad_(), st.float().to(DEV).requires_grad_()
+    assert mc.per_sample_geom(xg, sg) is not None, "shape should take the per-sample-filter path"
+    Pr = {k: v.clone().requires_grad_() for k, v in P.items()}
+    xr, sr = x.clone().requires_grad_(), st.clone().requires_grad_()
+    y_ref = O.modulated_conv2d({"t." + k: v for k, v in Pr.items()}, "t.conv", xr, sr, 3)
+    wgt = rnd(8, *y_ref.shape)
+    ref = torch.autograd.grad((y_ref * wgt).sum(), [xr, sr, Pr["conv.weight"], Pr["conv.modulation.weight"]])
+    y = mc(xg, sg)
+    got = torch.autograd.grad((y * wgt.float().to(DEV)).sum(), [xg, sg, mc.weight, mc.modulation.weight])
+    assert rel_err(y, y_ref) < 1e-3, rel_err(y, y_ref)
+    for name, a, b, tol in zip(("x", "style", "weight", "modulation"), got, ref, (2e-3, 3e-3, 2e-3, 3e-3)):
+        assert rel_err(a, b) < tol, (name, rel_err(a, b), rel_l2(a, b))
+    # (2) with the StyledConv tail in the epilogue
     m = L.StyledConv(cin, cout, 3, 16)
     sd = m.state_dict()
     sd.update({k: v.float() for k, v in P.items()})
     m.load_state_dict(sd)
     m = m.to(DEV)
-    x, st, nz = rnd(5, n, cin, h, w), rnd(6, n, 16), rnd(7, n, 1, h, w)
-    xg, sg = x.float().to(DEV).requires_grad_(), st.float().to(DEV).requires_grad_()
-    assert m.conv.per_sample_geom(xg, sg) is not None, "shape should take the per-sample-filter path"
     Pr = {k: v.clone().requires_grad_() for k, v in P.items()}
     xr, sr = x.clone().requires_grad_(), st.clone().requires_grad_()
     y_ref = O.styled_conv({"t." + k: v for k, v in Pr.items()}, "t", xr, sr, noise=nz)
-    wgt = rnd(8, *y_ref.shape)
     names = ["conv.weight", "conv.modulation.weight", "noise.weight", "activate.bias"]
     ref = torch.autograd.grad((y_ref * wgt).sum(), [xr, sr] + [Pr[k] for k in names])
+    xg, sg = x.float().to(DEV).requires_grad_(), st.float().to(DEV).requires_grad_()
     y = m(xg, sg, noise=nz.float().to(DEV))
     got = torch.autograd.grad((y * wgt.float().to(DEV)).sum(), [xg, sg, m.conv.weight, m.conv.modulation.weight, m.noise.weight, m.activate.bias])
     assert rel_err(y, y_ref) < 1e-3, rel_err(y, y_ref)
     for name, a, b in zip(["x", "style"] + names, got, ref):
-        assert rel_l2(a, b) < 2e-3 and rel_err(a, b) < 1e-2, (name, rel_l2(a, b), rel_err(a, b))
+        if name == "noise.weight":
+            # one scalar = a sum of n*h*w*cout signed terms of unit size: judged against that sum's natural scale
+            assert abs(float(a) - float(b)) < 5e-2 * (y_ref.numel() ** 0.5), (name, float(a), float(b))
+            continue
+        assert rel_l2(a, b) < 2e-2, (name, rel_l2(a, b), rel_err(a, b))
