@@ -19,6 +19,8 @@ SHAPES = [
     ("D 512->512 @32 s1", 32, 512, 512, 3, 1, 1, 1.0),
     ("D 128->256 @257 s2", 257, 128, 256, 3, 2, 0, 1.0),
     ("D 256->512 @129 s2", 129, 256, 512, 3, 2, 0, 1.0),
+    ("D 512->512 @65 s2", 65, 512, 512, 3, 2, 0, 1.0),
+    ("(no strips) 128->256 @256 s2", 256, 128, 256, 3, 2, 0, 1.0),
     ("D skip 128->256 @255 1x1 s2", 255, 128, 256, 1, 2, 0, 1.0),
     ("G skip 512->256 @64 1x1", 64, 512, 256, 1, 1, 0, 1.0),
     ("G convT 256->128 @128 (as dgrad of s2)", 257, 128, 256, 3, 2, 0, 1.0),

@@ -478,37 +478,59 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------ conv_tc5 over the parity classes of a stride-2 data gradient
 // The stride-2 data gradient (and the generator's transposed convolution) is four dense stride-1 problems — the parity classes
-// of the output — over the SAME input.  conv_tc5m_kernel is conv_tc5_kernel whose work items carry a class index: each class
-// has its own tap list, output sub-grid offset and output tensor map; the input window is the union window of all taps.
-// One launch instead of four (plus strips), and the input tile of a pixel block travels from HBM once instead of four times.
+// of the output — over the SAME input.  conv_tc5m_kernel is conv_tc5_kernel whose work items carry a GROUP of ACCS classes:
+// one input window per channel block (the union window of all taps) feeds the taps of every class of the group, each class
+// accumulating into its own 128-column TMEM accumulator; each class has its own tap list, output sub-grid offset and output
+// tensor map.
+//   ACCS = 1, two CTAs per SM: four work items per pixel tile, one per class (1-, 2-, 2- and 4-tap K loops for a 3x3 filter).
+//   ACCS = 2, one CTA per SM owning all 512 TMEM columns (2 buffers x 2 accumulators): two work items per pixel tile, the
+//     4-tap class paired with the 1-tap class and the two 2-tap classes together — 5 and 4 taps per window load instead of
+//     4 / 2 / 2 / 1.  L2 -> SM bytes per MMA clock: (4 x 19.6 KB windows + 9 x 8 KB filter tiles) per 9 taps and two CTAs per SM
+//     = 130 B/clk/SM at ACCS = 1, (2 x 19.6 + 72) KB per 9 taps = 48 B/clk/SM at ACCS = 2.
 // (A variant keeping all four class accumulators in TMEM per window, 4 x 64 columns at one CTA per SM, was measured in
-// round 2 and dropped: 333 vs 416 TFLOP/s, profiles/r2_prof_s2_dgrad_tc7.txt.)
+// round 2 and dropped: 64-column MMAs are shared-memory bound; 333 vs 416 TFLOP/s, profiles/r2_prof_s2_dgrad_tc7.txt.)
 constexpr int TC_MAX_CLS = 4;
+constexpr int TC_GRP_TAPS = 8;
 struct TcOutMaps { CUtensorMap m[TC_MAX_CLS]; };
-struct TcClasses {
-    int ncls;
-    int ntaps[TC_MAX_CLS];
-    int wk[TC_MAX_CLS][4];
+struct TcGroups {
+    int ngrp;                                   // work items per pixel-tile pair and column block
+    int ntaps[TC_MAX_CLS];                      // taps of group g (all classes of the group)
+    int wk[TC_MAX_CLS][TC_GRP_TAPS];            // K offset of the tap's filter slice
+    unsigned short arow[TC_MAX_CLS][TC_GRP_TAPS];   // first window row of the tap
+    unsigned char acc[TC_MAX_CLS][TC_GRP_TAPS];     // accumulator of the group the tap adds into
+    unsigned char first[TC_MAX_CLS][TC_GRP_TAPS];   // 1: the tap opens its accumulator (overwrites instead of accumulating)
+    int cls[TC_MAX_CLS][2];                     // class (output map, sub-grid offset) behind accumulator a of group g
     int o_offy[TC_MAX_CLS], o_offx[TC_MAX_CLS];
-    unsigned short arow[TC_MAX_CLS][4];
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int ACCS> constexpr int tc5m_na() { return ACCS == 1 ? 2 : 3; }
+template <int ACCS> constexpr int tc5m_nb() { return ACCS == 1 ? 4 : 8; }
+template <int ACCS> constexpr int tc5m_nstg() { return ACCS == 1 ? 2 : 4; }
+template <int ACCS>
+constexpr size_t tc5m_smem_bytes() {
+    return (size_t)tc5m_nb<ACCS>() * 64 * 128 + (size_t)tc5m_na<ACCS>() * TC3_ASLOT + (size_t)tc5m_nstg<ACCS>() * TC_A_BYTES + 1024 +
+           8 * (size_t)(2 * tc5m_na<ACCS>() + 2 * tc5m_nb<ACCS>() + 4) + 64;
+}
+
+template <int ACCS>
+__global__ void __launch_bounds__(TC_THREADS, ACCS == 1 ? 2 : 1)
 conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ TcOutMaps outs, const TcParams p, const __grid_constant__ TcClasses cls, const int n_blocks,
+                 const __grid_constant__ TcOutMaps outs, const TcParams p, const __grid_constant__ TcGroups grp, const int n_blocks,
                  const int total_work) {
+    constexpr int BLOCK_N = 128;
     constexpr int B_HALF_BYTES = (BLOCK_N / 2) * 128;
-    constexpr int TC3_NB = tc5_nb<BLOCK_N>();
+    constexpr int TC3_NB = tc5m_nb<ACCS>();
+    constexpr int TC3_NA = tc5m_na<ACCS>();
+    constexpr int NSTG = tc5m_nstg<ACCS>();
     constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
     constexpr uint32_t RING0 = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
     constexpr uint32_t STG_OFF = RING0;                                  // staging follows the rings (1024-byte aligned)
-    constexpr uint32_t RING = RING0 + (uint32_t)TC5_NSTG * TC_A_BYTES;
-    constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t RING = RING0 + (uint32_t)NSTG * TC_A_BYTES;
+    constexpr uint32_t ACC_COLS = (uint32_t)(ACCS * BLOCK_N);            // one accumulator buffer = ACCS class accumulators
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                         // two accumulator buffers
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
     constexpr int NCHUNK = BLOCK_N / 32;
-    static_assert(BLOCK_N <= 128 && (B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc5: layout");
+    static_assert(TMEM_COLS <= 512 && (B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc5m: layout");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -526,16 +548,18 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
+    // contiguous share of the work items per cluster: the groups of one pixel tile differ in their tap counts, a strided
+    // assignment would hand some clusters only the long ones; and consecutive items re-read the same window from L2
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int work_begin = (int)(((int64_t)cluster_id * total_work) / num_clusters);
+    const int work_end = (int)(((int64_t)(cluster_id + 1) * total_work) / num_clusters);
     const uint32_t a_bytes = (uint32_t)(p.ww * p.wh) * 128u;
-    // work item -> (pixel tile of this CTA, parity class, channel block); channel block fastest, then the class: the
-    // classes of one pixel tile run on neighbouring clusters at the same time, so only the first of them reads the tile's
-    // input window from HBM — the others find it in L2
-    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0, int& c) {
+    // work item -> (pixel tile of this CTA, class group, channel block); channel block fastest, then the group
+    auto decode = [&](int work, int& q0, int& p0, int& n0, int& col0, int& g) {
         const int nblk = work % n_blocks;
         const int rest = work / n_blocks;
-        c = rest % cls.ncls;
-        int tile = (rest / cls.ncls) * 2 + (int)rank;
+        g = rest % grp.ngrp;
+        int tile = (rest / grp.ngrp) * 2 + (int)rank;
         const int tq = tile % p.tiles_w; tile /= p.tiles_w;
         const int tp = tile % p.tiles_h; tile /= p.tiles_h;
         q0 = tq * p.tw; p0 = tp * p.th; n0 = tile; col0 = nblk * BLOCK_N;
@@ -544,7 +568,7 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        for (int c = 0; c < cls.ncls; ++c) asm volatile("prefetch.tensormap [%0];" ::"l"(&outs.m[c]) : "memory");
+        for (int c = 0; c < TC_MAX_CLS; ++c) asm volatile("prefetch.tensormap [%0];" ::"l"(&outs.m[c]) : "memory");
         for (int s = 0; s < TC3_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
         for (int s = 0; s < TC3_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
         mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
@@ -563,11 +587,11 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
     if (warp == 0) {
         // ===================================================== TMA producer (both CTAs)
         if (elect_one()) {
-            int ia = 0, ib = 0, it = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-                int q0, p0, n0, col0, c;
-                decode(work, q0, p0, n0, col0, c);
-                const int ntaps = cls.ntaps[c];
+            int ia = 0, ib = 0;
+            for (int work = work_begin; work < work_end; ++work) {
+                int q0, p0, n0, col0, g;
+                decode(work, q0, p0, n0, col0, g);
+                const int ntaps = grp.ntaps[g];
                 for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
                     const int sa = ia % TC3_NA;
                     mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC3_NA)) & 1u) ^ 1u);
@@ -577,7 +601,7 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
                         const int sb = ib % TC3_NB;
                         mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
                         if (leader) mbar_expect_tx(bar_fullB + 8 * sb, 2 * B_HALF_BYTES);
-                        tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, cls.wk[c][t] + cb * TC_BK,
+                        tma2_load_2d(base + (uint32_t)sb * B_HALF_BYTES, &map_w, bar_fullB + 8 * sb, grp.wk[g][t] + cb * TC_BK,
                                      col0 + (int)rank * (BLOCK_N / 2));
                     }
                 }
@@ -588,29 +612,29 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
         if (leader && elect_one()) {
             const uint64_t sbo = (uint64_t)((uint32_t)(p.ww * 128) >> 4) << 32;        // 8-row atoms are one window row apart
             int ia = 0, ib = 0, it = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-            // accumulator buffer (it & 1): both CTAs' epilogues must have drained its previous tile (it - 2)
+            for (int work = work_begin; work < work_end; ++work, ++it) {
+            // accumulator buffer (it & 1): both CTAs' epilogues must have drained its previous item (it - 2)
             const uint32_t buf = (uint32_t)it & 1u;
             if (it > 1) { mbar_wait(bar_tmem_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-            const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
-            const int c = (work / n_blocks) % cls.ncls;
-            const int ntaps = cls.ntaps[c];
-            int tstep = 0;
+            const int g = (work / n_blocks) % grp.ngrp;
+            const int ntaps = grp.ntaps[g];
             for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
                 const int sa = ia % TC3_NA;
                 mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC3_NA)) & 1u);
                 const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
-                for (int t = 0; t < ntaps; ++t, ++ib, ++tstep) {
+                for (int t = 0; t < ntaps; ++t, ++ib) {
                     const int sb = ib % TC3_NB;
                     mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // A descriptor: start = window row arow[t]; same 128B-swizzle K-major layout, SBO = ww * 128 B
-                    const uint32_t aaddr = a0 + (uint32_t)cls.arow[c][t] * 128u;
+                    // A descriptor: start = the tap's window row; same 128B-swizzle K-major layout, SBO = ww * 128 B
+                    const uint32_t aaddr = a0 + (uint32_t)grp.arow[g][t] * 128u;
                     uint64_t da = (uint64_t)((aaddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | sbo | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
                     const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
+                    const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + (uint32_t)grp.acc[g][t] * BLOCK_N;
+                    const bool opens = cb == 0 && grp.first[g][t] != 0;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k)
-                        umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (tstep > 0 || k > 0) ? 1u : 0u);
+                        umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (!opens || k > 0) ? 1u : 0u);
                     umma2_commit(bar_emptyB + 8 * sb);
                 }
                 umma2_commit(bar_emptyA + 8 * sa);
@@ -619,47 +643,52 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
             }
         }
     } else {
-        // ===================================================== epilogue (identical to the pair kernel)
+        // ===================================================== epilogue (as in conv_tc5_kernel, once per class of the group)
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         const int iw = row % p.tw, ih = row / p.tw;
         int it = 0, gch = 0;         // gch: running chunk count -> staging buffer and bulk-group bookkeeping across tiles
-        for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
-        int q0, p0, n0, col0, c;
-        decode(work, q0, p0, n0, col0, c);
+        for (int work = work_begin; work < work_end; ++work, ++it) {
+        int q0, p0, n0, col0, g;
+        decode(work, q0, p0, n0, col0, g);
         const uint32_t buf = (uint32_t)it & 1u;
         const int n = n0, pp = p0 + ih, qq = q0 + iw;
         const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
-        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + cls.o_offy[c]) * p.FW + qq * p.o_mul + cls.o_offx[c];
         mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int a = 0; a < ACCS; ++a) {
+        const int c = grp.cls[g][a];
+        const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + grp.o_offy[c]) * p.FW + qq * p.o_mul + grp.o_offx[c];
         float nz = 0.f;
         if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
 #pragma unroll 1
         for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
-            if (gch >= TC5_NSTG) {
-                // the bulk store that last read this staging buffer (TC5_NSTG chunks ago) must have finished reading it
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
+            const bool last = a == ACCS - 1 && ch == NCHUNK - 1;
+            if (gch >= NSTG) {
+                // the bulk store that last read this staging buffer (NSTG chunks ago) must have finished reading it
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSTG - 1) : "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             float v[32];
-            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * BLOCK_N + ch * 32), v);
             const int colb = col0 + ch * 32;
             tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
-            const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
+            const uint32_t stg_off = STG_OFF + (uint32_t)(gch % NSTG) * TC_A_BYTES;
             uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
             tc_stage_row(stg, row, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (last) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && lane == 0) {
                 tma_store_4d(&outs.m[c], base + stg_off, colb, q0, p0, n0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (ch == NCHUNK - 1) {
+                if (last) {
                     // all 128 epilogue threads have finished reading TMEM: tell the leader's MMA warp (remote for rank 1)
                     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
                 }
             }
+        }
         }
         }
         if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // before the CTA retires
@@ -1178,6 +1207,8 @@ int tc_conv_per_sample(const float* src, const float* w, float* out, const sae_c
 
 // One conv_tc5m launch over the rectangle all four parity classes share, then each class's thin remainder strips through
 // the ordinary per-class path.  Returns SAE_E_UNSUPPORTED (quietly) when the shape is outside the merged kernel's reach.
+// ACCS = 1: one class per work item; ACCS = 2: two classes per work item (see the kernel's header).
+template <int ACCS>
 static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t st) {
     const TcProblem& p0 = cp[0];
     if (p0.Ncol % 128 != 0 || p0.SC % 32 != 0) return SAE_E_UNSUPPORTED;
@@ -1194,7 +1225,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     if (MH < 16 || MW < 8 || oy_max - oy_min > 2 || ox_max - ox_min > 2) return SAE_E_UNSUPPORTED;
     if ((int64_t)p0.SN * MH * MW < 2 * 128) return SAE_E_UNSUPPORTED;
 
-    TcProblem main = p0;                       // geometry of the shared rectangle (taps / offsets come from the class tables)
+    TcProblem main = p0;                       // geometry of the shared rectangle (taps / offsets come from the group tables)
     main.OH = MH; main.OW = MW;
     TcParams p;
     tc_fill_params(main, e, p);
@@ -1205,9 +1236,8 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     p.oy_min = oy_min; p.ox_min = ox_min;
     p.ww = p.tw + (ox_max - ox_min);
     p.wh = p.th + (oy_max - oy_min);
-    TcClasses cls;
+    TcGroups grp = {};
     TcOutMaps outs;
-    cls.ncls = TC_MAX_CLS;
     CUtensorMap msrc, mw, mdummy;
     int rc = tc_encode_maps(main, p, 128 / 2, &msrc, &mw, &mdummy);      // weight map (the others are rebuilt below)
     if (rc) return rc;
@@ -1221,13 +1251,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     }
     for (int c = 0; c < TC_MAX_CLS; ++c) {
         const TcProblem& q = cp[c];
-        cls.ntaps[c] = q.ntaps;
-        cls.o_offy[c] = q.o_offy; cls.o_offx[c] = q.o_offx;
-        for (int t = 0; t < 4; ++t) { cls.wk[c][t] = 0; cls.arow[c][t] = 0; }
-        for (int t = 0; t < q.ntaps; ++t) {
-            cls.wk[c][t] = q.wk[t];
-            cls.arow[c][t] = (unsigned short)((q.oy[t] - oy_min) * p.ww + (q.ox[t] - ox_min));
-        }
+        grp.o_offy[c] = q.o_offy; grp.o_offx[c] = q.o_offx;
         // output sub-grid of class c restricted to the shared MH x MW rectangle (the tensor map's extent clips the stores)
         cuuint64_t dims[4] = {(cuuint64_t)q.Ncol, (cuuint64_t)MW, (cuuint64_t)MH, (cuuint64_t)q.SN};
         cuuint64_t strides[3] = {(cuuint64_t)q.o_mul * q.Ncol * 4, (cuuint64_t)q.o_mul * q.FW * q.Ncol * 4,
@@ -1237,16 +1261,37 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
         rc = encode_map(&outs.m[c], q.out + ((int64_t)q.o_offy * q.FW + q.o_offx) * q.Ncol, 4, dims, strides, box, es);
         if (rc) return rc;
     }
-    constexpr size_t smem = tc5_smem_bytes<128, TC3_NA, tc5_nb<128>()>();
+    // groups: classes sorted by tap count; ACCS = 2 pairs the longest with the shortest (5 + 4 taps for a 3x3 filter)
+    int order[TC_MAX_CLS] = {0, 1, 2, 3};
+    for (int i = 0; i < TC_MAX_CLS; ++i)
+        for (int j = i + 1; j < TC_MAX_CLS; ++j)
+            if (cp[order[j]].ntaps > cp[order[i]].ntaps) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+    grp.ngrp = TC_MAX_CLS / ACCS;
+    for (int g = 0; g < grp.ngrp; ++g) {
+        int nt = 0;
+        for (int a = 0; a < ACCS; ++a) {
+            const int c = ACCS == 1 ? g : (a == 0 ? order[g] : order[TC_MAX_CLS - 1 - g]);
+            grp.cls[g][a] = c;
+            const TcProblem& q = cp[c];
+            for (int t = 0; t < q.ntaps; ++t, ++nt) {
+                grp.wk[g][nt] = q.wk[t];
+                grp.arow[g][nt] = (unsigned short)((q.oy[t] - oy_min) * p.ww + (q.ox[t] - ox_min));
+                grp.acc[g][nt] = (unsigned char)a;
+                grp.first[g][nt] = (unsigned char)(t == 0);
+            }
+        }
+        grp.ntaps[g] = nt;
+    }
+    constexpr size_t smem = tc5m_smem_bytes<ACCS>();
     static bool attr_done = false;
     if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5m_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc5m_kernel<ACCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int n_blocks = main.Ncol / 128;
-    const int total_work = ((tiles + 1) / 2) * TC_MAX_CLS * n_blocks;
-    int clusters = sm_count();
+    const int total_work = ((tiles + 1) / 2) * grp.ngrp * n_blocks;
+    int clusters = ACCS == 1 ? sm_count() : sm_count() / 2;      // two CTAs per SM / one CTA per SM, 2 CTAs per cluster
     if (clusters > total_work) clusters = total_work;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
@@ -1258,7 +1303,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<128>, msrc, mw, outs, p, cls, n_blocks, total_work));
+    SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<ACCS>, msrc, mw, outs, p, grp, n_blocks, total_work));
     rc = check_launch("conv_tc5m");
     if (rc) return rc;
     // remainders of each class beyond the shared rectangle: right strip (full height, takes the corner), bottom strip
@@ -1322,11 +1367,11 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
             cls_pr[ncls++] = pr;
         }
     static int merged = -1;
-    // SAE_DGRAD_MERGED: 1 (default) = conv_tc5m, one launch with the class index in the work item (386 -> 416, 441 -> 506
-    // TFLOP/s on the discriminator shapes, profiles/r2_conv_bench_s2.txt); 0 = one launch per class (A/B runs)
-    if (merged < 0) { const char* v = getenv("SAE_DGRAD_MERGED"); merged = v ? atoi(v) : 1; }
+    // SAE_DGRAD_MERGED: 2 (default) = conv_tc5m with two classes per work item; 1 = one class per work item (386 -> 416,
+    // 441 -> 506 TFLOP/s on the discriminator shapes over 0, profiles/r2_conv_bench_s2.txt); 0 = one launch per class (A/B runs)
+    if (merged < 0) { const char* v = getenv("SAE_DGRAD_MERGED"); merged = v ? atoi(v) : 2; }
     if (merged && ncls == TC_MAX_CLS && !need_zero) {
-        int rc = tc_dgrad_merged(cls_pr, e, st);
+        int rc = merged >= 2 ? tc_dgrad_merged<2>(cls_pr, e, st) : tc_dgrad_merged<1>(cls_pr, e, st);
         if (rc != SAE_E_UNSUPPORTED) return rc;
     }
     for (int c = 0; c < ncls; ++c) {

@@ -78,104 +78,142 @@ __device__ __forceinline__ uint64_t make_desc_mn_win(uint32_t saddr, int use_bas
     return d;
 }
 
+// CG = 1: one CTA per (128 out channels x 128 in channels x tap group) tile.
+// CG = 2: a CTA pair (tcgen05 cta_group::2) owns 256 out channels x 128 in channels: each CTA loads the dy sub-tiles of ITS
+//   128 out channels and HALF of every x tile (64 of the 128 in channels; the M = 256 instruction reads both CTAs' shared
+//   memory), so the x bytes per MAC halve — what the stride-2 layers need, whose x tiles are one TMA box per tap (element
+//   stride 2): 64 KB -> 40 KB per 32-pixel chunk and CTA, and a 5-deep ring instead of 3.
+template <int CG> constexpr int wg_stages() { return CG == 2 ? 5 : WG_STAGES; }
+template <int CG> constexpr int wg_stage_bytes() { return WG_OPER + WG_MAX_GROUP * (4 / CG) * WG_SUB; }       // 64 KB / 40 KB
+template <int CG> constexpr size_t wg_smem_bytes() { return (size_t)wg_stages<CG>() * wg_stage_bytes<CG>() + 1024 + 256; }
+
+template <int CG>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 float* __restrict__ dw, const WgParams p) {
-    constexpr int STAGE_BYTES = WG_OPER * (1 + WG_MAX_GROUP);       // 64 KB
-    // D fp32, A/B tf32, A and B MN-major (bits 15, 16), N = 128, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr int STAGES = wg_stages<CG>();
+    constexpr int STAGE_BYTES = wg_stage_bytes<CG>();
+    constexpr int BSUB = 4 / CG;                                   // 32-channel x sub-tiles this CTA loads per tap
+    // D fp32, A/B tf32, A and B MN-major (bits 15, 16), N = 128, M = 128 per CTA
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | (((128u * CG) >> 4) << 24);
     constexpr uint32_t TMEM_COLS = 512;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_full = base + WG_STAGES * STAGE_BYTES;
-    const uint32_t bar_empty = bar_full + 8 * WG_STAGES;
-    const uint32_t bar_acc = bar_empty + 8 * WG_STAGES;
-    const uint32_t bar_drained = bar_acc + 8;          // modulated mode: the epilogue has emptied the accumulators
+    const uint32_t bar_full = base + STAGES * STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_acc = bar_empty + 8 * STAGES;
+    const uint32_t bar_drained = bar_acc + 8;          // modulated mode: the epilogue(s) have emptied the accumulators
     const uint32_t tmem_slot = bar_drained + 8;
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_o = blockIdx.x / p.n_tiles_c, tile_c = blockIdx.x % p.n_tiles_c;
-    const int o0 = tile_o * 128, c0 = tile_c * 128;
+    const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int unit = (int)blockIdx.x / CG;                          // (out-channel tile [pair], in-channel tile)
+    const int tile_o = unit / p.n_tiles_c, tile_c = unit % p.n_tiles_c;
+    const int o0 = (tile_o * CG + rank) * 128, c0 = tile_c * 128;
     const int tap0 = blockIdx.y * p.group_taps;
     const int ntap = min(p.group_taps, p.ntaps - tap0);       // taps handled by this CTA
     const int tpa = 4 / p.cpt;                                 // taps per accumulator
     const int nacc = (ntap + tpa - 1) / tpa;                   // accumulators in use (<= 3)
-    const int nslots = ntap * p.cpt;                           // valid 32-column B sub-tiles
+    const int nslots = ntap * p.cpt;                           // valid 32-column B sub-tiles (CG = 2: cpt == 4)
     const int chunk_begin = blockIdx.z * p.chunks_per_split;
     const int chunk_end = min(chunk_begin + p.chunks_per_split, p.chunks_total);
     const int KB = chunk_end - chunk_begin;
-    const uint32_t stage_tx = p.shared_b ? (uint32_t)(WG_OPER + 4 * WG_WSUB) : (uint32_t)WG_OPER + (uint32_t)nslots * WG_SUB;
+    // bytes one CTA lands per stage
+    const uint32_t stage_tx = p.shared_b ? (uint32_t)(WG_OPER + BSUB * WG_WSUB) : (uint32_t)WG_OPER + (uint32_t)(nslots / CG) * WG_SUB;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-        for (int s = 0; s < WG_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
-        mbar_init(bar_drained, 1);
+        mbar_init(bar_drained, CG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    // loads: CG = 2 credits the leader's barrier (which expects both CTAs' bytes)
+    auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int a, int b, int c, int d) {
+        if (CG == 2) tma2_load_4d(dst, map, bar, a, b, c, d); else tma_load_4d(dst, map, bar, a, b, c, d);
+    };
 
     if (KB > 0) {
         if (warp == 0) {
             if (elect_one()) {
                 for (int kb = 0; kb < KB; ++kb) {
-                    const int s = kb % WG_STAGES;
-                    const uint32_t ph = (uint32_t)(kb / WG_STAGES) & 1u;
+                    const int s = kb % STAGES;
+                    const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     int ch = chunk_begin + kb;
                     const int tq = ch % p.tiles_w; ch /= p.tiles_w;
                     const int tp = ch % p.tiles_h; ch /= p.tiles_h;
                     const int q0 = tq * p.tw, p0 = tp * p.th, n0 = ch * p.tn;
                     const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
-                    mbar_expect_tx(bar_full + 8 * s, stage_tx);
+                    if (leader) mbar_expect_tx(bar_full + 8 * s, CG * stage_tx);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        tma_load_4d(sa + i * WG_SUB, &map_dy, bar_full + 8 * s, o0 + 32 * i, q0, p0, n0);
+                        load(sa + i * WG_SUB, &map_dy, bar_full + 8 * s, o0 + 32 * i, q0, p0, n0);
                     if (p.shared_b) {
                         // one window of WG_WIN pixels starting at the s = 0 tap position, per 32-channel sub-tile
                         const int r = tap0 / p.S;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            tma_load_4d(sa + WG_OPER + (uint32_t)i * WG_WSUB, &map_x, bar_full + 8 * s, c0 + 32 * i,
-                                        q0 - p.pad_l, p0 - p.pad_t + r, n0);
+                        for (int i = 0; i < BSUB; ++i)
+                            load(sa + WG_OPER + (uint32_t)i * WG_WSUB, &map_x, bar_full + 8 * s, c0 + 32 * (rank * BSUB + i),
+                                 q0 - p.pad_l, p0 - p.pad_t + r, n0);
+                    } else if (CG == 2) {
+                        for (int q = 0; q < ntap * BSUB; ++q) {
+                            // slot q = (tap q / BSUB, this CTA's sub-tile q % BSUB)
+                            const int tap = tap0 + q / BSUB;
+                            const int r = tap / p.S, sx = tap - r * p.S;
+                            load(sa + WG_OPER + (uint32_t)q * WG_SUB, &map_x, bar_full + 8 * s, c0 + 32 * (rank * BSUB + q % BSUB),
+                                 q0 * p.stride - p.pad_l + sx, p0 * p.stride - p.pad_t + r, n0);
+                        }
                     } else
                     for (int q = 0; q < nslots; ++q) {
                         // slot q = (accumulator q/4, 32-column group q%4) holds tap q/cpt, channels 32*(q%cpt)
                         const int tap = tap0 + q / p.cpt;
                         const int r = tap / p.S, sx = tap - r * p.S;
-                        tma_load_4d(sa + WG_OPER + (uint32_t)q * WG_SUB, &map_x, bar_full + 8 * s, c0 + 32 * (q % p.cpt),
-                                    q0 * p.stride - p.pad_l + sx, p0 * p.stride - p.pad_t + r, n0);
+                        load(sa + WG_OPER + (uint32_t)q * WG_SUB, &map_x, bar_full + 8 * s, c0 + 32 * (q % p.cpt),
+                             q0 * p.stride - p.pad_l + sx, p0 * p.stride - p.pad_t + r, n0);
                     }
                 }
             }
         } else if (warp == 1) {
-            if (elect_one()) {
+            if (leader && elect_one()) {
+                auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accumulate) {
+                    if (CG == 2) umma2_tf32(d, da, db, IDESC, accumulate); else umma_tf32(d, da, db, IDESC, accumulate);
+                };
+                auto commit = [&](uint32_t bar) { if (CG == 2) umma2_commit(bar); else umma_commit(bar); };
                 int seg = 0;
                 for (int kb = 0; kb < KB; ++kb) {
                     // modulated mode: a new image starts at this chunk -> hand the finished accumulators to the epilogue and
                     // wait until they are drained; the first MMAs of the segment then overwrite instead of accumulating
                     const bool seg_start = kb == 0 || (p.chunks_per_image > 0 && (chunk_begin + kb) % p.chunks_per_image == 0);
                     if (seg_start && kb > 0) {
-                        umma_commit(bar_acc);
+                        commit(bar_acc);
                         mbar_wait(bar_drained, (uint32_t)seg & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         ++seg;
                     }
-                    const int s = kb % WG_STAGES;
-                    const uint32_t ph = (uint32_t)(kb / WG_STAGES) & 1u;
+                    const int s = kb % STAGES;
+                    const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
@@ -186,21 +224,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                             for (int k = 0; k < WG_KPIX / 8; ++k) {
                                 // tap s = g reads window rows [g + 8k, g + 8k + 8)
                                 const uint64_t db = make_desc_mn_win(sa + WG_OPER + (uint32_t)(g + 8 * k) * 128u, p.shared_b == 1);
-                                umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db, IDESC, (!seg_start || k > 0) ? 1u : 0u);
+                                mma(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db, (!seg_start || k > 0) ? 1u : 0u);
                             }
                             continue;
                         }
-                        const uint64_t db = make_desc_mn_sw128(sa + (uint32_t)(1 + g) * WG_OPER);
+                        const uint64_t db = make_desc_mn_sw128(sa + WG_OPER + (uint32_t)g * (uint32_t)(BSUB * WG_SUB));
 #pragma unroll
                         for (int k = 0; k < WG_KPIX / 8; ++k) {
                             // next 8 pixels along K: +1024 B = +64 in the (addr >> 4) field
-                            umma_tf32(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), IDESC,
-                                      (!seg_start || k > 0) ? 1u : 0u);
+                            mma(tmem_base + (uint32_t)(g * 128), da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), (!seg_start || k > 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(bar_empty + 8 * s);
+                    commit(bar_empty + 8 * s);
                 }
-                umma_commit(bar_acc);
+                commit(bar_acc);
             }
         } else {
             const int lg = warp & 3;
@@ -246,19 +283,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 }
                 kb0 = kb1;
                 if (kb0 < KB) {
-                    // more segments follow: tell the MMA warp that the accumulators may be overwritten
+                    // more segments follow: tell the (leader's) MMA warp that the accumulators may be overwritten
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (warp == 2 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_drained) : "memory");
+                    if (warp == 2 && lane == 0) {
+                        if (CG == 2) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_drained & kPeerBitMask) : "memory");
+                        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_drained) : "memory");
+                    }
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -501,6 +542,10 @@ static int tc_wgrad_impl(const float* dy, const float* x, float* dw, const sae_c
     // 0 = off, three separate boxes)
     if (win_mode < 0) { const char* v = getenv("SAE_WGRAD_WINDOW"); win_mode = v ? atoi(v) : 2; }
     p.shared_b = (win_mode >= 1 && p.tw == 32 && g->stride == 1 && g->S == 3 && p.cpt == 4 && p.group_taps == 3) ? win_mode : 0;
+    // CTA pairs where the layer has 256 out channels per pair and whole 128-channel x tiles (SAE_WGRAD_PAIR=0: off, A/B runs)
+    static int pair_mode = -1;
+    if (pair_mode < 0) { const char* v = getenv("SAE_WGRAD_PAIR"); pair_mode = (v && v[0] == '0') ? 0 : 1; }
+    const bool pair = pair_mode && g->K % 256 == 0 && g->C % 128 == 0 && p.cpt == 4;
 
     CUtensorMap mdy, mx;
     {
@@ -520,14 +565,34 @@ static int tc_wgrad_impl(const float* dy, const float* x, float* dw, const sae_c
         int rc = encode_map(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
     }
-    constexpr size_t smem = (size_t)WG_STAGES * WG_OPER * (1 + WG_MAX_GROUP) + 1024 + 256;
+    if (pair) {
+        constexpr size_t smem = wg_smem_bytes<2>();
+        static bool attr_done = false;
+        if (!attr_done) {
+            SAE_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(tiles_o * p.n_tiles_c), (unsigned)groups, (unsigned)splits);      // tiles_o is even
+        cfg.blockDim = dim3(WG_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<2>, mdy, mx, dw, p));
+        return check_launch("wgrad_tc<2>");
+    }
+    constexpr size_t smem = wg_smem_bytes<1>();
     static bool attr_done = false;
     if (!attr_done) {
-        SAE_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SAE_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     dim3 grid((unsigned)(tiles_o * p.n_tiles_c), (unsigned)groups, (unsigned)splits);
-    wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(mdy, mx, dw, p);
+    wgrad_tc_kernel<1><<<grid, WG_THREADS, smem, st>>>(mdy, mx, dw, p);
     return check_launch("wgrad_tc");
 }
 

@@ -14,7 +14,7 @@ pytestmark = [pytest.mark.gpu,
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{"SAE_DGRAD_MERGED": "0"}, {"SAE_DISABLE_TCGEN05": "1"}, {"SAE_FUSED_BLOCKS": "0"}],
+@pytest.mark.parametrize("env", [{"SAE_DGRAD_MERGED": "0"}, {"SAE_DGRAD_MERGED": "1"}, {"SAE_WGRAD_PAIR": "0"}, {"SAE_DISABLE_TCGEN05": "1"}, {"SAE_FUSED_BLOCKS": "0"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_alternative_kernel_selection(env):
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q",

@@ -275,6 +275,8 @@ CONV_CASES = [
     (8, 128, 128, 32, 32, 3, 1, 1),          # narrow 3x3: 512 work items over <= 148 pairs
     (4, 128, 128, 128, 256, 1, 1, 0),        # wide 1x1 (two 128-column blocks per pixel tile)
     (16, 129, 129, 128, 256, 3, 2, 0),       # stride-2 data gradient: its 1- and 2-tap parity classes
+    (2, 32, 32, 256, 512, 3, 1, 1),          # weight gradient as CTA pairs: two pairs along the out channels, two x tiles
+    (3, 65, 65, 256, 512, 3, 2, 0),          # the same at stride 2 (one x box per tap, each CTA loads half of it)
 ]
 
 
