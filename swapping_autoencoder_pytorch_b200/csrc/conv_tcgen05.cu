@@ -129,10 +129,27 @@ constexpr size_t tc_smem_bytes() {
     return (ring > epi ? ring : epi) + 1024 /*alignment slack*/ + 256 /*barriers*/;
 }
 
+// Up to TC_MAX_BATCH problems over the same filter matrix in one launch (the thin remainder strips of the four parity classes of
+// a stride-2 data gradient: each is a handful of tiles whose cost is the latency of one K loop — launched one after the
+// other they cost 4 x 20..30 us behind a 0.5 ms main kernel, together one).  blockIdx.x walks the problems' tiles back to back.
+constexpr int TC_MAX_BATCH = 4;
+struct TcBatch {
+    int count;
+    int tile_end[TC_MAX_BATCH];               // running sum of the problems' pixel-tile counts
+    TcParams p[TC_MAX_BATCH];
+    CUtensorMap src[TC_MAX_BATCH], out[TC_MAX_BATCH];
+    CUtensorMap w;
+};
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ TcBatch batch) {
+    int prob = 0;
+    while (prob + 1 < batch.count && (int)blockIdx.x >= batch.tile_end[prob]) ++prob;
+    const TcParams& p = batch.p[prob];
+    const CUtensorMap& map_src = batch.src[prob];
+    const CUtensorMap& map_out = batch.out[prob];
+    const CUtensorMap& map_w = batch.w;
     constexpr int STAGES = tc_stages<BLOCK_N>();
     constexpr int B_BYTES = BLOCK_N * 128;
     constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
@@ -154,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // tile coordinates
-    int tile = blockIdx.x;
+    int tile = (int)blockIdx.x - (prob > 0 ? batch.tile_end[prob - 1] : 0);
     const int tq = tile % p.tiles_w; tile /= p.tiles_w;
     const int tp = tile % p.tiles_h; tile /= p.tiles_h;
     const int tnb = tile;
@@ -503,17 +520,20 @@ struct TcGroups {
     int o_offy[TC_MAX_CLS], o_offx[TC_MAX_CLS];
 };
 
-template <int ACCS> constexpr int tc5m_na() { return ACCS == 1 ? 2 : 3; }
+// ring depths: ACCS = 1 as conv_tc5_kernel (two CTAs per SM); ACCS = 2 pools the SM's shared memory: 4 window slots of 20 KB
+// (17 x 9 pixels — a 3x3 filter's classes; the launcher checks), 8 filter tiles, 4 staging buffers = 208 KB
+template <int ACCS> constexpr int tc5m_na() { return ACCS == 1 ? 2 : 4; }
+template <int ACCS> constexpr int tc5m_aslot() { return ACCS == 1 ? TC3_ASLOT : 20 * 1024; }
 template <int ACCS> constexpr int tc5m_nb() { return ACCS == 1 ? 4 : 8; }
 template <int ACCS> constexpr int tc5m_nstg() { return ACCS == 1 ? 2 : 4; }
 template <int ACCS>
 constexpr size_t tc5m_smem_bytes() {
-    return (size_t)tc5m_nb<ACCS>() * 64 * 128 + (size_t)tc5m_na<ACCS>() * TC3_ASLOT + (size_t)tc5m_nstg<ACCS>() * TC_A_BYTES + 1024 +
+    return (size_t)tc5m_nb<ACCS>() * 64 * 128 + (size_t)tc5m_na<ACCS>() * tc5m_aslot<ACCS>() + (size_t)tc5m_nstg<ACCS>() * TC_A_BYTES + 1024 +
            8 * (size_t)(2 * tc5m_na<ACCS>() + 2 * tc5m_nb<ACCS>() + 4) + 64;
 }
 
 template <int ACCS>
-__global__ void __launch_bounds__(TC_THREADS, ACCS == 1 ? 2 : 1)
+__global__ void __launch_bounds__(64 + 128 * ACCS, ACCS == 1 ? 2 : 1)
 conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ TcOutMaps outs, const TcParams p, const __grid_constant__ TcGroups grp, const int n_blocks,
                  const int total_work) {
@@ -522,15 +542,16 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
     constexpr int TC3_NB = tc5m_nb<ACCS>();
     constexpr int TC3_NA = tc5m_na<ACCS>();
     constexpr int NSTG = tc5m_nstg<ACCS>();
+    constexpr uint32_t ASLOT = (uint32_t)tc5m_aslot<ACCS>();
     constexpr uint32_t B_RING = (uint32_t)TC3_NB * B_HALF_BYTES;
-    constexpr uint32_t RING0 = B_RING + (uint32_t)TC3_NA * TC3_ASLOT;
+    constexpr uint32_t RING0 = B_RING + (uint32_t)TC3_NA * ASLOT;
     constexpr uint32_t STG_OFF = RING0;                                  // staging follows the rings (1024-byte aligned)
     constexpr uint32_t RING = RING0 + (uint32_t)NSTG * TC_A_BYTES;
     constexpr uint32_t ACC_COLS = (uint32_t)(ACCS * BLOCK_N);            // one accumulator buffer = ACCS class accumulators
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                         // two accumulator buffers
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((256u >> 4) << 24);
     constexpr int NCHUNK = BLOCK_N / 32;
-    static_assert(TMEM_COLS <= 512 && (B_RING % 1024u) == 0 && (TC3_ASLOT % 1024) == 0, "tc5m: layout");
+    static_assert(TMEM_COLS <= 512 && (B_RING % 1024u) == 0 && (ASLOT % 1024u) == 0, "tc5m: layout");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -572,7 +593,7 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
         for (int s = 0; s < TC3_NA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
         for (int s = 0; s < TC3_NB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
         mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
-        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
+        mbar_init(bar_tmem_empty, 2 * ACCS); mbar_init(bar_tmem_empty + 8, 2 * ACCS);      // both CTAs x ACCS epilogue groups
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -596,7 +617,7 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
                     const int sa = ia % TC3_NA;
                     mbar_wait(bar_emptyA + 8 * sa, (((uint32_t)(ia / TC3_NA)) & 1u) ^ 1u);
                     if (leader) mbar_expect_tx(bar_fullA + 8 * sa, 2 * a_bytes);
-                    tma2_load_4d(a_ring + (uint32_t)sa * TC3_ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
+                    tma2_load_4d(a_ring + (uint32_t)sa * ASLOT, &map_src, bar_fullA + 8 * sa, cb * TC_BK, q0 + p.ox_min, p0 + p.oy_min, n0);
                     for (int t = 0; t < ntaps; ++t, ++ib) {
                         const int sb = ib % TC3_NB;
                         mbar_wait(bar_emptyB + 8 * sb, (((uint32_t)(ib / TC3_NB)) & 1u) ^ 1u);
@@ -621,7 +642,7 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
             for (int cb = 0; cb < p.num_cblk; ++cb, ++ia) {
                 const int sa = ia % TC3_NA;
                 mbar_wait(bar_fullA + 8 * sa, ((uint32_t)(ia / TC3_NA)) & 1u);
-                const uint32_t a0 = a_ring + (uint32_t)sa * TC3_ASLOT;
+                const uint32_t a0 = a_ring + (uint32_t)sa * ASLOT;
                 for (int t = 0; t < ntaps; ++t, ++ib) {
                     const int sb = ib % TC3_NB;
                     mbar_wait(bar_fullB + 8 * sb, ((uint32_t)(ib / TC3_NB)) & 1u);
@@ -643,11 +664,17 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
             }
         }
     } else {
-        // ===================================================== epilogue (as in conv_tc5_kernel, once per class of the group)
+        // ===================================================== epilogue: one group of four warps PER class accumulator of the item
+        // (as in conv_tc5_kernel; ncu's stall sampling of the single-group version showed the epilogue warps busy ~90 % of the
+        // kernel — two 64 KB tiles per item and CTA against 4-5 taps of MMAs — and the tensor pipe waiting for free accumulators)
+        const int eg = (warp - 2) >> 2;                  // epilogue group = accumulator within the item
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         const int iw = row % p.tw, ih = row / p.tw;
-        int it = 0, gch = 0;         // gch: running chunk count -> staging buffer and bulk-group bookkeeping across tiles
+        const bool boss = ((warp - 2) & 3) == 0 && lane == 0;          // the group's store-issuing thread
+        const uint32_t barid = 1u + (uint32_t)eg;
+        constexpr int GS = NSTG / ACCS;                  // staging buffers per group
+        int it = 0, gch = 0;         // gch: the group's running chunk count -> staging buffer and bulk-group bookkeeping across tiles
         for (int work = work_begin; work < work_end; ++work, ++it) {
         int q0, p0, n0, col0, g;
         decode(work, q0, p0, n0, col0, g);
@@ -656,42 +683,39 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
         const bool valid = n < p.ON && pp < p.OH && qq < p.OW;
         mbar_wait(bar_acc + 8 * buf, (uint32_t)(it >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int a = 0; a < ACCS; ++a) {
-        const int c = grp.cls[g][a];
+        const int c = grp.cls[g][eg];
         const int64_t pixel = ((int64_t)n * p.FH + pp * p.o_mul + grp.o_offy[c]) * p.FW + qq * p.o_mul + grp.o_offx[c];
         float nz = 0.f;
         if (p.epi.noise && valid) nz = __ldg(p.epi.noise_weight) * __ldg(p.epi.noise + pixel);
 #pragma unroll 1
         for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
-            const bool last = a == ACCS - 1 && ch == NCHUNK - 1;
-            if (gch >= NSTG) {
-                // the bulk store that last read this staging buffer (NSTG chunks ago) must have finished reading it
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSTG - 1) : "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool last = ch == NCHUNK - 1;
+            if (gch >= GS) {
+                // the bulk store that last read this staging buffer (GS chunks ago) must have finished reading it
+                if (boss) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(GS - 1) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
             }
             float v[32];
-            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * BLOCK_N + ch * 32), v);
+            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(eg * BLOCK_N + ch * 32), v);
             const int colb = col0 + ch * 32;
             tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
-            const uint32_t stg_off = STG_OFF + (uint32_t)(gch % NSTG) * TC_A_BYTES;
+            const uint32_t stg_off = STG_OFF + (uint32_t)(eg * GS + gch % GS) * TC_A_BYTES;
             uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
             tc_stage_row(stg, row, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (last) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2 && lane == 0) {
+            asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+            if (boss) {
                 tma_store_4d(&outs.m[c], base + stg_off, colb, q0, p0, n0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 if (last) {
-                    // all 128 epilogue threads have finished reading TMEM: tell the leader's MMA warp (remote for rank 1)
+                    // this group's 128 threads have finished reading TMEM: tell the leader's MMA warp (remote for rank 1)
                     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
                 }
             }
         }
         }
-        }
-        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // before the CTA retires
+        if (boss) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // before the CTA retires
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();
@@ -706,19 +730,24 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
 // element stride), a persistent loop over (tile pair, column block) work items, two accumulator buffers in TMEM and dedicated
 // output staging, so loads and MMAs of tile i + 1 overlap the epilogue of tile i.
 // BLOCK_N = 128: 3 x (16 KB A + 8 KB half-B) + 2 x 16 KB staging = 104 KB, two CTAs per SM.
-// BLOCK_N = 256: ONE CTA per SM owning all 512 TMEM columns (2 x 256) and a 5-deep ring, 5 x (16 KB + 16 KB) + 32 KB = 192 KB.
+// BLOCK_N = 256: ONE CTA per SM owning all 512 TMEM columns (2 x 256), a 5-deep ring and two epilogue groups: 5 x (16 KB + 16 KB) + 4 x 16 KB = 224 KB.
 // The per-tap kernels are bound by the L2 -> SM feed (ncu, profiles/r2_prof_s2_fprop_tc6.txt: lts 58 %, tensor pipe 53 %):
 // 256 columns halve the A bytes per MAC and the deeper ring covers the L2 latency that 3 stages x 256 clk cannot.
 template <int BLOCK_N>
 constexpr int tc6_stages() { return BLOCK_N >= 256 ? 5 : 3; }
 
+// epilogue groups of four warps: one per 128 output columns (BLOCK_N = 256: two groups, each with its own two staging buffers
+// and named barrier — a single group drained 8 x 16 KB per item against a K loop that is only twice as long as at 128 columns)
+template <int BLOCK_N> constexpr int tc6_groups() { return BLOCK_N / 128; }
+template <int BLOCK_N> constexpr int tc6_threads() { return 64 + 128 * tc6_groups<BLOCK_N>(); }
+
 template <int BLOCK_N>
 constexpr size_t tc6_smem_bytes() {
-    return (size_t)tc6_stages<BLOCK_N>() * (TC_A_BYTES + (BLOCK_N / 2) * 128) + (size_t)TC5_NSTG * TC_A_BYTES + 1024 + 256;
+    return (size_t)tc6_stages<BLOCK_N>() * (TC_A_BYTES + (BLOCK_N / 2) * 128) + (size_t)(tc6_groups<BLOCK_N>() * TC5_NSTG) * TC_A_BYTES + 1024 + 256;
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, BLOCK_N >= 256 ? 1 : 2)
+__global__ void __launch_bounds__(tc6_threads<BLOCK_N>(), BLOCK_N >= 256 ? 1 : 2)
 conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const TcParams p, const int n_blocks, const int total_work) {
     constexpr int STAGES = tc6_stages<BLOCK_N>();
@@ -734,9 +763,10 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t RING = (uint32_t)STAGES * STAGE_BYTES;
     constexpr uint32_t STG_OFF = RING;                                     // dedicated staging behind the ring
-    constexpr uint32_t BAR_OFF = RING + (uint32_t)TC5_NSTG * TC_A_BYTES;
+    constexpr int EG = tc6_groups<BLOCK_N>();
+    constexpr uint32_t BAR_OFF = RING + (uint32_t)(EG * TC5_NSTG) * TC_A_BYTES;
     static_assert(RING % 1024u == 0, "tc6: staging must stay 1024-byte aligned");
-    constexpr int NCHUNK = BLOCK_N / 32;
+    constexpr int NCHUNK = BLOCK_N / 32 / EG;                              // 32-column chunks per epilogue group
     const uint32_t bar_full = base + BAR_OFF;
     const uint32_t bar_empty = bar_full + 8 * STAGES;
     const uint32_t bar_acc = bar_empty + 8 * STAGES;              // [2]
@@ -769,7 +799,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
-        mbar_init(bar_tmem_empty, 2); mbar_init(bar_tmem_empty + 8, 2);
+        mbar_init(bar_tmem_empty, 2 * EG); mbar_init(bar_tmem_empty + 8, 2 * EG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -825,10 +855,13 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
             }
         }
     } else {
-        // ===================================================== epilogue: identical to the 1-CTA kernel (own 128 rows)
+        // ===================================================== epilogue: group eg of four warps owns columns [128 eg, 128 eg + 128)
+        const int eg = (warp - 2) >> 2;
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         const int iw = row % p.tw, ih = (row / p.tw) % p.th, in_ = row / (p.tw * p.th);
+        const bool boss = ((warp - 2) & 3) == 0 && lane == 0;
+        const uint32_t barid = 1u + (uint32_t)eg;
         int it = 0, gch = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters, ++it) {
         int q0, p0, n0, col0;
@@ -845,28 +878,28 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_consta
         for (int ch = 0; ch < NCHUNK; ++ch, ++gch) {
             if (gch >= TC5_NSTG) {
                 // the bulk store that last read this staging buffer (TC5_NSTG chunks ago) must have finished reading it
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (boss) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TC5_NSTG - 1) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
             }
             float v[32];
-            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
-            const int colb = col0 + ch * 32;
+            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(eg * 128 + ch * 32), v);
+            const int colb = col0 + eg * 128 + ch * 32;
             tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
-            const uint32_t stg_off = STG_OFF + (uint32_t)(gch % TC5_NSTG) * TC_A_BYTES;
+            const uint32_t stg_off = STG_OFF + (uint32_t)(eg * TC5_NSTG + gch % TC5_NSTG) * TC_A_BYTES;
             uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
             tc_stage_row(stg, row, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (ch == NCHUNK - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2 && lane == 0) {
+            asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+            if (boss) {
                 tma_store_4d(&map_out, base + stg_off, colb, q0, p0, n0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (ch == NCHUNK - 1)      // all 128 epilogue threads are done with this accumulator buffer
+                if (ch == NCHUNK - 1)      // this group's 128 threads are done with the accumulator buffer
                     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((bar_tmem_empty + 8 * buf) & kPeerBitMask) : "memory");
             }
         }
         }
-        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (boss) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                      // nobody leaves (or frees TMEM) while the peer may still touch this CTA
@@ -955,22 +988,38 @@ static int tc_encode_maps(const TcProblem& pr, const TcParams& p, int b_rows, CU
     return SAE_OK;
 }
 
+// one-tile-per-CTA launch of up to TC_MAX_BATCH problems that share the filter matrix, the column count and the epilogue
 template <int BLOCK_N>
-static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
-    TcParams p;
-    tc_fill_params(pr, e, p);
-    CUtensorMap msrc, mw, mout;
-    int rc = tc_encode_maps(pr, p, BLOCK_N, &msrc, &mw, &mout);
-    if (rc) return rc;
+static int tc_launch_batch(const TcProblem* prs, int count, const EpiParams& e, cudaStream_t st) {
+    TcBatch b;
+    if (count < 1 || count > TC_MAX_BATCH) return fail(SAE_E_INVALID, "conv_tc: batch of %d problems", count);
+    b.count = count;
+    int tiles = 0;
+    for (int i = 0; i < count; ++i) {
+        tc_fill_params(prs[i], e, b.p[i]);
+        CUtensorMap mw;
+        int rc = tc_encode_maps(prs[i], b.p[i], BLOCK_N, &b.src[i], &mw, &b.out[i]);
+        if (rc) return rc;
+        if (i == 0) b.w = mw;
+        else if (prs[i].wmat != prs[0].wmat || prs[i].Ncol != prs[0].Ncol || prs[i].Ktot != prs[0].Ktot)
+            return fail(SAE_E_INVALID, "conv_tc: batched problems must share the filter matrix");
+        tiles += b.p[i].tiles_w * b.p[i].tiles_h * b.p[i].tiles_n;
+        b.tile_end[i] = tiles;
+    }
     constexpr size_t smem = tc_smem_bytes<BLOCK_N>();
     static bool attr_done = false;
     if (!attr_done) {
         SAE_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(pr.Ncol / BLOCK_N));
-    conv_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(msrc, mw, mout, p);
+    dim3 grid((unsigned)tiles, (unsigned)(prs[0].Ncol / BLOCK_N));
+    conv_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(b);
     return check_launch("conv_tc");
+}
+
+template <int BLOCK_N>
+static int tc_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) {
+    return tc_launch_batch<BLOCK_N>(&pr, 1, e, st);
 }
 
 // persistent per-tap pair launch (conv_tc6_kernel): stride-2 fprop, small maps — everything the shared window does not take
@@ -996,7 +1045,7 @@ static int tc6_launch(const TcProblem& pr, const EpiParams& e, cudaStream_t st) 
     int clusters = BLOCK_N >= 256 ? sm_count() / 2 : sm_count();
     if (clusters > total_work) clusters = total_work;
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.blockDim = dim3(tc6_threads<BLOCK_N>(), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1224,6 +1273,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     }
     if (MH < 16 || MW < 8 || oy_max - oy_min > 2 || ox_max - ox_min > 2) return SAE_E_UNSUPPORTED;
     if ((int64_t)p0.SN * MH * MW < 2 * 128) return SAE_E_UNSUPPORTED;
+    if ((16 + oy_max - oy_min) * (8 + ox_max - ox_min) * 128 > tc5m_aslot<ACCS>()) return SAE_E_UNSUPPORTED;      // window slot
 
     TcProblem main = p0;                       // geometry of the shared rectangle (taps / offsets come from the group tables)
     main.OH = MH; main.OW = MW;
@@ -1295,7 +1345,7 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     if (clusters > total_work) clusters = total_work;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2), 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.blockDim = dim3(64 + 128 * ACCS, 1, 1);      // producer warp, MMA warp, four epilogue warps per class accumulator
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1306,11 +1356,20 @@ static int tc_dgrad_merged(const TcProblem* cp, const EpiParams& e, cudaStream_t
     SAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc5m_kernel<ACCS>, msrc, mw, outs, p, grp, n_blocks, total_work));
     rc = check_launch("conv_tc5m");
     if (rc) return rc;
-    // remainders of each class beyond the shared rectangle: right strip (full height, takes the corner), bottom strip
+    // remainders of each class beyond the shared rectangle: right strip (full height, takes the corner), bottom strip —
+    // all of them in ONE launch of the one-tile kernel (profiles/r2_wgrad_pairs.txt: 0.597 ms with four strip launches
+    // against 0.523 ms for the strip-free 256^2 shape)
+    TcProblem strips[2 * TC_MAX_CLS];
+    int ns = 0;
     for (int c = 0; c < TC_MAX_CLS; ++c) {
         const TcProblem& q = cp[c];
-        if (MW < q.OW) { rc = tc_dispatch(tc_subproblem(q, 0, q.OH, MW, q.OW), e, st); if (rc) return rc; }
-        if (MH < q.OH) { rc = tc_dispatch(tc_subproblem(q, MH, q.OH, 0, MW), e, st); if (rc) return rc; }
+        if (MW < q.OW) strips[ns++] = tc_subproblem(q, 0, q.OH, MW, q.OW);
+        if (MH < q.OH) strips[ns++] = tc_subproblem(q, MH, q.OH, 0, MW);
+    }
+    for (int i = 0; i < ns; i += TC_MAX_BATCH) {
+        const int cnt = ns - i < TC_MAX_BATCH ? ns - i : TC_MAX_BATCH;
+        rc = tc_launch_batch<128>(strips + i, cnt, e, st);
+        if (rc) return rc;
     }
     return SAE_OK;
 }
@@ -1371,7 +1430,8 @@ int tc_dgrad(const float* dy, const float* wt, float* dx, const sae_conv_geom* g
     // 441 -> 506 TFLOP/s on the discriminator shapes over 0, profiles/r2_conv_bench_s2.txt); 0 = one launch per class (A/B runs)
     if (merged < 0) { const char* v = getenv("SAE_DGRAD_MERGED"); merged = v ? atoi(v) : 2; }
     if (merged && ncls == TC_MAX_CLS && !need_zero) {
-        int rc = merged >= 2 ? tc_dgrad_merged<2>(cls_pr, e, st) : tc_dgrad_merged<1>(cls_pr, e, st);
+        int rc = merged >= 2 ? tc_dgrad_merged<2>(cls_pr, e, st) : SAE_E_UNSUPPORTED;
+        if (rc == SAE_E_UNSUPPORTED) rc = tc_dgrad_merged<1>(cls_pr, e, st);
         if (rc != SAE_E_UNSUPPORTED) return rc;
     }
     for (int c = 0; c < ncls; ++c) {
