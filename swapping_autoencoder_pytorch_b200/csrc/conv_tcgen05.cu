@@ -75,6 +75,7 @@ struct TcParams {
                                         // batch; Ncol = per-sample filters [N, Ncol, Ktot], the style-modulated convolution)
     int b_resident;                     // shared-window kernel: the whole filter slice of this CTA's column block (ntaps x
                                         // num_cblk tiles) fits the B ring and is loaded ONCE per CTA instead of once per pixel tile
+    int debug;                          // timing experiments (SAE_TC_DEBUG, conv_tc5m only): 1 no output stores, 2 no epilogue work, 4 no MMAs
     EpiParams epi;
 };
 
@@ -653,9 +654,11 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
                     const uint64_t db = make_desc_sw128(base + (uint32_t)sb * B_HALF_BYTES);
                     const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + (uint32_t)grp.acc[g][t] * BLOCK_N;
                     const bool opens = cb == 0 && grp.first[g][t] != 0;
+                    if (!(p.debug & 4)) {
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k)
                         umma2_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (!opens || k > 0) ? 1u : 0u);
+                    }
                     umma2_commit(bar_emptyB + 8 * sb);
                 }
                 umma2_commit(bar_emptyA + 8 * sa);
@@ -696,17 +699,19 @@ conv_tc5m_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_const
                 asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
             }
             float v[32];
-            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(eg * BLOCK_N + ch * 32), v);
             const int colb = col0 + ch * 32;
-            tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
             const uint32_t stg_off = STG_OFF + (uint32_t)(eg * GS + gch % GS) * TC_A_BYTES;
+            if (!(p.debug & 2)) {
+            tmem_ld32(tmem_base + buf * ACC_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(eg * BLOCK_N + ch * 32), v);
+            tc_epilogue_math(v, p.epi, colb, pixel, p.Ncol, valid, nz);
             uint8_t* stg = smem_gen + stg_off + (size_t)row * 128;
             tc_stage_row(stg, row, v);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (last) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
             if (boss) {
-                tma_store_4d(&outs.m[c], base + stg_off, colb, q0, p0, n0);
+                if (!(p.debug & 3)) tma_store_4d(&outs.m[c], base + stg_off, colb, q0, p0, n0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 if (last) {
                     // this group's 128 threads have finished reading TMEM: tell the leader's MMA warp (remote for rank 1)
@@ -956,6 +961,9 @@ static void tc_fill_params(const TcProblem& pr, const EpiParams& e, TcParams& p)
     p.o_mul = pr.o_mul; p.o_offy = pr.o_offy; p.o_offx = pr.o_offx; p.FH = pr.FH; p.FW = pr.FW;
     p.w_nstride = pr.w_per_sample ? pr.Ncol : 0;
     p.b_resident = 0;
+    static int dbg = -1;
+    if (dbg < 0) { const char* v = getenv("SAE_TC_DEBUG"); dbg = v ? atoi(v) : 0; }
+    p.debug = dbg;
     p.epi = e;
 }
 

@@ -170,21 +170,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                     if (++tq == p.tiles_w) { tq = 0; if (++tp == p.tiles_h) { tp = 0; ++tnb; } }
                     const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
                     if (leader) mbar_expect_tx(bar_full + 8 * s, CG * stage_tx);
-                    if (CG == 2 && p.five_d) {
-                        // pair mode: 5-D tensor maps whose outermost dimension walks the 32-channel sub-tiles (128 bytes apart
-                        // in memory, WG_SUB / WG_WSUB apart in shared memory): one TMA instruction per operand tile instead of
-                        // one per sub-tile — 4 instead of 10 per stage at stride 2.  The producer is ONE thread; at ~50 clk of
-                        // issue per bulk-tensor instruction ten of them filled the 768 clk a stage's MMAs take.
-                        tma2_load_5d(sa, &map_dy, bar_full + 8 * s, 0, q0, p0, n0, o0 / 32);
+                    if (p.five_d) {
+                        // 5-D tensor maps whose outermost dimension walks the 32-channel sub-tiles (128 bytes apart in memory,
+                        // WG_SUB / WG_WSUB apart in shared memory): one TMA instruction per operand tile instead of one per
+                        // sub-tile — e.g. 4 instead of 10 per stage for a CTA of a pair at stride 2.  The producer is ONE thread; at
+                        // ~90 clk of issue per bulk-tensor instruction ten of them filled the 768 clk a stage's MMAs take
+                        // (profiles/r2_s2_family_call18.txt: 625 -> 721 TFLOP/s from this alone).
+                        auto load5 = [&](uint32_t dst, const CUtensorMap* map, int a, int b, int c, int d, int e) {
+                            if (CG == 2) tma2_load_5d(dst, map, bar_full + 8 * s, a, b, c, d, e); else tma_load_5d(dst, map, bar_full + 8 * s, a, b, c, d, e);
+                        };
+                        load5(sa, &map_dy, 0, q0, p0, n0, o0 / 32);
                         if (p.shared_b) {
-                            tma2_load_5d(sa + WG_OPER, &map_x, bar_full + 8 * s, 0, q0 - p.pad_l, p0 - p.pad_t + tap0 / p.S, n0,
-                                         c0 / 32 + rank * BSUB);
+                            load5(sa + WG_OPER, &map_x, 0, q0 - p.pad_l, p0 - p.pad_t + tap0 / p.S, n0, c0 / 32 + rank * BSUB);
                         } else {
                             for (int q = 0; q < ntap; ++q) {
                                 const int tap = tap0 + q;
                                 const int r = tap / p.S, sx = tap - r * p.S;
-                                tma2_load_5d(sa + WG_OPER + (uint32_t)(q * BSUB) * WG_SUB, &map_x, bar_full + 8 * s, 0,
-                                             q0 * p.stride - p.pad_l + sx, p0 * p.stride - p.pad_t + r, n0, c0 / 32 + rank * BSUB);
+                                load5(sa + WG_OPER + (uint32_t)(q * BSUB) * WG_SUB, &map_x, 0, q0 * p.stride - p.pad_l + sx,
+                                      p0 * p.stride - p.pad_t + r, n0, c0 / 32 + rank * BSUB);
                             }
                         }
                         continue;
@@ -587,29 +590,29 @@ static int tc_wgrad_impl(const float* dy, const float* x, float* dw, const sae_c
         int rc = encode_map(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
     }
-    if (pair) {
-        // 5-D views: (32 channels, W, H, N, channel block) — see the producer.  The channel-block dimension has the SMALLEST
-        // stride (128 bytes); should a driver refuse such a view, the 4-D maps encoded above stay in use (p.five_d = 0).
-        static int five_d = -1;
-        if (five_d < 0) { const char* v = getenv("SAE_WGRAD_5D"); five_d = (v && v[0] == '0') ? 0 : 1; }
-        if (five_d) {
-            CUtensorMap m5dy, m5x;
-            cuuint64_t ddims[5] = {32, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N, (cuuint64_t)(g->K / 32)};
-            cuuint64_t dstr[4] = {(cuuint64_t)g->K * 4, (cuuint64_t)g->Q * g->K * 4, (cuuint64_t)g->P * g->Q * g->K * 4, 128};
-            cuuint32_t dbox[5] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn, 4};
-            cuuint32_t des[5] = {1, 1, 1, 1, 1};
-            cuuint64_t xdims[5] = {32, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N, (cuuint64_t)(g->C / 32)};
-            cuuint64_t xstr[4] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4, 128};
-            cuuint32_t xbox[5] = {32, (cuuint32_t)(p.tw * g->stride), (cuuint32_t)(p.th * g->stride), (cuuint32_t)p.tn, 2};
-            if (p.shared_b) xbox[1] = WG_WIN;
-            cuuint32_t xes[5] = {1, (cuuint32_t)g->stride, (cuuint32_t)g->stride, 1, 1};
-            if (encode_map(&m5dy, dy, 5, ddims, dstr, dbox, des, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) == SAE_OK &&
-                encode_map(&m5x, x, 5, xdims, xstr, xbox, xes, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) == SAE_OK) {
-                mdy = m5dy; mx = m5x; p.five_d = 1;
-            } else {
-                five_d = 0;
-            }
+    // 5-D views (32 channels, W, H, N, channel block) — see the producer; whole 128-channel operand tiles only (cpt == 4).  The
+    // channel-block dimension has the SMALLEST stride (128 bytes); should a driver refuse such a view, the 4-D maps above stay.
+    static int five_d = -1;
+    if (five_d < 0) { const char* v = getenv("SAE_WGRAD_5D"); five_d = (v && v[0] == '0') ? 0 : 1; }
+    if (five_d && p.cpt == 4 && g->C % 32 == 0 && g->K % 32 == 0) {
+        CUtensorMap m5dy, m5x;
+        cuuint64_t ddims[5] = {32, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N, (cuuint64_t)(g->K / 32)};
+        cuuint64_t dstr[4] = {(cuuint64_t)g->K * 4, (cuuint64_t)g->Q * g->K * 4, (cuuint64_t)g->P * g->Q * g->K * 4, 128};
+        cuuint32_t dbox[5] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn, 4};
+        cuuint32_t des[5] = {1, 1, 1, 1, 1};
+        cuuint64_t xdims[5] = {32, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N, (cuuint64_t)(g->C / 32)};
+        cuuint64_t xstr[4] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4, 128};
+        cuuint32_t xbox[5] = {32, (cuuint32_t)(p.tw * g->stride), (cuuint32_t)(p.th * g->stride), (cuuint32_t)p.tn, pair ? 2u : 4u};
+        if (p.shared_b) xbox[1] = WG_WIN;
+        cuuint32_t xes[5] = {1, (cuuint32_t)g->stride, (cuuint32_t)g->stride, 1, 1};
+        if (encode_map(&m5dy, dy, 5, ddims, dstr, dbox, des, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) == SAE_OK &&
+            encode_map(&m5x, x, 5, xdims, xstr, xbox, xes, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) == SAE_OK) {
+            mdy = m5dy; mx = m5x; p.five_d = 1;
+        } else {
+            five_d = 0;
         }
+    }
+    if (pair) {
         constexpr size_t smem = wg_smem_bytes<2>();
         static bool attr_done = false;
         if (!attr_done) {
