@@ -31,7 +31,7 @@ extern "C" {
 #define SAE_E_UNSUPPORTED  -3   /* valid request this build has no kernel for                */
 
 /* ABI version of this header; bumped on any signature change. */
-#define SAE_ABI_VERSION 12
+#define SAE_ABI_VERSION 13
 int         sae_abi_version(void);
 const char* sae_last_error(void);
 /* number of kernels launched by this library in the calling process since load
@@ -88,11 +88,12 @@ int sae_fused_bias_act(const float* x, const float* bias, const float* ref, floa
  * .sum() kernel, fused_act.py:32-41).  grad_bias must be zero-initialised by the caller (or hold
  * a value to accumulate into).  Optional: noise != NULL accumulates d/d(noise_weight) =
  * sum(grad_in * noise) into grad_noise_weight[0].  Layout restriction: step_b == 1 (channels
- * innermost, i.e. NHWC or [B, C]). */
+ * innermost, i.e. NHWC or [B, C]).  act_mask != NULL (size_b % 32 == 0): the branch is read from the bit mask a
+ * forward kernel wrote (sae_conv_epilogue.act_mask, sae_fir_bias_act) and `out` is not touched (may be NULL). */
 int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_in, float* grad_bias,
                           int64_t size_x, int size_b, float alpha, float scale,
                           const float* noise, int64_t noise_div, float* grad_noise_weight,
-                          int round_tf32, void* stream);
+                          int round_tf32, const uint32_t* act_mask, void* stream);
 
 /* sae_upfirdn2d_separable (up = down = 1) followed by sae_bias_act_backward, in ONE pass:
  *   grad_in = FIR(grad) * (act_out > 0 ? 1 : alpha) * scale,   grad_bias[c] += sum over pixels of grad_in
@@ -105,7 +106,7 @@ int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_i
 int sae_fir_act_backward(const float* grad, const float* taps_y, const float* taps_x, const float* act_out,
                          float* grad_in, float* grad_bias, int64_t major, int in_h, int in_w, int minor,
                          int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                         float alpha, float scale, int round_tf32, void* stream);
+                         float alpha, float scale, int round_tf32, const uint32_t* act_mask, void* stream);
 
 /* sae_upfirdn2d_separable (up = down = 1) followed by NoiseInjection + bias + leaky-ReLU, in ONE pass:
  *   out = lrelu(FIR(x) + noise_weight * noise[pixel] + bias[c], alpha) * scale
@@ -117,7 +118,7 @@ int sae_fir_act_backward(const float* grad, const float* taps_y, const float* ta
 int sae_fir_bias_act(const float* x, const float* taps_y, const float* taps_x, const float* bias, const float* noise,
                      const float* noise_weight, float* out, int64_t major, int in_h, int in_w, int minor,
                      int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                     float alpha, float scale, int round_tf32, void* stream);
+                     float alpha, float scale, int round_tf32, uint32_t* act_mask, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * modulate — x_s[n,h,w,c] = x[n,h,w,c] * s[n,c]: the "input * style" step of
@@ -211,6 +212,10 @@ typedef struct sae_conv_epilogue {
     float   res_scale;
     int32_t act;           /* 1 = linear, 3 = leaky relu */
     int32_t round_tf32;
+    uint32_t* act_mask;    /* optional (tcgen05 kernels only, K % 32 == 0; NULL elsewhere): bit (i & 31) of word i >> 5 is set
+                              when element i of y (NHWC order) went through the positive branch of the activation.  The backward
+                              passes take it instead of the 4-byte-per-element output (sae_bias_act_backward, sae_fir_act_backward):
+                              12 -> 8.1 bytes per element on kernels that run at the HBM roofline. */
 } sae_conv_epilogue;
 
 /* impl: 0 = auto (tcgen05/TMA kernel when the shape qualifies, otherwise the generic

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsae_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-SAE_ABI_VERSION = 12
+SAE_ABI_VERSION = 13
 
 c_float_p = ctypes.c_void_p   # raw device pointers travel as integers
 c_stream = ctypes.c_void_p
@@ -31,7 +31,8 @@ class ConvEpilogue(ctypes.Structure):
     """Mirror of ``sae_conv_epilogue``."""
     _fields_ = [("bias", ctypes.c_void_p), ("noise", ctypes.c_void_p), ("noise_weight", ctypes.c_void_p),
                 ("residual", ctypes.c_void_p), ("alpha", ctypes.c_float), ("gain", ctypes.c_float),
-                ("res_scale", ctypes.c_float), ("act", ctypes.c_int32), ("round_tf32", ctypes.c_int32)]
+                ("res_scale", ctypes.c_float), ("act", ctypes.c_int32), ("round_tf32", ctypes.c_int32),
+                ("act_mask", ctypes.c_void_p)]
 
 
 # name -> (restype, argtypes); the test-suite checks that every one of these is exported.
@@ -53,13 +54,13 @@ SIGNATURES = {
                                           c_float_p, c_float_p, ctypes.c_int64, ctypes.c_int, c_stream]),
     "sae_bias_act_backward": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int64, ctypes.c_int,
                                              ctypes.c_float, ctypes.c_float, c_float_p, ctypes.c_int64, c_float_p,
-                                             ctypes.c_int, c_stream]),
+                                             ctypes.c_int, ctypes.c_void_p, c_stream]),
     "sae_fir_act_backward": (ctypes.c_int, [c_float_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_float_p, c_float_p,
                                             ctypes.c_int64] + [ctypes.c_int] * 9 + [ctypes.c_float, ctypes.c_float,
-                                                                                    ctypes.c_int, c_stream]),
+                                                                                    ctypes.c_int, ctypes.c_void_p, c_stream]),
     "sae_fir_bias_act": (ctypes.c_int, [c_float_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                         ctypes.c_int64] + [ctypes.c_int] * 9 + [ctypes.c_float, ctypes.c_float, ctypes.c_int,
-                                                                                c_stream]),
+                                                                                ctypes.c_void_p, c_stream]),
     "sae_modulate": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                     ctypes.c_int, c_stream]),
     "sae_modulate_backward": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int,

@@ -111,6 +111,8 @@ class CudaKernels:
         # makes that truncation exact and unbiased.  Set False for bit-exact fp32 results from the pointwise kernels.
         self.round_tf32 = True
         self.fused_fir_act = os.environ.get("SAE_FUSED_FIR_ACT", "1") != "0"
+        # activation bit masks next to the tensor-core convs' / the FIR + activation kernel's outputs (A/B: SAE_ACT_MASK=0)
+        self.act_masks = os.environ.get("SAE_ACT_MASK", "1") != "0"
 
     # ------------------------------------------------------------------ FIR
     def upfirdn2d(self, x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, taps=None):
@@ -152,7 +154,8 @@ class CudaKernels:
                   "sae_fused_bias_act")
         return out
 
-    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None):
+    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None, mask=None):
+        """mask: the activation bit mask a forward kernel wrote for ``out`` (``act_mask_of(out)``) — read instead of ``out``"""
         _need_cuda(grad_out, out, noise)
         c = out.shape[-1]
         gi = torch.empty_like(out)
@@ -160,11 +163,11 @@ class CudaKernels:
         gnw = torch.zeros(1, device=out.device, dtype=out.dtype) if noise is not None else None
         with torch.cuda.device(out.device):
             check(self.lib.sae_bias_act_backward(_ptr(grad_out), _ptr(out), _ptr(gi), _ptr(gb), out.numel(), c,
-                                                 alpha, scale, _ptr(noise), c, _ptr(gnw), int(self.round_tf32), _stream()),
+                                                 alpha, scale, _ptr(noise), c, _ptr(gnw), int(self.round_tf32), _ptr(mask), _stream()),
                   "sae_bias_act_backward")
         return gi, gb, gnw
 
-    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True):
+    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True, mask=None):
         """(FIR(grad) masked by the activation saved in ``act_out``, bias gradient) in one pass, or None when the shape is
         outside the fused kernel's configuration (the caller then runs upfirdn2d + bias_act_backward).
         grad [N,h,w,C]; act_out [N,oh,ow,C]; taps = (taps_y, taps_x) host factors; pad = (x0, x1, y0, y1)."""
@@ -182,7 +185,7 @@ class CudaKernels:
         tx = (ctypes.c_float * kw)(*taps[1])
         with torch.cuda.device(grad.device):
             rc = self.lib.sae_fir_act_backward(_ptr(grad), ty, tx, _ptr(act_out), _ptr(gi), _ptr(gb), n, h, w, c, kh, kw,
-                                               px0, px1, py0, py1, alpha, scale, int(self.round_tf32), _stream())
+                                               px0, px1, py0, py1, alpha, scale, int(self.round_tf32), _ptr(mask), _stream())
         if rc == -3:            # SAE_E_UNSUPPORTED: e.g. no TMA on this device
             return None
         check(rc, "sae_fir_act_backward")
@@ -200,14 +203,17 @@ class CudaKernels:
         if c % 32 != 0 or kh != kw or kh not in (3, 4) or oh < 8 or ow < 8 or n == 0 or x.data_ptr() % 16 != 0:
             return None
         out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
+        mask = self._new_act_mask(out, 3, True)
         ty = (ctypes.c_float * kh)(*taps[0])
         tx = (ctypes.c_float * kw)(*taps[1])
         with torch.cuda.device(x.device):
             rc = self.lib.sae_fir_bias_act(_ptr(x), ty, tx, _ptr(bias), _ptr(noise), _ptr(noise_weight), _ptr(out), n, h, w, c,
-                                           kh, kw, px0, px1, py0, py1, alpha, scale, int(self.round_tf32), _stream())
+                                           kh, kw, px0, px1, py0, py1, alpha, scale, int(self.round_tf32), _ptr(mask), _stream())
         if rc == -3:
             return None
         check(rc, "sae_fir_bias_act")
+        if mask is not None:
+            out._sae_act_mask = mask
         return out
 
     # ------------------------------------------------------------- modulate
@@ -325,8 +331,15 @@ class CudaKernels:
         return out
 
     # ----------------------------------------------------------------- conv
+    def _new_act_mask(self, y, act, tensor_core_kernel):
+        """1 bit per element of an activation output ``y`` [..., C] (C % 32 == 0), written by the kernel that produces y and read
+        by the activation's backward instead of y itself (sae_conv_epilogue.act_mask); None where no kernel would write it"""
+        if act != 3 or not tensor_core_kernel or not self.act_masks or y.shape[-1] % 32 != 0 or y.numel() == 0:
+            return None
+        return torch.empty(y.numel() // 32, device=y.device, dtype=torch.int32)
+
     def _epi(self, bias=None, act=1, alpha=0.2, gain=1.0, noise=None, noise_weight=None, residual=None,
-             res_scale=1.0, round_tf32=None):
+             res_scale=1.0, round_tf32=None, act_mask=None):
         _need_cuda(bias, noise, noise_weight, residual)
         e = ConvEpilogue()
         e.bias = bias.data_ptr() if bias is not None else None
@@ -335,6 +348,7 @@ class CudaKernels:
         e.residual = residual.data_ptr() if residual is not None else None
         e.alpha, e.gain, e.res_scale, e.act = alpha, gain, res_scale, act
         e.round_tf32 = int(self.round_tf32 if round_tf32 is None else round_tf32)
+        e.act_mask = act_mask.data_ptr() if act_mask is not None else None
         return e
 
     def conv_fprop(self, x, w_krsc, g, impl=None, prepared=False, **epi):
@@ -345,10 +359,16 @@ class CudaKernels:
         assert tuple(x.shape) == (g.N, g.H, g.W, g.C) and tuple(w_krsc.shape) == (g.K, g.R, g.S, g.C), \
             (tuple(x.shape), tuple(w_krsc.shape), g.key())
         y = torch.empty((g.N, g.P, g.Q, g.K), device=x.device, dtype=x.dtype)
-        e = self._epi(**epi)
+        impl = self.conv_impl if impl is None else impl
+        mask = None
+        if epi.get("act", 1) == 3 and self.act_masks:
+            mask = self._new_act_mask(y, 3, impl == 2 or (impl == 0 and self.conv_impl_for(g, 0) == 2))
+        e = self._epi(act_mask=mask, **epi)
         with torch.cuda.device(x.device):
-            check(self.lib.sae_conv2d_fprop(_ptr(x), _ptr(w_krsc), _ptr(y), ctypes.byref(g), ctypes.byref(e),
-                                            self.conv_impl if impl is None else impl, _stream()), "sae_conv2d_fprop")
+            check(self.lib.sae_conv2d_fprop(_ptr(x), _ptr(w_krsc), _ptr(y), ctypes.byref(g), ctypes.byref(e), impl, _stream()),
+                  "sae_conv2d_fprop")
+        if mask is not None:
+            y._sae_act_mask = mask
         return y
 
     def conv_dgrad(self, dy, w_krsc, g, impl=None, w_crsk=None, **epi):
@@ -397,10 +417,13 @@ class CudaKernels:
         """x [N,H,W,C], per-sample filters [N,K,R,S,C] -> y [N,P,Q,K]"""
         _need_cuda(x, w_nkrsc)
         y = torch.empty((g.N, g.P, g.Q, g.K), device=x.device, dtype=x.dtype)
-        e = self._epi(**epi)
+        mask = self._new_act_mask(y, epi.get("act", 1), True)          # only the tcgen05 kernel implements per-sample filters
+        e = self._epi(act_mask=mask, **epi)
         with torch.cuda.device(x.device):
             check(self.lib.sae_conv2d_fprop_per_sample(_ptr(x), _ptr(w_nkrsc), _ptr(y), ctypes.byref(g), ctypes.byref(e), _stream()),
                   "sae_conv2d_fprop_per_sample")
+        if mask is not None:
+            y._sae_act_mask = mask
         return y
 
     def conv_dgrad_per_sample(self, dy, w_ncrsk, g, **epi):
@@ -509,6 +532,13 @@ class CudaKernels:
 
 
 _kernels = None
+
+
+def act_mask_of(t):
+    """the activation bit mask the producing kernel left next to ``t`` (None: the backward reads ``t`` itself).  The mask is a
+    Python attribute of the tensor object the kernel wrapper returned: callers that hand ``t`` to autograd (outputs of a
+    Function come back as new objects) read it right after the forward call and keep it in their ctx."""
+    return getattr(t, "_sae_act_mask", None) if t is not None else None
 
 
 def kernels():

@@ -67,16 +67,17 @@ struct EpiParams {
     const float* noise_weight;
     float alpha, gain, res_scale;
     int act, round_tf32;
+    uint32_t* act_mask;   // optional: sign bits of the activation output, 1 bit per element (see sae_conv_epilogue)
 };
 
 inline EpiParams make_epi(const sae_conv_epilogue* e) {
     EpiParams p;
     p.bias = nullptr; p.noise = nullptr; p.residual = nullptr; p.noise_weight = nullptr;
-    p.nw = 0.f; p.alpha = 0.2f; p.gain = 1.f; p.res_scale = 1.f; p.act = 1; p.round_tf32 = 0;
+    p.nw = 0.f; p.alpha = 0.2f; p.gain = 1.f; p.res_scale = 1.f; p.act = 1; p.round_tf32 = 0; p.act_mask = nullptr;
     if (e) {
         p.bias = e->bias; p.noise = e->noise; p.noise_weight = e->noise_weight;
         p.residual = e->residual; p.alpha = e->alpha; p.gain = e->gain;
-        p.res_scale = e->res_scale; p.act = e->act; p.round_tf32 = e->round_tf32;
+        p.res_scale = e->res_scale; p.act = e->act; p.round_tf32 = e->round_tf32; p.act_mask = e->act_mask;
     }
     return p;
 }

@@ -84,15 +84,20 @@ struct TcParams {
 // TF32 rounding on the 32 values a thread read from TMEM, then the 128-byte row into the chunk's staging tile
 // ([128 rows][128 bytes], 16-byte pieces XOR-swizzled by (row & 7): the layout the SWIZZLE_128B output tensor map reads).
 __device__ __forceinline__ void tc_epilogue_math(float (&v)[32], const EpiParams& e, int colb, int64_t pixel, int ncol, bool valid, float nz) {
+    uint32_t pos = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         float t = v[j];
         if (e.bias) t += __ldg(e.bias + colb + j);
         t += nz;
+        pos |= (t > 0.f ? 1u : 0u) << j;
         if (e.act == 3) t = t > 0.f ? t : t * e.alpha;
         t *= e.gain;
         v[j] = t;
     }
+    // activation bit mask: the thread holds the 32 consecutive channels of one pixel = exactly one word.  The backward passes
+    // then read 1 bit instead of 32 per element to learn the leaky-ReLU branch (sae_bias_act_backward, sae_fir_act_backward)
+    if (e.act_mask && valid) e.act_mask[(pixel * ncol + colb) >> 5] = pos;
     if (e.residual && valid) {
         const float4* r4 = reinterpret_cast<const float4*>(e.residual + pixel * ncol + colb);
 #pragma unroll

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(256)
 bias_act_bwd_kernel(const float* __restrict__ go, const float* __restrict__ outp, float* __restrict__ gi,
                     float* __restrict__ gb, int64_t size_v, int cv, int64_t stride_v,
                     float alpha, float scale,
-                    const float* __restrict__ noise, int64_t noise_div, float* __restrict__ gnw, int round_tf32) {
+                    const float* __restrict__ noise, int64_t noise_div, float* __restrict__ gnw, int round_tf32,
+                    const uint32_t* __restrict__ act_mask) {
     extern __shared__ float sacc[];   // [cv * VEC] (+1 slot for the noise-weight grad)
     const int C = cv * VEC;
     for (int i = threadIdx.x; i <= C; i += blockDim.x) sacc[i] = 0.f;
@@ -94,9 +95,15 @@ bias_act_bwd_kernel(const float* __restrict__ go, const float* __restrict__ outp
             float g[VEC], o[VEC];
             if (VEC == 4) {
                 float4 t = ldg_stream(reinterpret_cast<const float4*>(go) + i);
-                float4 q = ldg_stream(reinterpret_cast<const float4*>(outp) + i);
                 g[0] = t.x; g[1 % VEC] = t.y; g[2 % VEC] = t.z; g[3 % VEC] = t.w;
-                o[0] = q.x; o[1 % VEC] = q.y; o[2 % VEC] = q.z; o[3 % VEC] = q.w;
+                if (act_mask) {
+                    // 1 bit per element instead of the 4-byte activation output: elements 4i .. 4i+3 are bits (4i & 31) .. of word i >> 3
+                    const uint32_t wd = __ldg(act_mask + (i >> 3)) >> (((uint32_t)i & 7u) * 4u);
+                    o[0] = (wd & 1u) ? 1.f : 0.f; o[1 % VEC] = (wd & 2u) ? 1.f : 0.f; o[2 % VEC] = (wd & 4u) ? 1.f : 0.f; o[3 % VEC] = (wd & 8u) ? 1.f : 0.f;
+                } else {
+                    float4 q = ldg_stream(reinterpret_cast<const float4*>(outp) + i);
+                    o[0] = q.x; o[1 % VEC] = q.y; o[2 % VEC] = q.z; o[3 % VEC] = q.w;
+                }
             } else {
                 g[0] = go[i]; o[0] = outp[i];
             }
@@ -514,15 +521,17 @@ extern "C" int sae_fused_bias_act(const float* x, const float* bias, const float
 extern "C" int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_in, float* grad_bias,
                                      int64_t size_x, int size_b, float alpha, float scale,
                                      const float* noise, int64_t noise_div, float* grad_noise_weight,
-                                     int round_tf32, void* stream) {
+                                     int round_tf32, const uint32_t* act_mask, void* stream) {
     if (size_x == 0) return SAE_OK;
-    if (!grad_out || !out || !grad_in || size_b <= 0 || size_x % size_b != 0)
+    if (!grad_out || (!out && !act_mask) || !grad_in || size_b <= 0 || size_x % size_b != 0)
         return fail(SAE_E_INVALID, "bias_act_backward: bad arguments (size_x %% size_b must be 0)");
+    if (act_mask && size_b % 32 != 0) return fail(SAE_E_INVALID, "bias_act_backward: the activation bit mask needs a channel count that is a multiple of 32");
     if (noise && (!grad_noise_weight || noise_div <= 0)) return fail(SAE_E_INVALID, "bias_act_backward: noise needs grad slot");
     if (size_b > 12000) return fail(SAE_E_UNSUPPORTED, "bias_act_backward: more than 12000 channels");
     cudaStream_t st = (cudaStream_t)stream;
     uintptr_t al = reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(grad_in);
     bool vec = (size_b % 4 == 0) && (al % 16 == 0) && (!noise || noise_div % 4 == 0);
+    if (act_mask && !vec) return fail(SAE_E_INVALID, "bias_act_backward: the activation bit mask needs the vectorised path (16-byte aligned pointers)");
     const int V = vec ? 4 : 1;
     const int cv = size_b / V;
     const int64_t size_v = size_x / V;
@@ -539,11 +548,11 @@ extern "C" int sae_bias_act_backward(const float* grad_out, const float* out, fl
     if (vec) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(bias_act_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         bias_act_bwd_kernel<4><<<blocks, 256, smem, st>>>(grad_out, out, grad_in, grad_bias, size_v, cv, stride, alpha, scale,
-                                                         noise, noise_div, grad_noise_weight, round_tf32);
+                                                         noise, noise_div, grad_noise_weight, round_tf32, act_mask);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(bias_act_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         bias_act_bwd_kernel<1><<<blocks, 256, smem, st>>>(grad_out, out, grad_in, grad_bias, size_v, cv, stride, alpha, scale,
-                                                         noise, noise_div, grad_noise_weight, round_tf32);
+                                                         noise, noise_div, grad_noise_weight, round_tf32, nullptr);
     }
     return check_launch("bias_act_backward");
 }

@@ -255,6 +255,8 @@ struct FirMask {
     const float* bias;        // [minor] or null
     const float* noise;       // one value per output pixel, or null
     const float* noise_weight;
+    // activation bit mask, 1 bit per output element: read instead of act_out (MODE 1) / written next to the output (MODE 2)
+    uint32_t* act_mask;
 };
 
 // MODE: 0 plain FIR, 1 = MASK (activation backward applied to the result), 2 = ACT (noise + bias + leaky-ReLU applied to it)
@@ -331,7 +333,13 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ ou
         const bool inside = ox < p.out_w && oy0 + r0 + r < p.out_h;
         if (MASK) {
             if (inside) {
-                const float4 o = ldg_stream(reinterpret_cast<const float4*>(mk.act_out + off0 + (int64_t)r * p.out_w * p.minor));
+                float4 o;
+                if (mk.act_mask) {
+                    const uint32_t wd = __ldg(mk.act_mask + ((off0 + (int64_t)r * p.out_w * p.minor) >> 5)) >> (cvec * 4);
+                    o = make_float4((wd & 1u) ? 1.f : 0.f, (wd & 2u) ? 1.f : 0.f, (wd & 4u) ? 1.f : 0.f, (wd & 8u) ? 1.f : 0.f);
+                } else {
+                    o = ldg_stream(reinterpret_cast<const float4*>(mk.act_out + off0 + (int64_t)r * p.out_w * p.minor));
+                }
                 acc.x *= (o.x > 0.f ? mk.scale : mk.alpha * mk.scale); acc.y *= (o.y > 0.f ? mk.scale : mk.alpha * mk.scale);
                 acc.z *= (o.z > 0.f ? mk.scale : mk.alpha * mk.scale); acc.w *= (o.w > 0.f ? mk.scale : mk.alpha * mk.scale);
                 bsum.x += acc.x; bsum.y += acc.y; bsum.z += acc.z; bsum.w += acc.w;
@@ -341,6 +349,12 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ ou
             float nz = 0.f;
             if (mk.noise && inside) nz = nw * __ldg(mk.noise + ((int64_t)n * p.out_h + oy0 + r0 + r) * p.out_w + ox);
             acc.x += bias4.x + nz; acc.y += bias4.y + nz; acc.z += bias4.z + nz; acc.w += bias4.w + nz;
+            if (mk.act_mask) {
+                // the 8 lanes cvec = 0..7 of a pixel hold its 32 channels: OR their 4 sign bits into the pixel's mask word
+                uint32_t bits = ((acc.x > 0.f ? 1u : 0u) | (acc.y > 0.f ? 2u : 0u) | (acc.z > 0.f ? 4u : 0u) | (acc.w > 0.f ? 8u : 0u)) << (cvec * 4);
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 1); bits |= __shfl_xor_sync(0xffffffffu, bits, 2); bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+                if (inside && cvec == 0) mk.act_mask[(off0 + (int64_t)r * p.out_w * p.minor) >> 5] = bits;
+            }
             acc.x = (acc.x > 0.f ? acc.x : acc.x * mk.alpha) * mk.scale; acc.y = (acc.y > 0.f ? acc.y : acc.y * mk.alpha) * mk.scale;
             acc.z = (acc.z > 0.f ? acc.z : acc.z * mk.alpha) * mk.scale; acc.w = (acc.w > 0.f ? acc.w : acc.w * mk.alpha) * mk.scale;
         }
@@ -558,10 +572,10 @@ extern "C" int sae_upfirdn2d_separable(const float* input, const float* taps_y, 
 extern "C" int sae_fir_act_backward(const float* grad, const float* taps_y, const float* taps_x, const float* act_out,
                                     float* grad_in, float* grad_bias, int64_t major, int in_h, int in_w, int minor,
                                     int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                                    float alpha, float scale, int round_tf32, void* stream) {
+                                    float alpha, float scale, int round_tf32, const uint32_t* act_mask, void* stream) {
     using namespace sae;
     if (major == 0) return SAE_OK;
-    if (!grad || !taps_y || !taps_x || !act_out || !grad_in) return fail(SAE_E_INVALID, "fir_act_backward: null pointer");
+    if (!grad || !taps_y || !taps_x || (!act_out && !act_mask) || !grad_in) return fail(SAE_E_INVALID, "fir_act_backward: null pointer");
     if ((kernel_h != 3 && kernel_h != 4) || kernel_w != kernel_h) return fail(SAE_E_UNSUPPORTED, "fir_act_backward: taps must be 3 or 4, square");
     if (minor % 32 != 0 || ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(grad_in) | reinterpret_cast<uintptr_t>(act_out)) & 15) != 0)
         return fail(SAE_E_UNSUPPORTED, "fir_act_backward: needs minor %% 32 == 0 and 16-byte aligned pointers");
@@ -580,7 +594,7 @@ extern "C" int sae_fir_act_backward(const float* grad, const float* taps_y, cons
     for (int i = 0; i < kernel_h; ++i) t.y[i] = taps_y[kernel_h - 1 - i];
     for (int i = 0; i < kernel_w; ++i) t.x[i] = taps_x[kernel_w - 1 - i];
     FirMask mk;
-    mk.act_out = act_out; mk.grad_bias = grad_bias; mk.alpha = alpha; mk.scale = scale;
+    mk.act_out = act_out; mk.grad_bias = grad_bias; mk.alpha = alpha; mk.scale = scale; mk.act_mask = const_cast<uint32_t*>(act_mask);
     cudaStream_t st = (cudaStream_t)stream;
     mk.bias = nullptr; mk.noise = nullptr; mk.noise_weight = nullptr;
     int rc = kernel_h == 3 ? launch_tma<3, 3, 1>(grad, grad_in, p, t, st, mk) : launch_tma<4, 4, 1>(grad, grad_in, p, t, st, mk);
@@ -596,7 +610,7 @@ extern "C" int sae_fir_act_backward(const float* grad, const float* taps_y, cons
 extern "C" int sae_fir_bias_act(const float* x, const float* taps_y, const float* taps_x, const float* bias, const float* noise,
                                 const float* noise_weight, float* out, int64_t major, int in_h, int in_w, int minor,
                                 int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                                float alpha, float scale, int round_tf32, void* stream) {
+                                float alpha, float scale, int round_tf32, uint32_t* act_mask, void* stream) {
     using namespace sae;
     if (major == 0) return SAE_OK;
     if (!x || !taps_y || !taps_x || !out) return fail(SAE_E_INVALID, "fir_bias_act: null pointer");
@@ -619,7 +633,7 @@ extern "C" int sae_fir_bias_act(const float* x, const float* taps_y, const float
     for (int i = 0; i < kernel_h; ++i) t.y[i] = taps_y[kernel_h - 1 - i];
     for (int i = 0; i < kernel_w; ++i) t.x[i] = taps_x[kernel_w - 1 - i];
     FirMask mk;
-    mk.act_out = nullptr; mk.grad_bias = nullptr; mk.alpha = alpha; mk.scale = scale;
+    mk.act_out = nullptr; mk.grad_bias = nullptr; mk.alpha = alpha; mk.scale = scale; mk.act_mask = act_mask;
     mk.bias = bias; mk.noise = noise; mk.noise_weight = noise_weight;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = kernel_h == 3 ? launch_tma<3, 3, 2>(x, out, p, t, st, mk) : launch_tma<4, 4, 2>(x, out, p, t, st, mk);

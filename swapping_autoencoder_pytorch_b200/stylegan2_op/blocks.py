@@ -110,16 +110,17 @@ class FirSpec:
         assert out.shape[1] == in_h and out.shape[2] == in_w, (tuple(out.shape), in_h, in_w)
         return out
 
-    def adjoint_into_activation(self, k, g, act_out, slope, gain, want_bias):
+    def adjoint_into_activation(self, k, g, act_out, slope, gain, want_bias, mask=None):
         """``bias_act_backward(adjoint(g), act_out)`` — in one kernel when the fused FIR + activation-backward kernel
-        takes the shape (the blurred gradient then never exists in HBM), as two launches otherwise"""
+        takes the shape (the blurred gradient then never exists in HBM), as two launches otherwise.
+        mask: the activation bit mask of ``act_out`` if its producer wrote one"""
         in_h, in_w = act_out.shape[1], act_out.shape[2]
         if self.down == 1 and self.taps is not None:
             hit = k.fir_act_backward(g, _flip_taps(self.taps), act_out, self._adjoint_pad(g, in_h, in_w), slope, gain,
-                                     want_bias=want_bias)
+                                     want_bias=want_bias, mask=mask)
             if hit is not None:
                 return hit
-        gi, gb, _ = k.bias_act_backward(self.adjoint(k, g, in_h, in_w), act_out, slope, gain, want_bias=want_bias)
+        gi, gb, _ = k.bias_act_backward(self.adjoint(k, g, in_h, in_w), act_out, slope, gain, want_bias=want_bias, mask=mask)
         return gi, gb
 
 
@@ -142,6 +143,7 @@ class _FirNoiseBiasAct(Function):
         if out is None:
             out = k.bias_act(spec.forward(k, xh), bias.contiguous(), None, 3, 0, slope, gain, noise=noise_flat, noise_weight=nw)
         ctx.spec, ctx.cfg = spec, (slope, gain, tuple(noise.shape) if noise is not None else None, xh.shape[1], xh.shape[2])
+        ctx.act_mask = backend.act_mask_of(out)
         ctx.save_for_backward(out, noise_flat, nw)
         return _nchw(out)
 
@@ -151,7 +153,7 @@ class _FirNoiseBiasAct(Function):
         out, noise_flat, nw = ctx.saved_tensors
         slope, gain, noise_shape, in_h, in_w = ctx.cfg
         k = backend.kernels()
-        gi, gb, gnw = k.bias_act_backward(_nhwc(dy), out, slope, gain, want_bias=True, noise=noise_flat)
+        gi, gb, gnw = k.bias_act_backward(_nhwc(dy), out, slope, gain, want_bias=True, noise=noise_flat, mask=ctx.act_mask)
         dx = _nchw(ctx.spec.adjoint(k, gi, in_h, in_w)) if ctx.needs_input_grad[0] else None
         g_noise = None
         if noise_flat is not None and ctx.needs_input_grad[2]:
@@ -186,17 +188,18 @@ class _ResBlockDataGrad(Function):
     gradient inside ``data_gradients_only()``.  Its backward is the closed form in the module docstring."""
 
     @staticmethod
-    def forward(ctx, dy, w1, w2, ws, o1, o2, w1k, w1t, w2k, w2t, wsk, wst, spec, geoms):
+    def forward(ctx, dy, w1, w2, ws, o1, o2, w1k, w1t, w2k, w2t, wsk, wst, spec, geoms, masks):
         k = backend.kernels()
         g1, g2, gs = geoms
+        m1, m2 = masks
         dyh = _nhwc(dy)
-        gi2, _, _ = k.bias_act_backward(dyh, o2, spec.slope, spec.gain2, want_bias=False)
+        gi2, _, _ = k.bias_act_backward(dyh, o2, spec.slope, spec.gain2, want_bias=False, mask=m2)
         dh = k.conv_dgrad(dyh, wsk, gs, w_crsk=wst)
         dxs = spec.blur_s.adjoint(k, dh, g1.H, g1.W)
         dbl = k.conv_dgrad(gi2, w2k, g2, w_crsk=w2t)
-        gi1, _ = spec.blur2.adjoint_into_activation(k, dbl, o1, spec.slope, spec.gain1, False)
+        gi1, _ = spec.blur2.adjoint_into_activation(k, dbl, o1, spec.slope, spec.gain1, False, mask=m1)
         dx = k.conv_dgrad(gi1, w1k, g1, w_crsk=w1t, residual=dxs, res_scale=1.0)
-        ctx.spec, ctx.geoms = spec, geoms
+        ctx.spec, ctx.geoms, ctx.masks = spec, geoms, masks
         ctx.save_for_backward(dyh, gi2, gi1, o1, o2, w1k, w2k, wsk)
         return _nchw(dx)
 
@@ -206,6 +209,7 @@ class _ResBlockDataGrad(Function):
         dyh, gi2, gi1, o1, o2, w1k, w2k, wsk = ctx.saved_tensors
         spec = ctx.spec
         g1, g2, gs = ctx.geoms
+        m1, m2 = ctx.masks
         k = backend.kernels()
         need = ctx.needs_input_grad
         vh = _nhwc(v)
@@ -213,19 +217,19 @@ class _ResBlockDataGrad(Function):
         r = None
         if need[0] or need[2]:
             p1 = k.conv_fprop(vh, w1k, g1, prepared=True)
-            q1, _, _ = k.bias_act_backward(p1, o1, spec.slope, spec.gain1, want_bias=False)
+            q1, _, _ = k.bias_act_backward(p1, o1, spec.slope, spec.gain1, want_bias=False, mask=m1)
             r = spec.blur2.forward(k, q1)
         hv = spec.blur_s.forward(k, vh) if (need[0] or need[3]) else None
         d_dy = None
         if need[0]:
             p2 = k.conv_fprop(r, w2k, g2, prepared=True)
-            m2, _, _ = k.bias_act_backward(p2, o2, spec.slope, spec.gain2, want_bias=False)
-            d_dy = _nchw(k.conv_fprop(hv, wsk, gs, prepared=True, residual=m2, res_scale=1.0))
+            t2, _, _ = k.bias_act_backward(p2, o2, spec.slope, spec.gain2, want_bias=False, mask=m2)
+            d_dy = _nchw(k.conv_fprop(hv, wsk, gs, prepared=True, residual=t2, res_scale=1.0))
         unprep = k.filter_unprep
         dw1 = unprep(k.conv_wgrad(gi1, vh, g1), spec.s1) if need[1] else None
         dw2 = unprep(k.conv_wgrad(gi2, r, g2), spec.s2) if need[2] else None
         dws = unprep(k.conv_wgrad(dyh, hv, gs), spec.ss) if need[3] else None
-        return (d_dy, dw1, dw2, dws) + (None,) * 10
+        return (d_dy, dw1, dw2, dws) + (None,) * 11
 
 
 class _ResBlockFused(Function):
@@ -248,6 +252,7 @@ class _ResBlockFused(Function):
         assert (gs.P, gs.Q) == (g2.P, g2.Q), ("ResBlock branches disagree", gs.key(), g2.key())
         y = k.conv_fprop(h, wsk, gs, prepared=True, residual=o2, res_scale=1.0)
         ctx.spec, ctx.geoms = spec, (g1, g2, gs)
+        ctx.masks = (backend.act_mask_of(o1), backend.act_mask_of(o2))        # activation bit masks written by the two convs
         ctx.save_for_backward(x, w1, b1, w2, b2, ws, o1, bl, o2, h, w1k, w1t, w2k, w2t, wsk, wst)
         return _nchw(y)
 
@@ -260,7 +265,7 @@ class _ResBlockFused(Function):
             # R1: the recorded backward is asked for dx only; closed-form double backward (module docstring)
             dx = None
             if need[0]:
-                dx = _ResBlockDataGrad.apply(dy, w1, w2, ws, o1, o2, w1k, w1t, w2k, w2t, wsk, wst, spec, ctx.geoms)
+                dx = _ResBlockDataGrad.apply(dy, w1, w2, ws, o1, o2, w1k, w1t, w2k, w2t, wsk, wst, spec, ctx.geoms, ctx.masks)
             return (dx, None, None, None, None, None, None)
         if torch.is_grad_enabled():
             # the backward is being recorded by a general caller: differentiate the per-operator composition instead
@@ -271,9 +276,10 @@ class _ResBlockFused(Function):
             return tuple(next(got) if nd else None for nd in need[:6]) + (None,)
         k = backend.kernels()
         g1, g2, gs = ctx.geoms
+        m1, m2 = ctx.masks
         dyh = _nhwc(dy)
         need_x, need_w = need[0], (need[1] or need[3] or need[5])
-        gi2, gb2, _ = k.bias_act_backward(dyh, o2, spec.slope, spec.gain2, want_bias=need[4])
+        gi2, gb2, _ = k.bias_act_backward(dyh, o2, spec.slope, spec.gain2, want_bias=need[4], mask=m2)
         # skip branch: 1x1 conv <- decimating blur
         dws = k.conv_wgrad(dyh, h, gs) if need[5] else None
         dxs = None
@@ -285,7 +291,7 @@ class _ResBlockFused(Function):
         dx = gi1 = gb1 = dw1 = None
         if need_x or need[1] or need[2]:
             dbl = k.conv_dgrad(gi2, w2k, g2, w_crsk=w2t)
-            gi1, gb1 = spec.blur2.adjoint_into_activation(k, dbl, o1, spec.slope, spec.gain1, need[2])
+            gi1, gb1 = spec.blur2.adjoint_into_activation(k, dbl, o1, spec.slope, spec.gain1, need[2], mask=m1)
             if need[1]:
                 dw1 = k.conv_wgrad(gi1, _nhwc(x), g1)
             if need_x:

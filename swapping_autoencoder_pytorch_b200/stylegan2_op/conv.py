@@ -184,9 +184,10 @@ class _ConvBiasAct(Function):
 
     @staticmethod
     def forward(ctx, x, w, wt, bias, g, negative_slope, gain):
-        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g), prepared=wt is not None,
-                                                 bias=bias.contiguous(), act=3, alpha=negative_slope, gain=gain))
-        ctx.g, ctx.cfg = g, (negative_slope, gain)
+        y = backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, impl=_impl(g), prepared=wt is not None,
+                                         bias=bias.contiguous(), act=3, alpha=negative_slope, gain=gain)
+        out = _nchw(y)
+        ctx.g, ctx.cfg, ctx.act_mask = g, (negative_slope, gain), backend.act_mask_of(y)
         ctx.save_for_backward(x, w, wt, out)
         return out
 
@@ -197,7 +198,7 @@ class _ConvBiasAct(Function):
         # out.detach(): the mask is piecewise constant (the masked-gradient Function returns no gradient for it), but an
         # attached ``out`` would keep this node's own forward graph reachable from a recorded backward, and the engine
         # would then run a complete extra backward of the network on materialised zeros during R1's second backward
-        gi, gb = FusedLeakyReLUFunctionBackward.apply(dy, out.detach(), *ctx.cfg)
+        gi, gb = FusedLeakyReLUFunctionBackward.apply(dy, out.detach(), *ctx.cfg, ctx.act_mask)
         dx = _ConvDgrad.apply(gi, w, wt, ctx.g) if ctx.needs_input_grad[0] else None
         dw = _ConvWgrad.apply(gi, x, ctx.g) if _want_wgrad(ctx, 1) else None
         return dx, dw, None, gb, None, None, None
@@ -210,10 +211,11 @@ class _ConvNoiseBiasAct(Function):
     @staticmethod
     def forward(ctx, x, w, wt, noise, noise_weight, bias, g, negative_slope, gain):
         noise_flat = noise.reshape(-1).contiguous()
-        out = _nchw(backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, prepared=wt is not None, bias=bias.contiguous(),
-                                                 act=3, alpha=negative_slope, gain=gain, noise=noise_flat,
-                                                 noise_weight=noise_weight.contiguous()))
-        ctx.g, ctx.cfg = g, (negative_slope, gain, tuple(noise.shape))
+        y = backend.kernels().conv_fprop(_nhwc(x), w.contiguous(), g, prepared=wt is not None, bias=bias.contiguous(),
+                                         act=3, alpha=negative_slope, gain=gain, noise=noise_flat,
+                                         noise_weight=noise_weight.contiguous())
+        out = _nchw(y)
+        ctx.g, ctx.cfg, ctx.act_mask = g, (negative_slope, gain, tuple(noise.shape)), backend.act_mask_of(y)
         ctx.save_for_backward(x, w, wt, out, noise_flat, noise_weight)
         return out
 
@@ -223,7 +225,8 @@ class _ConvNoiseBiasAct(Function):
         x, w, wt, out, noise_flat, noise_weight = ctx.saved_tensors
         negative_slope, gain, noise_shape = ctx.cfg
         k = backend.kernels()
-        gi, gb, gnw = k.bias_act_backward(_nhwc(dy), _nhwc(out), negative_slope, gain, want_bias=True, noise=noise_flat)
+        gi, gb, gnw = k.bias_act_backward(_nhwc(dy), _nhwc(out), negative_slope, gain, want_bias=True, noise=noise_flat,
+                                          mask=ctx.act_mask)
         dx = _nchw(k.conv_dgrad(gi, w.contiguous(), ctx.g, w_crsk=wt)) if ctx.needs_input_grad[0] else None
         dw = k.conv_wgrad(gi, _nhwc(x), ctx.g) if ctx.needs_input_grad[1] else None
         g_noise = None
@@ -436,6 +439,7 @@ class _ModulatedConv(Function):
                 noise_flat = noise.reshape(-1).contiguous()
                 epi.update(noise=noise_flat, noise_weight=noise_weight.contiguous())
         out = k.conv_fprop_per_sample(xh, w_n, g, **epi)
+        ctx.act_mask = backend.act_mask_of(out)
         ctx.g, ctx.cfg = g, (act, negative_slope, gain, tuple(noise.shape) if noise is not None else None)
         ctx.save_for_backward(xh, sc, w, out if act else None, noise_flat, noise_weight if noise is not None else None)
         return _nchw(out)
@@ -448,7 +452,7 @@ class _ModulatedConv(Function):
         k = backend.kernels()
         gi, gb, gnw = _nhwc(dy), None, None
         if act:
-            gi, gb, gnw = k.bias_act_backward(gi, out, negative_slope, gain, want_bias=True, noise=noise_flat)
+            gi, gb, gnw = k.bias_act_backward(gi, out, negative_slope, gain, want_bias=True, noise=noise_flat, mask=ctx.act_mask)
         dx = None
         if ctx.needs_input_grad[0]:
             _, w_nt = k.filter_modulate(w.contiguous(), sc, want_krsc=False, want_crsk=True)

@@ -23,11 +23,13 @@ def _uncl(t):
 
 class FusedLeakyReLUFunctionBackward(Function):
     @staticmethod
-    def forward(ctx, grad_output, out, negative_slope, scale):
+    def forward(ctx, grad_output, out, negative_slope, scale, mask=None):
+        """mask: activation bit mask of ``out`` if its producer wrote one (backend.act_mask_of) — the first-order pass then reads
+        1 bit per element instead of ``out``; the second-order pass below keeps using ``out``"""
         ctx.save_for_backward(out)
         ctx.cfg = (negative_slope, scale)
         gi, gb, _ = backend.kernels().bias_act_backward(_cl(grad_output), _cl(out), negative_slope, scale,
-                                                        want_bias=True)
+                                                        want_bias=True, mask=mask)
         return _uncl(gi), gb
 
     @staticmethod
@@ -39,7 +41,7 @@ class FusedLeakyReLUFunctionBackward(Function):
             gradgrad_input = torch.zeros_like(out)
         gg = backend.kernels().bias_act(_cl(gradgrad_input), gradgrad_bias.contiguous() if gradgrad_bias is not None else None,
                                         _cl(out), 3, 1, negative_slope, scale)
-        return _uncl(gg), None, None, None
+        return _uncl(gg), None, None, None, None
 
 
 class FusedLeakyReLUFunction(Function):

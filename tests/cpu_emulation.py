@@ -60,7 +60,7 @@ class EmulatedKernels:
             t = torch.zeros_like(t)
         return t * scale
 
-    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None):
+    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None, mask=None):
         gi = torch.where(out > 0, grad_out, grad_out * alpha) * scale
         c = out.shape[-1]
         gb = gi.reshape(-1, c).sum(0) if want_bias else None
@@ -69,7 +69,7 @@ class EmulatedKernels:
             gnw = (gi.reshape(-1, c).sum(1) * noise.reshape(-1)).sum().reshape(1)
         return gi, gb, gnw
 
-    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True):
+    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True, mask=None):
         kernel = torch.outer(torch.tensor(taps[0]), torch.tensor(taps[1])).to(grad.dtype)
         d = self.upfirdn2d(grad, kernel, 1, 1, 1, 1, *pad)
         gi, gb, _ = self.bias_act_backward(d, act_out, alpha, scale, want_bias=want_bias)

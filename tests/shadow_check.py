@@ -63,12 +63,18 @@ class ShadowKernels:
         return self._both("bias_act", "x%s act%d grad%d noise%s" % (tuple(x.shape), act, grad, noise is not None),
                           (x, bias, ref, act, grad, alpha, scale), dict(noise=noise, noise_weight=noise_weight))
 
-    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None):
-        return self._both("bias_act_backward", "x%s noise%s" % (tuple(out.shape), noise is not None),
-                          (grad_out, out, alpha, scale), dict(want_bias=want_bias, noise=noise))
+    def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None, mask=None):
+        # (the activation bit mask goes to the real kernel only; the emulation reads ``out``: a wrong mask shows up as an error)
+        res = self.real.bias_act_backward(grad_out, out, alpha, scale, want_bias=want_bias, noise=noise, mask=mask)
+        ref = self.emu.bias_act_backward(_cpu(grad_out), _cpu(out), alpha, scale, want_bias=want_bias, noise=_cpu(noise))
+        for i, (o, r) in enumerate(zip(res, ref)):
+            if o is not None:
+                self.log.append(("bias_act_backward", "x%s noise%s mask%s out%d" % (tuple(out.shape), noise is not None, mask is not None, i),
+                                 _err(o, r)))
+        return res
 
-    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True):
-        out = self.real.fir_act_backward(grad, taps, act_out, pad, alpha, scale, want_bias=want_bias)
+    def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True, mask=None):
+        out = self.real.fir_act_backward(grad, taps, act_out, pad, alpha, scale, want_bias=want_bias, mask=mask)
         if out is None:           # shape outside the fused kernel: the caller issues the two separate (shadowed) calls
             return None
         ref = self.emu.fir_act_backward(_cpu(grad), taps, _cpu(act_out), pad, alpha, scale, want_bias=want_bias)

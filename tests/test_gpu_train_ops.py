@@ -320,3 +320,72 @@ def test_modulated_conv_per_sample_filters(n, cin, cout, h, w):
             assert abs(float(a) - float(b)) < 5e-2 * (y_ref.numel() ** 0.5), (name, float(a), float(b))
             continue
         assert rel_l2(a, b) < 2e-2, (name, rel_l2(a, b), rel_err(a, b))
+
+
+def _unpack_mask(mask, shape):
+    """int32 words -> bool tensor of ``shape`` (bit i & 31 of word i >> 5 = element i)"""
+    bits = (mask.view(-1, 1) >> torch.arange(32, device=mask.device, dtype=torch.int32).view(1, 32)) & 1
+    return bits.reshape(shape).bool()
+
+
+@pytest.mark.parametrize("n,h,c,k,r,stride,pad,per_sample", [
+    (4, 64, 128, 128, 3, 1, 1, False),        # shared-window pair kernel (conv_tc5<128>)
+    (3, 40, 64, 64, 3, 1, 1, False),          # conv_tc5<64>, ragged 16 x 8 tiling
+    (6, 128, 32, 32, 3, 1, 1, False),         # conv_tc5<32> with the resident filter slice
+    (4, 65, 128, 256, 3, 2, 0, False),        # stride 2: conv_tc6<256>, two epilogue groups
+    (4, 33, 64, 128, 3, 2, 0, False),         # stride 2: conv_tc6<128>
+    (2, 6, 64, 96, 3, 1, 1, False),           # small map: one-tile kernel, 96 output channels
+    (5, 64, 32, 128, 1, 1, 0, False),         # 1x1 (FromRGB shape)
+    (2, 64, 128, 128, 3, 1, 1, True),         # per-sample filters (modulated convolution)
+])
+def test_activation_bit_mask_matches_output_sign(n, h, c, k, r, stride, pad, per_sample):
+    """sae_conv_epilogue.act_mask: every tensor-core conv that applies the leaky-ReLU also writes 1 bit per output element
+    (positive branch or not); sae_bias_act_backward / sae_fir_act_backward read it instead of the 4-byte output.  The mask must
+    equal ``out > 0`` everywhere, and the masked-gradient pass must give the same bytes either way."""
+    kern = backend.kernels()
+    if not kern.act_masks:
+        pytest.skip("activation bit masks switched off (SAE_ACT_MASK=0)")
+    g = backend.make_geom(n, h, h, c, k, r, r, stride, pad, pad)
+    x = rnd(1, n, h, h, c).float().to(DEV)
+    bias = (rnd(2, k) * 0.3).float().to(DEV)
+    noise = rnd(3, n * g.P * g.Q).float().to(DEV)
+    nw = torch.tensor([0.4], device=DEV)
+    if per_sample:
+        w = (rnd(4, n, k, r, r, c) / (c * r * r) ** 0.5).float().to(DEV)
+        y = kern.conv_fprop_per_sample(x, w, g, bias=bias, act=3, alpha=0.2, gain=1.4, noise=noise, noise_weight=nw)
+    else:
+        w = (rnd(4, k, r, r, c) / (c * r * r) ** 0.5).float().to(DEV)
+        y = kern.conv_fprop(x, w, g, bias=bias, act=3, alpha=0.2, gain=1.4, noise=noise, noise_weight=nw)
+    mask = backend.act_mask_of(y)
+    assert mask is not None and mask.numel() * 32 == y.numel()
+    assert torch.equal(_unpack_mask(mask, y.shape), y > 0)
+    dy = rnd(5, *y.shape).float().to(DEV)
+    a = kern.bias_act_backward(dy, y, 0.2, 1.4, want_bias=True, noise=noise, mask=mask)
+    b = kern.bias_act_backward(dy, y, 0.2, 1.4, want_bias=True, noise=noise)
+    assert torch.equal(a[0], b[0])
+    assert rel_err(a[1], b[1]) < 1e-5 and rel_err(a[2], b[2]) < 1e-5          # (atomics: summation order differs run to run)
+    # linear epilogue: no mask
+    assert backend.act_mask_of(kern.conv_fprop(x, w[0] if per_sample else w, g, bias=bias)) is None
+
+
+def test_activation_bit_mask_through_the_fir_kernels():
+    """sae_fir_bias_act writes the mask, sae_fir_act_backward reads it (the blur adjoint in front of a ResBlock's first activation)"""
+    from swapping_autoencoder_pytorch_b200.stylegan2_op.upfirdn2d import _flip_taps
+    kern = backend.kernels()
+    if not kern.act_masks:
+        pytest.skip("activation bit masks switched off (SAE_ACT_MASK=0)")
+    t = [1.0, 3.0, 3.0, 1.0]
+    taps = ([v / 8 for v in t], [v / 8 for v in t])
+    x = rnd(1, 3, 37, 41, 64).float().to(DEV)
+    bias = (rnd(2, 64) * 0.3).float().to(DEV)
+    noise = rnd(3, 3 * 36 * 40).float().to(DEV)
+    out = kern.fir_bias_act(x, taps, (1, 1, 1, 1), bias, noise, torch.tensor([0.5], device=DEV), 0.2, 1.4)
+    assert tuple(out.shape) == (3, 36, 40, 64)
+    mask = backend.act_mask_of(out)
+    assert mask is not None and torch.equal(_unpack_mask(mask, out.shape), out > 0)
+    # the blur adjoint of a gradient of the blurred shape lands on the activation's shape
+    g = rnd(4, 3, 36 + 3 - 2 - 2 + 0, 40 + 3 - 2 - 2 + 0, 64).float().to(DEV)       # [3, 35, 39, 64] -> pad (2, 2) -> 36 x 40
+    a = kern.fir_act_backward(g, _flip_taps(taps), out, (2, 2, 2, 2), 0.2, 1.4, want_bias=True, mask=mask)
+    b = kern.fir_act_backward(g, _flip_taps(taps), out, (2, 2, 2, 2), 0.2, 1.4, want_bias=True)
+    assert a is not None and b is not None
+    assert torch.equal(a[0], b[0]) and rel_err(a[1], b[1]) < 1e-5
