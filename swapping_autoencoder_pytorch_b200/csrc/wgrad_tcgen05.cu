@@ -183,10 +183,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                         if (p.shared_b) {
                             load5(sa + WG_OPER, &map_x, 0, q0 - p.pad_l, p0 - p.pad_t + tap0 / p.S, n0, c0 / 32 + rank * BSUB);
                         } else {
+                            // slot layout: tap-major, the tap's sub-tiles side by side (BSUB of them in pair mode, cpt otherwise:
+                            // narrow layers pack 4 / cpt taps into one accumulator) — one box per tap covers them
+                            const int xs = CG == 2 ? BSUB : p.cpt;
                             for (int q = 0; q < ntap; ++q) {
                                 const int tap = tap0 + q;
                                 const int r = tap / p.S, sx = tap - r * p.S;
-                                load5(sa + WG_OPER + (uint32_t)(q * BSUB) * WG_SUB, &map_x, 0, q0 * p.stride - p.pad_l + sx,
+                                load5(sa + WG_OPER + (uint32_t)(q * xs) * WG_SUB, &map_x, 0, q0 * p.stride - p.pad_l + sx,
                                       p0 * p.stride - p.pad_t + r, n0, c0 / 32 + rank * BSUB);
                             }
                         }
@@ -590,11 +593,11 @@ static int tc_wgrad_impl(const float* dy, const float* x, float* dw, const sae_c
         int rc = encode_map(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
     }
-    // 5-D views (32 channels, W, H, N, channel block) — see the producer; whole 128-channel operand tiles only (cpt == 4).  The
+    // 5-D views (32 channels, W, H, N, channel block) — see the producer.  The
     // channel-block dimension has the SMALLEST stride (128 bytes); should a driver refuse such a view, the 4-D maps above stay.
     static int five_d = -1;
     if (five_d < 0) { const char* v = getenv("SAE_WGRAD_5D"); five_d = (v && v[0] == '0') ? 0 : 1; }
-    if (five_d && p.cpt == 4 && g->C % 32 == 0 && g->K % 32 == 0) {
+    if (five_d && g->C % 32 == 0 && g->K % 32 == 0) {
         CUtensorMap m5dy, m5x;
         cuuint64_t ddims[5] = {32, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N, (cuuint64_t)(g->K / 32)};
         cuuint64_t dstr[4] = {(cuuint64_t)g->K * 4, (cuuint64_t)g->Q * g->K * 4, (cuuint64_t)g->P * g->Q * g->K * 4, 128};
@@ -602,7 +605,7 @@ static int tc_wgrad_impl(const float* dy, const float* x, float* dw, const sae_c
         cuuint32_t des[5] = {1, 1, 1, 1, 1};
         cuuint64_t xdims[5] = {32, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N, (cuuint64_t)(g->C / 32)};
         cuuint64_t xstr[4] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4, 128};
-        cuuint32_t xbox[5] = {32, (cuuint32_t)(p.tw * g->stride), (cuuint32_t)(p.th * g->stride), (cuuint32_t)p.tn, pair ? 2u : 4u};
+        cuuint32_t xbox[5] = {32, (cuuint32_t)(p.tw * g->stride), (cuuint32_t)(p.th * g->stride), (cuuint32_t)p.tn, pair ? 2u : (cuuint32_t)p.cpt};
         if (p.shared_b) xbox[1] = WG_WIN;
         cuuint32_t xes[5] = {1, (cuuint32_t)g->stride, (cuuint32_t)g->stride, 1, 1};
         if (encode_map(&m5dy, dy, 5, ddims, dstr, dbox, des, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) == SAE_OK &&

@@ -319,6 +319,34 @@ def _pad4(input, weight):
     return input, weight, None
 
 
+_PAD32_MIN = 40          # narrower layers stay as they are (their cost is bandwidth, not the tensor-core path)
+
+
+def _round32(c):
+    return c if (c % 32 == 0 or c < _PAD32_MIN) else c + 32 - c % 32
+
+
+def _pad32(input, weight, transposed=False):
+    """Wide layers whose channel counts are not multiples of 32 — the ffhq1024 option set's generator runs 409 / 204 / 102
+    channels (netG_scale_capacity 0.8, experiments/ffhq1024_pretrained_launcher.py:23-27) — are zero-padded to the next
+    multiple so that they run on the tcgen05 kernels (whose TMA rows are 32 channels) instead of the shape-complete mma.sync
+    kernel: input through the channel-pad kernel, filter through a memoised F.pad, output through a channel slice; all three
+    are differentiable, so gradients come back in the original shapes.  Returns (input, weight, Cout to slice back to or None).
+    weight is [Cout, Cin, R, S], or [Cin, Cout, R, S] when ``transposed``."""
+    ci_axis, co_axis = (0, 1) if transposed else (1, 0)
+    cin, cout = weight.shape[ci_axis], weight.shape[co_axis]
+    cin_p, cout_p = _round32(cin), _round32(cout)
+    if cin_p == cin and cout_p == cout:
+        return input, weight, None
+    if cin_p != cin:
+        input = _PadChannels.apply(input, cin_p)
+    pads = [0, 0, 0, 0, 0, 0, 0, 0]                  # F.pad lists the last dimension first: (S, R, dim 1, dim 0)
+    pads[5 if ci_axis == 1 else 7] = cin_p - cin
+    pads[5 if co_axis == 1 else 7] = cout_p - cout
+    weight = memo(weight, ("pad32", transposed), lambda w=weight: F.pad(w, tuple(pads)))
+    return input, weight, (cout if cout_p != cout else None)
+
+
 def _geom_for(input, weight, stride, padding):
     n, c, h, w_ = input.shape
     k, c2, r, s = weight.shape
@@ -332,6 +360,8 @@ def _geom_for(input, weight, stride, padding):
 def conv2d_bias_act(input, weight, bias, stride=1, padding=0, negative_slope=0.2, scale=2 ** 0.5, wscale=1.0):
     """fused_leaky_relu(F.conv2d(input, weight * wscale, stride=stride, padding=padding), bias) in one kernel"""
     input, weight, cout = _pad4(input, weight)
+    if cout is None:
+        input, weight, cout = _pad32(input, weight)
     if cout is not None:
         bias = F.pad(bias, (0, weight.shape[0] - cout))
     g = _geom_for(input, weight, stride, padding)
@@ -343,21 +373,31 @@ def conv2d_bias_act(input, weight, bias, stride=1, padding=0, negative_slope=0.2
 def conv2d_noise_bias_act(input, weight, noise, noise_weight, bias, padding=0, negative_slope=0.2, scale=2 ** 0.5,
                           wscale=1.0):
     """fused_leaky_relu(F.conv2d(input, weight * wscale, padding=padding) + noise_weight * noise, bias) in one kernel"""
+    input, weight, cout = _pad32(input, weight)
+    if cout is not None:
+        bias = F.pad(bias, (0, weight.shape[0] - cout))
     g = _geom_for(input, weight, 1, padding)
     w, wt = prep_filter(weight, wscale)
-    return _ConvNoiseBiasAct.apply(input, w, wt, noise, noise_weight, bias, g, negative_slope, scale)
+    out = _ConvNoiseBiasAct.apply(input, w, wt, noise, noise_weight, bias, g, negative_slope, scale)
+    return out if cout is None else out[:, :cout]
 
 
 def conv2d_residual(input, weight, residual, scale, stride=1, padding=0, wscale=1.0):
     """(F.conv2d(input, weight * wscale, stride=stride, padding=padding) + residual) * scale in one kernel"""
+    input, weight, cout = _pad32(input, weight)
+    if cout is not None:
+        residual = _PadChannels.apply(residual, weight.shape[0])
     g = _geom_for(input, weight, stride, padding)
     w, wt = prep_filter(weight, wscale)
-    return _ConvResidual.apply(input, w, wt, residual, g, scale)
+    out = _ConvResidual.apply(input, w, wt, residual, g, scale)
+    return out if cout is None else out[:, :cout]
 
 
 def conv2d(input, weight, bias=None, stride=1, padding=0, wscale=1.0):
     """``F.conv2d(input, weight * wscale, bias, stride, padding)`` for NCHW-shaped input, [Cout,Cin,R,S] weight."""
     input, weight, cout = _pad4(input, weight)
+    if cout is None:
+        input, weight, cout = _pad32(input, weight)
     g = _geom_for(input, weight, stride, padding)
     w, wt = prep_filter(weight, wscale)
     out = _ConvFprop.apply(input, w, wt, g)
@@ -371,14 +411,16 @@ def conv2d(input, weight, bias=None, stride=1, padding=0, wscale=1.0):
 def conv_transpose2d(input, weight, stride=2, padding=0, wscale=1.0):
     """``F.conv_transpose2d(input, weight[Cin,Cout,R,S], stride, padding)`` — computed as the data-gradient of
     the strided convolution whose filter is ``weight`` read as [K=Cin, C=Cout, R, S]."""
+    assert input.shape[1] == weight.shape[0]
+    input, weight, cout_orig = _pad32(input, weight, transposed=True)
     n, cin, h, w_ = input.shape
     cin2, cout, r, s = weight.shape
-    assert cin == cin2
     oh = (h - 1) * stride - 2 * padding + r
     ow = (w_ - 1) * stride - 2 * padding + s
     g = make_geom(n, oh, ow, cout, cin, r, s, stride, padding, padding, P=h, Q=w_)
     w, wt = prep_filter(weight, wscale)
-    return _ConvDgrad.apply(input, w, wt, g)
+    out = _ConvDgrad.apply(input, w, wt, g)
+    return out if cout_orig is None else out[:, :cout_orig]
 
 
 def linear(input, weight, bias=None, wscale=1.0):

@@ -81,6 +81,37 @@ def test_conv_family_gradcheck():
     assert torch.autograd.gradcheck(linear, (xl, wl), atol=1e-7)
 
 
+def test_wide_layers_with_odd_channel_counts_are_padded_to_multiples_of_32():
+    """conv.py _pad32 (the ffhq1024 option set's 409 / 204 / 102-channel generator): every public conv entry point pads input,
+    filter, bias and residual channels to the next multiple of 32 and slices the result — values and gradients must be those of
+    the unpadded convolution"""
+    import torch.nn.functional as F
+    from swapping_autoencoder_pytorch_b200.stylegan2_op import conv as C
+    x = rnd(1, 2, 41, 6, 5).requires_grad_()
+    w = (rnd(2, 51, 41, 3, 3) / 19).requires_grad_()
+    b = rnd(3, 51).requires_grad_()
+    res = rnd(4, 2, 51, 6, 5).requires_grad_()
+    noise, nw = rnd(5, 2, 1, 6, 5), torch.tensor([0.3], dtype=torch.float64, requires_grad=True)
+    wt = (rnd(6, 41, 51, 3, 3) / 19).requires_grad_()
+    lrelu = lambda t: F.leaky_relu(t, 0.2) * 2 ** 0.5
+    cases = [
+        (lambda: C.conv2d(x, w, b, padding=1), lambda: F.conv2d(x, w, b, padding=1), (x, w, b)),
+        (lambda: C.conv2d_bias_act(x, w, b, stride=2, padding=0), lambda: lrelu(F.conv2d(x, w, b, stride=2)), (x, w, b)),
+        (lambda: C.conv2d_noise_bias_act(x, w, noise, nw, b, padding=1),
+         lambda: lrelu(F.conv2d(x, w, padding=1) + nw * noise + b.view(1, -1, 1, 1)), (x, w, b, nw)),
+        (lambda: C.conv2d_residual(x, w, res, 0.7, padding=1), lambda: (F.conv2d(x, w, padding=1) + res) * 0.7, (x, w, res)),
+        (lambda: C.conv_transpose2d(x, wt, stride=2), lambda: F.conv_transpose2d(x, wt, stride=2), (x, wt)),
+    ]
+    for ours, ref, ins in cases:
+        y, yr = ours(), ref()
+        assert y.shape == yr.shape and rel_err(y, yr) < TOL
+        u = rnd(9, *yr.shape)
+        for a, r_ in zip(torch.autograd.grad((y * u).sum(), ins), torch.autograd.grad((yr * u).sum(), ins)):
+            assert rel_err(a, r_) < TOL
+    # narrow layers are left alone
+    assert C._round32(3) == 3 and C._round32(25) == 25 and C._round32(409) == 416 and C._round32(64) == 64
+
+
 def test_layers_against_reference():
     from swapping_autoencoder_pytorch_b200 import stylegan2_layers as L
     meta, G = load_golden("layers")
