@@ -61,6 +61,10 @@ class EmulatedKernels:
         return t * scale
 
     def bias_act_backward(self, grad_out, out, alpha, scale, want_bias=True, noise=None, mask=None):
+        if mask is not None:
+            assert mask.dtype == torch.bool and mask.shape == out.shape and torch.equal(mask, out > 0), \
+                "activation mask handed to the backward of a different tensor"
+            self.mask_uses = getattr(self, "mask_uses", 0) + 1
         gi = torch.where(out > 0, grad_out, grad_out * alpha) * scale
         c = out.shape[-1]
         gb = gi.reshape(-1, c).sum(0) if want_bias else None
@@ -72,7 +76,7 @@ class EmulatedKernels:
     def fir_act_backward(self, grad, taps, act_out, pad, alpha, scale, want_bias=True, mask=None):
         kernel = torch.outer(torch.tensor(taps[0]), torch.tensor(taps[1])).to(grad.dtype)
         d = self.upfirdn2d(grad, kernel, 1, 1, 1, 1, *pad)
-        gi, gb, _ = self.bias_act_backward(d, act_out, alpha, scale, want_bias=want_bias)
+        gi, gb, _ = self.bias_act_backward(d, act_out, alpha, scale, want_bias=want_bias, mask=mask)
         return gi, gb
 
     def modulate(self, x, s):
@@ -124,11 +128,16 @@ class EmulatedKernels:
             y = y + bias
         if noise is not None:
             y = y + noise_weight * noise.reshape(*y.shape[:-1], 1)
+        pos = (y > 0) if act == 3 else None
         if act == 3:
             y = torch.where(y > 0, y, y * alpha)
         y = y * gain
         if residual is not None:
             y = (y + residual) * res_scale
+        if pos is not None:
+            # stand-in for the activation bit mask of the CUDA kernels (sae_conv_epilogue.act_mask): the callers must hand exactly
+            # this object back to the activation backward of exactly this tensor — bias_act_backward checks it
+            y._sae_act_mask = pos
         return y
 
     def conv_fprop(self, x, w_krsc, g, impl=None, prepared=False, **epi):
@@ -217,7 +226,9 @@ class EmulatedKernels:
         kernel = torch.outer(torch.tensor(taps[0]), torch.tensor(taps[1])).to(x.dtype)
         px0, px1, py0, py1 = pad
         y = self.upfirdn2d(x, kernel, 1, 1, 1, 1, px0, px1, py0, py1)
-        return self.bias_act(y, bias, None, 3, 0, alpha, scale, noise=noise, noise_weight=noise_weight)
+        out = self.bias_act(y, bias, None, 3, 0, alpha, scale, noise=noise, noise_weight=noise_weight)
+        out._sae_act_mask = out > 0
+        return out
 
     # ------------------------------------------------ style-modulated conv, per-sample filters (include/sae_b200.h)
     def conv_modulated_ok(self, g):
@@ -237,7 +248,10 @@ class EmulatedKernels:
             if e.get("residual") is not None:
                 e["residual"] = e["residual"][n:n + 1]
             outs.append(self.conv_fprop(x[n:n + 1], w_nkrsc[n], g1, **e))
-        return torch.cat(outs)
+        y = torch.cat(outs)
+        if all(hasattr(o, "_sae_act_mask") for o in outs):
+            y._sae_act_mask = torch.cat([o._sae_act_mask for o in outs])
+        return y
 
     def conv_dgrad_per_sample(self, dy, w_ncrsk, g, **epi):
         g1 = type(g)(1, *g.key()[1:])

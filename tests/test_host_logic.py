@@ -223,6 +223,10 @@ def test_train_steps_run_and_alternate(fp64_default):
     assert "G_L1" in g and "G_GAN_mix" in g and "L1_dist" in g
     changed2 = {k for k, v in model.state_dict().items() if not torch.equal(v, before[k])}
     assert any(k.startswith("G.") for k in changed2) and any(k.startswith("E.") for k in changed2)
+    # activation masks: the emulation attaches a stand-in mask to every activation output and its bias_act_backward asserts that a
+    # mask it is given belongs to the tensor it is given — so the D, R1 and G steps above also checked the mask plumbing of
+    # conv.py / blocks.py (first and second order); make sure that plumbing was actually exercised
+    assert getattr(backend.kernels(), "mask_uses", 0) > 20
 
 
 def test_filter_memo_shares_derived_filters(fp64_default):
