@@ -7,10 +7,13 @@
 // dimension, the reduction runs over pixels), which tcgen05 supports for tf32 through the transposed
 // (a_major = b_major = MN) shared-memory descriptors — so the NHWC activations are consumed as they are, no
 // transposes materialised:
-//   * A stage  = dy box of 32 pixels x 128 channels  = 4 TMA boxes (32 ch x 32 px, SWIZZLE_128B_ATOM_32B — the only
-//     layout tcgen05 accepts for MN-major 32-bit operands)
-//   * B stages = for each of the (up to 3) taps of this CTA's tap group, the x box shifted by the tap, 4 TMA boxes;
+//   * A stage  = dy box of 32 pixels x 128 channels  = four 32-channel sub-tiles of 32 ch x 32 px (SWIZZLE_128B_ATOM_32B — the
+//     only layout tcgen05 accepts for MN-major 32-bit operands), fetched by ONE TMA instruction through a 5-D tensor map
+//     whose outermost dimension walks the sub-tiles (the single producer thread is issue-bound otherwise, see the kernel)
+//   * B stages = for each of the (up to 3) taps of this CTA's tap group, the x box shifted by the tap (one instruction each);
 //     out-of-bounds pixels are zero-filled by TMA (= the conv padding), element stride = conv stride
+//   * layers with 256 out channels per tile pair run as CTA pairs (cta_group::2, wgrad_tc_kernel<2>): half of every x tile
+//     per CTA, a 5-deep ring
 //   * one TMEM accumulator (128 x 128 fp32 = 128 columns) per tap; the dy tile is reused by all taps of the group
 //   * grid = (M tiles x N tiles, tap groups, pixel splits); partial sums are reduced with vectorised fp32 atomics
 //     (red.global.add.v4.f32) straight from the TMEM read — dW must be zero-initialised by the caller.
