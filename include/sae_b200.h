@@ -101,8 +101,9 @@ int sae_bias_act_backward(const float* grad_out, const float* out, float* grad_i
  * reference upfirdn2d.py:24-60 (UpFirDn2dBackward) + fused_act.py:23-41 (FusedLeakyReLUFunctionBackward) back to back;
  * the blurred gradient never travels through HBM.  grad: [major, in_h, in_w, minor]; act_out / grad_in:
  * [major, out_h, out_w, minor] with out = in + pad0 + pad1 - k + 1.  taps are HOST arrays, unflipped, 3 or 4 of them.
- * grad_bias (may be NULL) is accumulated into.  Returns SAE_E_UNSUPPORTED outside the TMA-tiled configuration
- * (minor % 32 == 0, outputs >= 8 x 8): issue the two separate calls then. */
+ * grad_bias (may be NULL) is accumulated into.  act_mask (may be NULL): the activation bit mask of act_out (see
+ * sae_conv_epilogue.act_mask), read instead of act_out, which may then be NULL.  Returns SAE_E_UNSUPPORTED outside the
+ * TMA-tiled configuration (minor % 32 == 0, outputs >= 8 x 8): issue the two separate calls then. */
 int sae_fir_act_backward(const float* grad, const float* taps_y, const float* taps_x, const float* act_out,
                          float* grad_in, float* grad_bias, int64_t major, int in_h, int in_w, int minor,
                          int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
@@ -114,7 +115,8 @@ int sae_fir_act_backward(const float* grad, const float* taps_y, const float* ta
  * (stylegan2_layers.py:306-309 self.blur(out), then :398-405 noise -> FusedLeakyReLU; fused_act.py:89-96):
  * the blurred activation never travels through HBM.  x: [major, in_h, in_w, minor]; out: [major, out_h, out_w, minor];
  * noise: one value per OUTPUT pixel ([major, out_h, out_w]) or NULL; bias: [minor] or NULL.  taps are HOST arrays,
- * unflipped.  Returns SAE_E_UNSUPPORTED outside the TMA-tiled configuration (minor % 32 == 0, outputs >= 8 x 8). */
+ * unflipped.  act_mask (may be NULL): receives the activation bit mask of out, [major * out_h * out_w * minor / 32] words.
+ * Returns SAE_E_UNSUPPORTED outside the TMA-tiled configuration (minor % 32 == 0, outputs >= 8 x 8). */
 int sae_fir_bias_act(const float* x, const float* taps_y, const float* taps_x, const float* bias, const float* noise,
                      const float* noise_weight, float* out, int64_t major, int in_h, int in_w, int minor,
                      int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
